@@ -1,0 +1,97 @@
+/*
+ * mc_oracle.h — C entry points of the CPU ORACLE (test infrastructure, NOT product).
+ *
+ * The oracle is a dependency-free C++17 restatement of the reference algorithm for
+ * the hot path (FieldProblem::solve and everything it calls).  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load it.  The product library (libmcb.so) never links or calls it.
+ *
+ * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures
+ *  and cannot be built here (needs Eigen 3 + Boost), so
+ * this restatement is anchored on the reference's own formulas through known-answer
+ * tests authored in tests/ (SURVEY.md §8c KA1-KA6), not on outputs of the reference.
+ *
+ * Descriptors are the structs of include/mcb.h so the same tables can be handed to
+ * the CUDA library.
+ */
+#ifndef MC_ORACLE_H_
+#define MC_ORACLE_H_
+
+#include <stdint.h>
+#include "../include/mcb.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct orc_material orc_material;
+typedef struct orc_domain   orc_domain;
+typedef struct orc_problem  orc_problem;
+
+#define ORC_RNG_MT19937 0   /* reference-faithful stream consumption, one engine per thread */
+#define ORC_RNG_PHILOX  1   /* counter-based, keyed by (seed, particle id): the GPU's stream */
+
+const char* orc_last_error(void);
+
+/* Material::Material(disp, relax, temp)  material.cpp:82-162 */
+orc_material* orc_material_load(const char* disp_path, const char* relax_path, double temp);
+void   orc_material_free(orc_material*);
+int    orc_material_desc(const orc_material*, mcb_material_desc* out); /* pointers into the oracle */
+double orc_material_cond(const orc_material*);                         /* Material::cond() */
+int    orc_material_alias(const orc_material*, int which, double* wprob, int32_t* walias,
+                          double* pprob, int32_t* palias);
+
+/* Shipped domains (domain.cpp): kind in {"bulk","film","jct","tee","tube"}; dim/div are the
+ * constructor vectors (NOT the CLI shorthand).  */
+orc_domain* orc_domain_create(const char* kind, const double* dim, int ndim,
+                              const int64_t* div, int ndiv, double dT);
+/* One Parallelepiped<...> with arbitrary boundary kinds (MCB_BDRY_*), wall temperatures
+ * T[6] and volumetric gradT (subdomain.h:145-158); Peri faces are paired 0<->3, 1<->4,
+ * 2<->5 by pure translation (as BulkDomain::init does, domain.cpp:137-141). */
+orc_domain* orc_domain_box(const double origin[3], const double mat[9], const int64_t div[3],
+                           const double grad_t[3], const int32_t kinds[6], const double T[6]);
+void   orc_domain_free(orc_domain*);
+int    orc_domain_desc(const orc_domain*, mcb_domain_desc* out);
+int64_t orc_domain_cols(const orc_domain*);
+/* cell volumes per column: Field(1, dom, CellVolF())  problem.cpp:302-306,441-442 */
+int    orc_domain_cell_vol(const orc_domain*, double* vol);
+
+/* FieldProblem subclasses  problem.cpp:315-342, 451-648 */
+orc_problem* orc_problem_create(const orc_material*, const orc_domain*, int kind,
+                                int64_t nemit, int64_t size, int64_t maxscat, int64_t maxloop);
+void   orc_problem_free(orc_problem*);
+int    orc_problem_desc(const orc_problem*, mcb_problem_desc* out);
+
+/* FieldProblem::solve for n in [n_begin,n_end) inside an OpenMP parallel region of
+ * `nthreads` threads + the critical-section sum of main.cpp:151-166.  out_field rows x cols. */
+int    orc_solve(const orc_problem*, int rng_mode, uint64_t seed,
+                 int64_t n_begin, int64_t n_end, int nthreads,
+                 double* out_field, mcb_stats* stats);
+/* The raw tally (before postProc / volume / power). */
+int    orc_solve_raw(const orc_problem*, int rng_mode, uint64_t seed,
+                     int64_t n_begin, int64_t n_end, int nthreads,
+                     double* raw_field, mcb_stats* stats);
+/* problem.cpp:439-444 on a raw tally, in place */
+int    orc_finalize(const orc_problem*, double* field);
+
+/* Philox mode: state of particles [n_begin,n_end) after emission + nsteps loop trips. */
+int    orc_trace(const orc_problem*, uint64_t seed, int64_t n_begin, int64_t n_end,
+                 int64_t nsteps, mcb_trace_out* out);
+
+int    orc_cell_index(const orc_domain*, int64_t n, const double* pos, const int32_t* sdom,
+                      int64_t* index);
+int    orc_accumulate(const orc_domain*, int32_t rows, int64_t n, const int32_t* sdom,
+                      const double* bpos, const double* epos, const double* amount,
+                      double* field);
+void   orc_philox_words(uint64_t seed, uint64_t particle, uint32_t event, uint32_t block,
+                        uint32_t out[4]);
+/* first `n` doubles of uniform_01 / uniform(-1,1) / uniform_int(0,m-1) from mt19937(seed),
+ * to pin the Boost-equivalent distributions in tests. which: 0,1,2 */
+void   orc_mt_draws(uint32_t seed, int which, int64_t m, int64_t n, double* out);
+
+int    orc_max_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
