@@ -1,0 +1,645 @@
+// mcb_api.cu — host side of the C ABI declared in include/mcb.h.
+//
+// Flattens the POD descriptors into device tables, drives the slot schedule (emit/refill + step
+// launches, tail compaction), finalises the field.  No CPU fallback: every entry point needs a
+// working sm_100 device.  Reference citations: file:line relative to /root/reference/montecarlo/.
+#include "mcb_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace mcb;
+
+namespace {
+
+thread_local std::string g_create_err;
+
+#define CUDA_TRY(ctx, expr)                                                                   \
+    do {                                                                                      \
+        cudaError_t e_ = (expr);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(e_);                  \
+            return MCB_ECUDA;                                                                 \
+        }                                                                                     \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr; size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        if (count <= n && p) return cudaSuccess;
+        release();
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e == cudaSuccess) n = count; else p = nullptr;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+// boost::random::discrete_distribution<long,double>: Walker alias table (random.h:26), as used by
+// Material::Dist (material.cpp:51-75).  Published algorithm (Boost.Random 1.5x, discrete_distribution.hpp).
+void build_alias(const double* w, size_t n, double* prob, int32_t* alias) {
+    std::vector<std::pair<double, int32_t>> below, above;
+    double sum = 0.0;
+    for (size_t i = 0; i < n; ++i) sum += w[i];
+    const double avg = sum / (double)n;
+    for (size_t i = 0; i < n; ++i) {
+        const double v = w[i] / avg;
+        if (v < 1.0) below.emplace_back(v, (int32_t)i); else above.emplace_back(v, (int32_t)i);
+    }
+    for (size_t i = 0; i < n; ++i) { prob[i] = 0.0; alias[i] = 0; }
+    size_t b = 0, a = 0;
+    while (b < below.size() && a < above.size()) {
+        prob[below[b].second] = below[b].first; alias[below[b].second] = above[a].second;
+        above[a].first -= (1.0 - below[b].first);
+        if (above[a].first < 1.0) { below[b] = above[a]; ++a; } else { ++b; }
+    }
+    for (; b < below.size(); ++b) prob[below[b].second] = 1.0;
+    for (; a < above.size(); ++a) prob[above[a].second] = 1.0;
+}
+
+struct AliasTables {            // entry (w,p) at [w*np + p]
+    std::vector<double> wprob, pprob; std::vector<int32_t> walias, palias;
+    void build(const double* pdf, long nw, long np) {     // pdf(w,p) at [w + nw*p] (column-major)
+        wprob.resize(nw); walias.resize(nw); pprob.resize(nw * np); palias.resize(nw * np);
+        std::vector<double> rowsum(nw), row(np);
+        for (long w = 0; w < nw; ++w) { double s = 0.0; for (long p = 0; p < np; ++p) s += pdf[w + nw * p]; rowsum[w] = s; }
+        build_alias(rowsum.data(), nw, wprob.data(), walias.data());
+        for (long w = 0; w < nw; ++w) {
+            for (long p = 0; p < np; ++p) row[p] = pdf[w + nw * p];
+            build_alias(row.data(), np, &pprob[w * np], &palias[w * np]);
+        }
+    }
+};
+
+inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
+
+} // namespace
+
+struct mcb_ctx {
+    int device = 0; int sm_count = 148; size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    std::string err;
+    mcb_options opt{};
+    // material
+    bool has_mat = false; long nw = 0, np = 0; double energy_sum = 0, flux_sum = 0;
+    MaterialView mv{}; DevBuf<unsigned char> mat_blob;
+    AliasTables flux_alias, scat_alias;
+    DevBuf<double> f_wprob, f_pprob; DevBuf<int32_t> f_walias, f_palias;
+    // geometry
+    bool has_dom = false; GeometryView gv{}; DevBuf<unsigned char> geo_blob;
+    std::vector<DSdom> h_sdom; int nemitter = 0;
+    DevBuf<DEmitter> emitters; DevBuf<double> cell_vol; long long cols = 0;
+    // problem / run state
+    DevBuf<long long> emit_cdf;
+    DevBuf<double> state[2]; DevBuf<unsigned long long> imeta[2]; long long slots_alloc = 0;
+    DevBuf<Counters> ctr; Counters* h_ctr = nullptr;     // pinned mirror
+    DevBuf<double> field;
+};
+
+namespace {
+
+StateSoA soa_of(mcb_ctx* c, int which, long long n) {
+    StateSoA s;
+    double* d = c->state[which].p;
+    s.px = d; s.py = d + n; s.pz = d + 2 * n; s.dx = d + 3 * n; s.dy = d + 4 * n; s.dz = d + 5 * n; s.sn = d + 6 * n;
+    s.meta = c->imeta[which].p; s.pidstep = c->imeta[which].p + n;
+    return s;
+}
+
+int check_problem(mcb_ctx* c, const mcb_problem_desc* p) {
+    if (!p) { c->err = "null problem"; return MCB_EINVAL; }
+    if (!c->has_mat || !c->has_dom) { c->err = "upload material and domain before solving"; return MCB_ESTATE; }
+    int rows;
+    switch (p->kind) {
+    case MCB_PROB_TEMP: rows = 1; break;
+    case MCB_PROB_FLUX: rows = 3; break;
+    case MCB_PROB_MULTI: rows = 4; break;
+    case MCB_PROB_CUMTEMP: rows = (int)p->size + 1; break;
+    case MCB_PROB_CUMFLUX: rows = 3 * ((int)p->size + 1); break;
+    default: c->err = "Invalid problem"; return MCB_EINVAL;
+    }
+    if (p->rows != rows) { c->err = "problem rows inconsistent with kind/size"; return MCB_EINVAL; }
+    if ((p->kind == MCB_PROB_CUMTEMP || p->kind == MCB_PROB_CUMFLUX) && (p->size <= 0 || p->step <= 0)) {
+        c->err = "Cum* problems need size > 0 and step > 0"; return MCB_EINVAL;
+    }
+    if (!p->emit_count) { c->err = "null emit_count"; return MCB_EINVAL; }
+    long long tot = 0;
+    for (int i = 0; i < c->nemitter; ++i) { if (p->emit_count[i] < 0) { c->err = "negative emit_count"; return MCB_EINVAL; } tot += p->emit_count[i]; }
+    if (tot != p->nemit) { c->err = "nemit != sum(emit_count)"; return MCB_EINVAL; }
+    if (p->maxloop < 0 || p->maxloop > MCB_MAX_LOOP) { c->err = "maxloop out of range (< 2^24)"; return MCB_EINVAL; }
+    if (p->maxscat < 0 || p->maxscat > 0x7FFFFFFFll) { c->err = "maxscat out of range"; return MCB_EINVAL; }
+    if ((unsigned long long)p->nemit > MCB_MAX_PID) { c->err = "nemit out of range (< 2^40)"; return MCB_EINVAL; }
+    return MCB_OK;
+}
+
+template <int KIND>
+cudaError_t launch_step_kind(const StepParams& P, bool smem_tally, int grid, int block, size_t smem, cudaStream_t s) {
+    if (smem_tally) {
+        cudaError_t e = cudaFuncSetAttribute(k_step<KIND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k_step<KIND, true><<<grid, block, smem, s>>>(P);
+    } else {
+        cudaError_t e = cudaFuncSetAttribute(k_step<KIND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k_step<KIND, false><<<grid, block, smem, s>>>(P);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_step(const StepParams& P, bool smem_tally, int grid, int block, size_t smem, cudaStream_t s) {
+    switch (P.kind) {
+    case MCB_PROB_TEMP: return launch_step_kind<MCB_PROB_TEMP>(P, smem_tally, grid, block, smem, s);
+    case MCB_PROB_FLUX: return launch_step_kind<MCB_PROB_FLUX>(P, smem_tally, grid, block, smem, s);
+    case MCB_PROB_MULTI: return launch_step_kind<MCB_PROB_MULTI>(P, smem_tally, grid, block, smem, s);
+    case MCB_PROB_CUMTEMP: return launch_step_kind<MCB_PROB_CUMTEMP>(P, smem_tally, grid, block, smem, s);
+    default: return launch_step_kind<MCB_PROB_CUMFLUX>(P, smem_tally, grid, block, smem, s);
+    }
+}
+
+int ensure_slots(mcb_ctx* c, long long slots) {
+    if (slots <= c->slots_alloc) return MCB_OK;
+    for (int w = 0; w < 2; ++w) {
+        CUDA_TRY(c, c->state[w].alloc((size_t)slots * 7));
+        CUDA_TRY(c, c->imeta[w].alloc((size_t)slots * 2));
+    }
+    c->slots_alloc = slots;
+    return MCB_OK;
+}
+
+struct RunPlan { long long slots; int S, block, grid; bool smem_tally; size_t smem; };
+
+int plan_run(mcb_ctx* c, const mcb_problem_desc* prob, long long nparticles, RunPlan* r) {
+    const mcb_options& o = c->opt;
+    r->block = o.block > 0 ? o.block : 512;
+    if (r->block % 32 != 0 || r->block > 512) { c->err = "block must be a multiple of 32, <= 512"; return MCB_EINVAL; }
+    const int per_sm = o.ctas_per_sm > 0 ? o.ctas_per_sm : 1;
+    r->S = o.steps_per_launch > 0 ? o.steps_per_launch : 16;
+    long long slots = o.slots > 0 ? o.slots : (long long)c->sm_count * r->block * 32;   // ~2.4 M resident phonons
+    slots = std::min(slots, std::max<long long>(nparticles, 1));
+    r->slots = slots;
+    const long long tiles = (slots + r->block - 1) / r->block;
+    r->grid = (int)std::min<long long>((long long)c->sm_count * per_sm, std::max<long long>(tiles, 1));
+    const size_t base = 16 + (size_t)c->mv.bytes + (size_t)c->gv.bytes;
+    const size_t hist = (size_t)prob->rows * (size_t)c->cols * sizeof(double);
+    const size_t budget = c->smem_optin / (size_t)per_sm > 1024 ? c->smem_optin / (size_t)per_sm - 1024 : 0;
+    bool smem_tally = (o.tally_mode == 1) || (o.tally_mode == 0 && base + hist <= budget && hist <= 96 * 1024);
+    if (o.tally_mode == 2) smem_tally = false;
+    if (smem_tally && base + hist > c->smem_optin) { c->err = "tally_mode=1 but the field does not fit in shared memory"; return MCB_ELIMIT; }
+    r->smem_tally = smem_tally;
+    r->smem = base + (smem_tally ? hist : 0);
+    if (r->smem > c->smem_optin) { c->err = "material + geometry tables exceed the shared-memory staging area"; return MCB_ELIMIT; }
+    return MCB_OK;
+}
+
+void fill_params(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, StepParams* P) {
+    std::memset(P, 0, sizeof *P);
+    P->mat_blob = c->mat_blob.p; P->mv = c->mv; P->geo_blob = c->geo_blob.p; P->gv = c->gv;
+    P->emitters = c->emitters.p; P->emit_cdf = c->emit_cdf.p; P->nemitter = c->nemitter;
+    P->f_wprob = c->f_wprob.p; P->f_pprob = c->f_pprob.p; P->f_walias = c->f_walias.p; P->f_palias = c->f_palias.p;
+    P->kind = prob->kind; P->rows = prob->rows; P->cum_step = prob->step > 0 ? prob->step : 1;
+    P->maxscat = prob->maxscat; P->maxloop = prob->maxloop; P->seed = seed;
+    P->ctr = c->ctr.p; P->field_len = (long long)prob->rows * c->cols;
+}
+
+int upload_cdf(mcb_ctx* c, const mcb_problem_desc* prob) {
+    std::vector<long long> cdf(c->nemitter);
+    long long acc = 0;
+    for (int i = 0; i < c->nemitter; ++i) { acc += prob->emit_count[i]; cdf[i] = acc; }     // problem.cpp:374-378
+    CUDA_TRY(c, c->emit_cdf.alloc(cdf.size()));
+    CUDA_TRY(c, cudaMemcpyAsync(c->emit_cdf.p, cdf.data(), cdf.size() * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return MCB_OK;
+}
+
+// The schedule: launches of k_step over the resident slots until every particle of
+// [n_begin, n_end) has been emitted and has terminated; the tail is compacted.
+int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n_begin, int64_t n_end,
+              double* raw_field_dev, mcb_stats* stats) {
+    int rc = check_problem(c, prob);
+    if (rc) return rc;
+    if (n_begin < 0 || n_end > prob->nemit || n_begin > n_end) { c->err = "bad particle range"; return MCB_EINVAL; }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    RunPlan plan;
+    rc = plan_run(c, prob, n_end - n_begin, &plan);
+    if (rc) return rc;
+    rc = ensure_slots(c, plan.slots);
+    if (rc) return rc;
+    rc = upload_cdf(c, prob);
+    if (rc) return rc;
+
+    StepParams P; fill_params(c, prob, seed, &P);
+    P.field = raw_field_dev; P.tally_smem = plan.smem_tally ? 1 : 0; P.do_tally = 1; P.refill = 1;
+    P.steps_per_launch = plan.S; P.n_end = (unsigned long long)n_end;
+
+    Counters init{}; init.next = (unsigned long long)n_begin;
+    CUDA_TRY(c, cudaMemcpyAsync(c->ctr.p, &init, sizeof init, cudaMemcpyHostToDevice, c->stream));
+    int cur = 0; long long nslots = plan.slots;
+    CUDA_TRY(c, cudaMemsetAsync(c->imeta[cur].p, 0, (size_t)nslots * sizeof(unsigned long long), c->stream));
+
+    long long launches = 0, step_launches = 0, slot_steps = 0;
+    CUDA_TRY(c, cudaEventRecord(c->ev0, c->stream));
+    float step_ms_total = 0.f;
+    const long long total = n_end - n_begin;
+    if (total > 0) for (;;) {
+        P.st = soa_of(c, cur, c->slots_alloc); P.nslots = nslots;
+        // live counter is rewritten by every launch
+        CUDA_TRY(c, cudaMemsetAsync(&c->ctr.p->live, 0, sizeof(unsigned long long), c->stream));
+        const long long tiles = (nslots + plan.block - 1) / plan.block;
+        const int grid = (int)std::min<long long>(plan.grid, std::max<long long>(tiles, 1));
+        CUDA_TRY(c, cudaEventRecord(c->ev2, c->stream));
+        CUDA_TRY(c, launch_step(P, plan.smem_tally, grid, plan.block, plan.smem, c->stream));
+        CUDA_TRY(c, cudaEventRecord(c->ev3, c->stream));
+        launches++; step_launches++; slot_steps += nslots * plan.S;
+        CUDA_TRY(c, cudaMemcpyAsync(c->h_ctr, c->ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        float ms = 0.f; cudaEventElapsedTime(&ms, c->ev2, c->ev3); step_ms_total += ms;
+        const unsigned long long live = c->h_ctr->live, next = c->h_ctr->next;
+        const bool all_emitted = next >= (unsigned long long)n_end;
+        if (all_emitted && live == 0) break;
+        if (all_emitted && (long long)live * 2 < nslots && nslots > (long long)plan.block * 64) {
+            // tail: compact the survivors so later launches stream only live state
+            const int other = cur ^ 1;
+            CUDA_TRY(c, cudaMemsetAsync(&c->ctr.p->compact_cursor, 0, sizeof(unsigned long long), c->stream));
+            k_compact<<<std::min<long long>((nslots + 255) / 256, (long long)c->sm_count * 8), 256, 0, c->stream>>>(
+                soa_of(c, cur, c->slots_alloc), soa_of(c, other, c->slots_alloc), nslots, c->ctr.p);
+            CUDA_TRY(c, cudaGetLastError());
+            launches++;
+            cur = other; nslots = (long long)live;
+        }
+    }
+    CUDA_TRY(c, cudaEventRecord(c->ev1, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_ctr, c->ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (stats) {
+        std::memset(stats, 0, sizeof *stats);
+        float ms = 0.f; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        stats->emitted = (int64_t)c->h_ctr->emitted; stats->steps = (int64_t)c->h_ctr->steps; stats->esc = (int64_t)c->h_ctr->esc;
+        stats->launches = launches; stats->cols = c->cols; stats->device_ms = ms; stats->step_ms = step_ms_total;
+        stats->step_launches = step_launches; stats->slot_steps = slot_steps;
+    }
+    return MCB_OK;
+}
+
+} // namespace
+
+// =============================================================================== C ABI
+extern "C" {
+
+int mcb_abi_version(void) { return MCB_ABI_VERSION; }
+
+const char* mcb_last_error(const mcb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int mcb_create(int device, mcb_ctx** out) {
+    if (!out) { g_create_err = "null out pointer"; return MCB_EINVAL; }
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_err = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count is 0") +
+                       " (there is no CPU fallback)";
+        return MCB_ENODEVICE;
+    }
+    if (device < 0 || device >= ndev) { g_create_err = "device ordinal out of range"; return MCB_EINVAL; }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { g_create_err = cudaGetErrorString(e); return MCB_ECUDA; }
+    if (prop.major != 10) {
+        g_create_err = std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                       "; this library is built for sm_100a only";
+        return MCB_ENODEVICE;
+    }
+    mcb_ctx* c = new mcb_ctx;
+    c->device = device; c->sm_count = prop.multiProcessorCount; c->smem_optin = prop.sharedMemPerBlockOptin;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess ||
+        (e = cudaEventCreate(&c->ev2)) != cudaSuccess || (e = cudaEventCreate(&c->ev3)) != cudaSuccess ||
+        (e = c->ctr.alloc(1)) != cudaSuccess || (e = cudaMallocHost(&c->h_ctr, sizeof(Counters))) != cudaSuccess) {
+        g_create_err = cudaGetErrorString(e); delete c; return MCB_ECUDA;
+    }
+    *out = c;
+    return MCB_OK;
+}
+
+void mcb_destroy(mcb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    c->mat_blob.release(); c->f_wprob.release(); c->f_pprob.release(); c->f_walias.release(); c->f_palias.release();
+    c->geo_blob.release(); c->emitters.release(); c->cell_vol.release(); c->emit_cdf.release();
+    for (int w = 0; w < 2; ++w) { c->state[w].release(); c->imeta[w].release(); }
+    c->ctr.release(); c->field.release();
+    if (c->h_ctr) cudaFreeHost(c->h_ctr);
+    if (c->ev0) cudaEventDestroy(c->ev0); if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev2) cudaEventDestroy(c->ev2); if (c->ev3) cudaEventDestroy(c->ev3);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int mcb_set_options(mcb_ctx* c, const mcb_options* o) {
+    if (!c || !o) return MCB_EINVAL;
+    if (o->slots < 0 || o->steps_per_launch < 0 || o->block < 0 || o->ctas_per_sm < 0 || o->tally_mode < 0 || o->tally_mode > 2) {
+        c->err = "negative / unknown option"; return MCB_EINVAL;
+    }
+    c->opt = *o;
+    return MCB_OK;
+}
+int mcb_get_options(const mcb_ctx* c, mcb_options* o) { if (!c || !o) return MCB_EINVAL; *o = c->opt; return MCB_OK; }
+
+int mcb_stream(const mcb_ctx* c, void** s) { if (!c || !s) return MCB_EINVAL; *s = (void*)c->stream; return MCB_OK; }
+
+int mcb_upload_material(mcb_ctx* c, const mcb_material_desc* m) {
+    if (!c) return MCB_EINVAL;
+    if (!m || !m->vel || !m->tau || !m->flux_pdf || !m->scat_pdf) { c->err = "null material table"; return MCB_EINVAL; }
+    if (m->nw <= 0 || m->np <= 0) { c->err = "Invalid dispersion table (nw, np must be > 0)"; return MCB_EINVAL; }
+    if (m->nw > 65535 || m->np > 255 || m->nw * m->np >= MCB_MAX_WP) { c->err = "material table too large (nw<=65535, np<=255)"; return MCB_ELIMIT; }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const long nw = m->nw, np = m->np, n = nw * np;
+    for (long i = 0; i < n; ++i)
+        if (!(m->vel[i] > 0.0) || !std::isfinite(m->tau[i]) || !(m->tau[i] >= 0.0)) { c->err = "vel must be > 0 and tau finite, >= 0"; return MCB_EINVAL; }
+    c->flux_alias.build(m->flux_pdf, nw, np);
+    c->scat_alias.build(m->scat_pdf, nw, np);
+    MaterialView v{}; v.nw = (int32_t)nw; v.np = (int32_t)np;
+    uint32_t off = 0;
+    v.off_lambda = off;  off = align16(off + (uint32_t)(n * 8));
+    v.off_inv_vel = off; off = align16(off + (uint32_t)(n * 8));
+    v.off_wprob = off;   off = align16(off + (uint32_t)(nw * 8));
+    v.off_pprob = off;   off = align16(off + (uint32_t)(n * 8));
+    v.off_walias = off;  off = align16(off + (uint32_t)(nw * 2));
+    v.off_palias = off;  off = align16(off + (uint32_t)(n * 1));
+    v.bytes = off;
+    if ((size_t)v.bytes + 16 > c->smem_optin) { c->err = "material tables exceed the shared-memory staging area"; return MCB_ELIMIT; }
+    std::vector<unsigned char> blob(v.bytes, 0);
+    double* lambda = reinterpret_cast<double*>(&blob[v.off_lambda]);
+    double* inv_vel = reinterpret_cast<double*>(&blob[v.off_inv_vel]);
+    double* wprob = reinterpret_cast<double*>(&blob[v.off_wprob]);
+    double* pprob = reinterpret_cast<double*>(&blob[v.off_pprob]);
+    uint16_t* walias = reinterpret_cast<uint16_t*>(&blob[v.off_walias]);
+    uint8_t* palias = reinterpret_cast<uint8_t*>(&blob[v.off_palias]);
+    for (long w = 0; w < nw; ++w) {
+        wprob[w] = c->scat_alias.wprob[w]; walias[w] = (uint16_t)c->scat_alias.walias[w];
+        for (long p = 0; p < np; ++p) {
+            const long src = w + nw * p, dst = w * np + p;
+            lambda[dst] = m->vel[src] * m->tau[src];          // vel(phn) * tau(phn)   material.cpp:221
+            inv_vel[dst] = 1.0 / m->vel[src];
+            pprob[dst] = c->scat_alias.pprob[dst]; palias[dst] = (uint8_t)c->scat_alias.palias[dst];
+        }
+    }
+    CUDA_TRY(c, c->mat_blob.alloc(v.bytes));
+    CUDA_TRY(c, cudaMemcpy(c->mat_blob.p, blob.data(), v.bytes, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, c->f_wprob.alloc(nw)); CUDA_TRY(c, c->f_walias.alloc(nw));
+    CUDA_TRY(c, c->f_pprob.alloc(n));  CUDA_TRY(c, c->f_palias.alloc(n));
+    CUDA_TRY(c, cudaMemcpy(c->f_wprob.p, c->flux_alias.wprob.data(), nw * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->f_walias.p, c->flux_alias.walias.data(), nw * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->f_pprob.p, c->flux_alias.pprob.data(), n * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->f_palias.p, c->flux_alias.palias.data(), n * 4, cudaMemcpyHostToDevice));
+    c->mv = v; c->nw = nw; c->np = np; c->energy_sum = m->energy_sum; c->flux_sum = m->flux_sum; c->has_mat = true;
+    return MCB_OK;
+}
+
+int mcb_get_alias(const mcb_ctx* c, int which, double* wprob, int32_t* walias, double* pprob, int32_t* palias) {
+    if (!c || !c->has_mat || which < 0 || which > 1) return MCB_EINVAL;
+    const AliasTables& a = which == 0 ? c->flux_alias : c->scat_alias;
+    std::memcpy(wprob, a.wprob.data(), a.wprob.size() * 8); std::memcpy(walias, a.walias.data(), a.walias.size() * 4);
+    std::memcpy(pprob, a.pprob.data(), a.pprob.size() * 8); std::memcpy(palias, a.palias.data(), a.palias.size() * 4);
+    return MCB_OK;
+}
+
+int mcb_upload_domain(mcb_ctx* c, const mcb_domain_desc* d) {
+    if (!c) return MCB_EINVAL;
+    if (!d || !d->sdoms || !d->planes || d->nsdom <= 0 || d->nplane <= 0) { c->err = "empty domain"; return MCB_EINVAL; }
+    if (d->nsdom > MCB_MAX_SDOM) { c->err = "too many subdomains"; return MCB_ELIMIT; }
+    if (d->nemitter <= 0 || !d->emitters) { c->err = "Domain has no emitters"; return MCB_EINVAL; }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    std::vector<DPlaneHot> hot(d->nplane); std::vector<DPlaneCold> cold(d->nplane);
+    for (int i = 0; i < d->nplane; ++i) {
+        const mcb_plane_desc& p = d->planes[i];
+        if (p.kind < MCB_BDRY_SPEC || p.kind > MCB_BDRY_PERI) { c->err = "unknown boundary kind"; return MCB_EINVAL; }
+        if (p.sdom < 0 || p.sdom >= d->nsdom) { c->err = "plane owner out of range"; return MCB_EINVAL; }
+        if (p.pair_count < 0 || p.pair_begin < 0 || p.pair_begin + p.pair_count > d->npair) { c->err = "pair range out of bounds"; return MCB_EINVAL; }
+        if ((p.kind == MCB_BDRY_PERI && p.pair_count != 1) || (p.kind == MCB_BDRY_INTER && p.pair_count < 1)) {
+            c->err = "Boundary not paired (Peri needs 1 partner, Inter >= 1)"; return MCB_EINVAL;   // isInit() boundary.cpp:339,503
+        }
+        hot[i] = {p.normal[0], p.normal[1], p.normal[2], p.offset};
+        DPlaneCold& q = cold[i]; std::memset(&q, 0, sizeof q);
+        q.kind = p.kind; q.sdom = p.sdom; q.pair_begin = p.pair_begin; q.pair_count = p.pair_count;
+        const double* m = p.kind == MCB_BDRY_PERI ? p.peri_rot : p.rot;
+        for (int k = 0; k < 9; ++k) q.m[k] = m[k];
+        for (int k = 0; k < 3; ++k) q.t[k] = p.peri_transl[k];
+    }
+    for (int i = 0; i < d->npair; ++i) if (d->pairs[i] < 0 || d->pairs[i] >= d->nplane) { c->err = "pair id out of range"; return MCB_EINVAL; }
+    std::vector<DSdom> sd(d->nsdom); std::vector<double> cell_vol;
+    long long cols = 0;
+    for (int s = 0; s < d->nsdom; ++s) {
+        const mcb_sdom_desc& S = d->sdoms[s]; DSdom& D = sd[s]; std::memset(&D, 0, sizeof D);
+        if (S.plane_count <= 0 || S.plane_begin < 0 || S.plane_begin + S.plane_count > d->nplane) { c->err = "sdom plane range out of bounds"; return MCB_EINVAL; }
+        if (!(S.vol > 0.0)) { c->err = "Volume too small, check vector order"; return MCB_EINVAL; }       // subdomain.h:189
+        for (int k = 0; k < 3; ++k) { D.o[k] = S.origin[k]; D.div[k] = (double)S.div[k]; D.max[k] = (int32_t)S.max[k]; }
+        for (int k = 0; k < 9; ++k) D.inv[k] = S.inv[k];
+        D.eps = S.eps; D.accum = S.accum; D.plane_begin = S.plane_begin; D.plane_count = S.plane_count;
+        D.stride1 = (int32_t)S.shape[0]; D.stride2 = (int32_t)(S.shape[0] * S.shape[1]);
+        const long long sp = S.shape[0] * S.shape[1] * S.shape[2];
+        if (S.accum < -2 || S.accum > 4 || sp < 0) { c->err = "bad accum flag / shape"; return MCB_EINVAL; }
+        if (sp == 0) D.col_offset = -1;                                                                    // field.cpp:34
+        else {
+            D.col_offset = (int32_t)cols; cols += sp;
+            if (S.cell != MCB_CELL_PARALLELEPIPED && sp != 1) { c->err = "gridded non-box cells are not built yet (SURVEY N3)"; return MCB_EINVAL; }
+            for (long long k = 0; k < sp; ++k) cell_vol.push_back(S.vol / (double)sp);                     // subdomain.cpp:269-273
+        }
+        if (cols > 0x7FFFFFFFll) { c->err = "too many cells"; return MCB_ELIMIT; }
+    }
+    std::vector<DEmitter> em(d->nemitter);
+    for (int i = 0; i < d->nemitter; ++i) {
+        const mcb_emitter_desc& e = d->emitters[i]; DEmitter& E = em[i]; std::memset(&E, 0, sizeof E);
+        E.kind = e.kind; E.index = e.index;
+        if (e.kind == MCB_EMIT_SDOM) {
+            if (e.index < 0 || e.index >= d->nsdom) { c->err = "emitter sdom out of range"; return MCB_EINVAL; }
+            const mcb_sdom_desc& S = d->sdoms[e.index];
+            if (S.cell != MCB_CELL_PARALLELEPIPED) { c->err = "volumetric emission from non-box cells is not built yet (SURVEY N3)"; return MCB_EINVAL; }
+            E.sdom = e.index;
+            for (int k = 0; k < 3; ++k) { E.o[k] = S.origin[k]; E.g[k] = S.grad_t[k]; }
+            for (int k = 0; k < 9; ++k) { E.a[k] = S.mat[k]; E.rot[k] = S.emit_rot[k]; }
+        } else if (e.kind == MCB_EMIT_BDRY) {
+            if (e.index < 0 || e.index >= d->nplane) { c->err = "emitter plane out of range"; return MCB_EINVAL; }
+            const mcb_plane_desc& p = d->planes[e.index];
+            if (p.shape != MCB_SHAPE_PARALLELOGRAM && p.shape != MCB_SHAPE_TRIANGLE) { c->err = "polygon emitters are not built yet (SURVEY N3)"; return MCB_EINVAL; }
+            E.sdom = p.sdom; E.shape = p.shape;
+            for (int k = 0; k < 3; ++k) E.o[k] = p.origin[k];
+            for (int k = 0; k < 6; ++k) E.a[k] = p.verts[k];
+            for (int k = 0; k < 9; ++k) E.rot[k] = p.rot[k];
+            E.g[0] = p.T;
+        } else { c->err = "unknown emitter kind"; return MCB_EINVAL; }
+    }
+    GeometryView v{}; v.nsdom = d->nsdom; v.nplane = d->nplane; v.npair = d->npair;
+    uint32_t off = 0;
+    v.off_hot = off;   off = align16(off + (uint32_t)(hot.size() * sizeof(DPlaneHot)));
+    v.off_cold = off;  off = align16(off + (uint32_t)(cold.size() * sizeof(DPlaneCold)));
+    v.off_sdom = off;  off = align16(off + (uint32_t)(sd.size() * sizeof(DSdom)));
+    v.off_pairs = off; off = align16(off + (uint32_t)(std::max(d->npair, 1) * sizeof(int32_t)));
+    v.bytes = off;
+    std::vector<unsigned char> blob(v.bytes, 0);
+    std::memcpy(&blob[v.off_hot], hot.data(), hot.size() * sizeof(DPlaneHot));
+    std::memcpy(&blob[v.off_cold], cold.data(), cold.size() * sizeof(DPlaneCold));
+    std::memcpy(&blob[v.off_sdom], sd.data(), sd.size() * sizeof(DSdom));
+    if (d->npair > 0) std::memcpy(&blob[v.off_pairs], d->pairs, d->npair * sizeof(int32_t));
+    CUDA_TRY(c, c->geo_blob.alloc(v.bytes));
+    CUDA_TRY(c, cudaMemcpy(c->geo_blob.p, blob.data(), v.bytes, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, c->emitters.alloc(em.size()));
+    CUDA_TRY(c, cudaMemcpy(c->emitters.p, em.data(), em.size() * sizeof(DEmitter), cudaMemcpyHostToDevice));
+    CUDA_TRY(c, c->cell_vol.alloc(cell_vol.size()));
+    if (!cell_vol.empty()) CUDA_TRY(c, cudaMemcpy(c->cell_vol.p, cell_vol.data(), cell_vol.size() * 8, cudaMemcpyHostToDevice));
+    c->gv = v; c->h_sdom = sd; c->nemitter = d->nemitter; c->cols = cols; c->has_dom = true;
+    return MCB_OK;
+}
+
+int mcb_field_cols(const mcb_ctx* c, int64_t* cols) {
+    if (!c || !cols || !c->has_dom) return MCB_EINVAL;
+    *cols = c->cols; return MCB_OK;
+}
+
+int mcb_solve_raw_dev(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n_begin, int64_t n_end,
+                      double* raw_field_dev, mcb_stats* stats) {
+    if (!c) return MCB_EINVAL;
+    if (!raw_field_dev) { c->err = "null device field"; return MCB_EINVAL; }
+    return run_solve(c, prob, seed, n_begin, n_end, raw_field_dev, stats);
+}
+
+int mcb_finalize_dev(mcb_ctx* c, const mcb_problem_desc* prob, double* field_dev) {
+    if (!c) return MCB_EINVAL;
+    int rc = check_problem(c, prob);
+    if (rc) return rc;
+    if (!field_dev) { c->err = "null device field"; return MCB_EINVAL; }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (c->cols > 0) {
+        k_finalize<<<(unsigned)((c->cols + 127) / 128), 128, 0, c->stream>>>(field_dev, prob->rows, c->cols, prob->kind, prob->size,
+                                                                            c->energy_sum, prob->power, c->cell_vol.p);
+        CUDA_TRY(c, cudaGetLastError());
+    }
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return MCB_OK;
+}
+
+int mcb_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n_begin, int64_t n_end,
+              double* out_field, mcb_stats* stats) {
+    if (!c) return MCB_EINVAL;
+    if (!out_field) { c->err = "null output field"; return MCB_EINVAL; }
+    int rc = check_problem(c, prob);
+    if (rc) return rc;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const size_t len = (size_t)prob->rows * (size_t)c->cols;
+    CUDA_TRY(c, c->field.alloc(len));
+    CUDA_TRY(c, cudaMemsetAsync(c->field.p, 0, std::max<size_t>(len, 1) * sizeof(double), c->stream));
+    rc = run_solve(c, prob, seed, n_begin, n_end, c->field.p, stats);
+    if (rc) return rc;
+    rc = mcb_finalize_dev(c, prob, c->field.p);
+    if (rc) return rc;
+    if (stats) stats->launches += 1;
+    CUDA_TRY(c, cudaMemcpyAsync(out_field, c->field.p, len * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return MCB_OK;
+}
+
+int mcb_trace(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n_begin, int64_t n_end, int64_t nsteps,
+              mcb_trace_out* o) {
+    if (!c) return MCB_EINVAL;
+    int rc = check_problem(c, prob);
+    if (rc) return rc;
+    if (!o || n_begin < 0 || n_end > prob->nemit || n_begin > n_end || nsteps < 0) { c->err = "bad trace arguments"; return MCB_EINVAL; }
+    const long long n = n_end - n_begin;
+    if (n == 0) return MCB_OK;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    RunPlan plan;
+    mcb_options saved = c->opt; c->opt.slots = n; c->opt.tally_mode = 2;
+    rc = plan_run(c, prob, n, &plan);
+    c->opt = saved;
+    if (rc) return rc;
+    if ((rc = ensure_slots(c, n))) return rc;
+    if ((rc = upload_cdf(c, prob))) return rc;
+    StepParams P; fill_params(c, prob, seed, &P);
+    P.maxloop = std::min<long long>(prob->maxloop, nsteps);
+    P.field = nullptr; P.tally_smem = 0; P.do_tally = 0; P.refill = 0;
+    P.steps_per_launch = (int)std::max<long long>(1, std::min<long long>(P.maxloop, 0x7FFFFFFF)); P.n_end = (unsigned long long)n_end;
+    P.st = soa_of(c, 0, c->slots_alloc); P.nslots = n;
+    Counters init{}; init.next = (unsigned long long)n_begin;
+    CUDA_TRY(c, cudaMemcpyAsync(c->ctr.p, &init, sizeof init, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(c->imeta[0].p, 0, (size_t)c->slots_alloc * 2 * sizeof(unsigned long long), c->stream));
+    CUDA_TRY(c, launch_step(P, false, plan.grid, plan.block, plan.smem, c->stream));
+    DevBuf<double> dpos, ddir, dsn; DevBuf<long long> dw, dp, dnscat, dsteps; DevBuf<int32_t> dsign, dalive, dsdom, dcell;
+    CUDA_TRY(c, dpos.alloc(3 * n)); CUDA_TRY(c, ddir.alloc(3 * n)); CUDA_TRY(c, dsn.alloc(n));
+    CUDA_TRY(c, dw.alloc(n)); CUDA_TRY(c, dp.alloc(n)); CUDA_TRY(c, dnscat.alloc(n)); CUDA_TRY(c, dsteps.alloc(n));
+    CUDA_TRY(c, dsign.alloc(n)); CUDA_TRY(c, dalive.alloc(n)); CUDA_TRY(c, dsdom.alloc(n)); CUDA_TRY(c, dcell.alloc(3 * n));
+    k_gather_trace<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(P.st, n, (unsigned long long)n_begin, n, (int)c->np,
+        c->geo_blob.p, c->gv, dpos.p, ddir.p, dsn.p, dw.p, dp.p, dsign.p, dalive.p, dsdom.p, dnscat.p, dsteps.p, dcell.p);
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+#define MCB_COPY_OUT(dst, src, count, type) if (dst) CUDA_TRY(c, cudaMemcpy(dst, src.p, (size_t)(count) * sizeof(type), cudaMemcpyDeviceToHost))
+    MCB_COPY_OUT(o->pos, dpos, 3 * n, double); MCB_COPY_OUT(o->dir, ddir, 3 * n, double); MCB_COPY_OUT(o->scat_next, dsn, n, double);
+    MCB_COPY_OUT(o->w, dw, n, long long); MCB_COPY_OUT(o->p, dp, n, long long); MCB_COPY_OUT(o->sign, dsign, n, int32_t);
+    MCB_COPY_OUT(o->alive, dalive, n, int32_t); MCB_COPY_OUT(o->sdom, dsdom, n, int32_t); MCB_COPY_OUT(o->nscat, dnscat, n, long long);
+    MCB_COPY_OUT(o->steps, dsteps, n, long long); MCB_COPY_OUT(o->cell, dcell, 3 * n, int32_t);
+#undef MCB_COPY_OUT
+    dpos.release(); ddir.release(); dsn.release(); dw.release(); dp.release(); dnscat.release(); dsteps.release();
+    dsign.release(); dalive.release(); dsdom.release(); dcell.release();
+    return MCB_OK;
+}
+
+int mcb_cell_index(mcb_ctx* c, int64_t n, const double* pos, const int32_t* sdom, int64_t* index) {
+    if (!c) return MCB_EINVAL;
+    if (!c->has_dom) { c->err = "upload a domain first"; return MCB_ESTATE; }
+    if (n < 0 || (n > 0 && (!pos || !sdom || !index))) { c->err = "bad arguments"; return MCB_EINVAL; }
+    if (n == 0) return MCB_OK;
+    for (int64_t i = 0; i < n; ++i) if (sdom[i] < 0 || sdom[i] >= c->gv.nsdom) { c->err = "sdom out of range"; return MCB_EINVAL; }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    DevBuf<double> dpos; DevBuf<int32_t> ds; DevBuf<long long> di;
+    CUDA_TRY(c, dpos.alloc(3 * n)); CUDA_TRY(c, ds.alloc(n)); CUDA_TRY(c, di.alloc(3 * n));
+    CUDA_TRY(c, cudaMemcpy(dpos.p, pos, 3 * n * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(ds.p, sdom, n * 4, cudaMemcpyHostToDevice));
+    k_cell_index<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->geo_blob.p, c->gv, n, dpos.p, ds.p, di.p);
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaMemcpy(index, di.p, 3 * n * 8, cudaMemcpyDeviceToHost));
+    dpos.release(); ds.release(); di.release();
+    return MCB_OK;
+}
+
+int mcb_accumulate(mcb_ctx* c, int32_t rows, int64_t n, const int32_t* sdom, const double* bpos, const double* epos,
+                   const double* amount, double* field) {
+    if (!c) return MCB_EINVAL;
+    if (!c->has_dom) { c->err = "upload a domain first"; return MCB_ESTATE; }
+    if (rows <= 0 || n < 0 || !field || (n > 0 && (!sdom || !bpos || !epos || !amount))) { c->err = "bad arguments"; return MCB_EINVAL; }
+    for (int64_t i = 0; i < n; ++i) if (sdom[i] < 0 || sdom[i] >= c->gv.nsdom) { c->err = "sdom out of range"; return MCB_EINVAL; }
+    if (n == 0 || c->cols == 0) return MCB_OK;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const size_t len = (size_t)rows * (size_t)c->cols;
+    DevBuf<double> db, de, da, df; DevBuf<int32_t> ds;
+    CUDA_TRY(c, db.alloc(3 * n)); CUDA_TRY(c, de.alloc(3 * n)); CUDA_TRY(c, da.alloc(rows * n)); CUDA_TRY(c, df.alloc(len)); CUDA_TRY(c, ds.alloc(n));
+    CUDA_TRY(c, cudaMemcpy(db.p, bpos, 3 * n * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(de.p, epos, 3 * n * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(da.p, amount, (size_t)rows * n * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(ds.p, sdom, n * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(df.p, field, len * 8, cudaMemcpyHostToDevice));
+    k_accumulate<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->geo_blob.p, c->gv, rows, n, ds.p, db.p, de.p, da.p, df.p);
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaMemcpy(field, df.p, len * 8, cudaMemcpyDeviceToHost));
+    db.release(); de.release(); da.release(); df.release(); ds.release();
+    return MCB_OK;
+}
+
+int mcb_philox_words(uint64_t seed, uint64_t particle, uint32_t event, uint32_t block, uint32_t out[4]) {
+    // runs the DEVICE generator on the current device (no host mirror, no fallback)
+    if (!out) return MCB_EINVAL;
+    uint32_t* d = nullptr;
+    if (cudaMalloc(&d, 16) != cudaSuccess) { g_create_err = "no CUDA device (there is no CPU fallback)"; return MCB_ENODEVICE; }
+    k_philox<<<1, 1>>>(seed, particle, event, block, d);
+    cudaError_t e = cudaMemcpy(out, d, 16, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) { g_create_err = cudaGetErrorString(e); return MCB_ECUDA; }
+    return MCB_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,427 @@
+// mcb_kernels.cuh — the CUDA kernels (sm_100a) of the phonon Monte Carlo hot path.
+//
+//   k_step      K1+K2 fused: refill freed slots by emitting the next particle (problem.cpp:386-399),
+//               then S trips of the loop body (problem.cpp:401-435): advect -> tally -> boundary or
+//               intrinsic scattering.  State streams HBM -> registers -> HBM once per launch.
+//               Material tables are staged into shared memory with a TMA bulk copy
+//               (cp.async.bulk + mbarrier); tallies go to a per-CTA shared-memory histogram
+//               (flushed once per CTA) or, for big fields, straight to L2 with fp64 RED.
+//   k_compact   K3: stream-compacts the active slots of the tail (no reference analogue; replaces the
+//               `break`s at problem.cpp:411,425,434).
+//   k_finalize  K4: postProc, / cellVol, * power_ (problem.cpp:439-444).
+//   k_cell_index / k_accumulate / k_gather_trace: diagnostics behind mcb_cell_index / mcb_accumulate / mcb_trace.
+#pragma once
+#include "mcb_device.cuh"
+#include "../../include/mcb.h"
+
+namespace mcb {
+
+// --------------------------------------------------------------- TMA bulk copy + mbarrier (PTX)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t phase) {
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+    return ok != 0;
+}
+
+// streaming state access: keep L1 for the tables' spill-over, do not allocate state lines
+__device__ __forceinline__ double ld_stream(const double* p) {
+    double v; asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v;
+}
+__device__ __forceinline__ unsigned long long ld_stream(const unsigned long long* p) {
+    unsigned long long v; asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p)); return v;
+}
+__device__ __forceinline__ void st_stream(double* p, double v) {
+    asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ void st_stream(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.global.L1::no_allocate.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// ------------------------------------------------------------------------------ particle
+struct Particle {
+    double px, py, pz, dx, dy, dz, sn;
+    uint32_t wp, sign, active, killed, sdom, nscat, step;
+    unsigned long long pid;
+};
+
+// Material::Dist::drawProp (material.cpp:71-75) on the two-level Walker tables; entry (w,p) at w*np+p
+template <typename WA, typename PA>
+__device__ __forceinline__ uint32_t draw_prop(Rng& g, int nw, int np, const double* wprob, const WA* walias,
+                                              const double* pprob, const PA* palias) {
+    uint32_t r = g.uint_below((uint32_t)nw);
+    double t = g.u01();
+    uint32_t w = t < wprob[r] ? r : (uint32_t)walias[r];
+    uint32_t q = g.uint_below((uint32_t)np);
+    double u = g.u01();
+    uint32_t p = u < pprob[w * np + q] ? q : (uint32_t)palias[w * np + q];
+    return w * (uint32_t)np + p;
+}
+// Material::drawScatNext (material.cpp:215-224); lambda = vel*tau
+__device__ __forceinline__ double draw_scat_next(Rng& g, double lambda) {
+    double d = 0.0;
+    while (d < 2.2250738585072014e-308) d = lambda * -log(1.0 - g.u01());
+    return d;
+}
+
+// problem.cpp:386-399 for particle `pid`: pick emitter, drawFluxProp, Emitter::emit, drawScatNext
+__device__ __noinline__ void emit_particle(const StepParams& P, const Tables& T, unsigned long long pid, Particle& ph) {
+    // emitter = upper_bound(emitCdf, n)  (problem.cpp:386-387)
+    int lo = 0, hi = P.nemitter;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if ((long long)pid < P.emit_cdf[mid]) hi = mid; else lo = mid + 1; }
+    const DEmitter& E = P.emitters[lo];
+    Rng g; g.begin(P.seed, pid, 0u);
+    uint32_t wp = draw_prop(g, T.nw, T.np, P.f_wprob, P.f_walias, P.f_pprob, P.f_palias);
+    double px, py, pz, dx, dy, dz; uint32_t sign;
+    if (E.kind == MCB_EMIT_SDOM) {
+        // ParallelepipedImpl::drawPos subdomain.cpp:275-281 ; drawDir :255-258 ; emitSign :260-263
+        double c0 = g.u01(), c1 = g.u01(), c2 = g.u01();
+        double mx, my, mz; matvec(E.a, c0, c1, c2, mx, my, mz);
+        px = E.o[0] + mx; py = E.o[1] + my; pz = E.o[2] + mz;
+        double ax, ay, az; draw_aniso(g, true, ax, ay, az);
+        matvec(E.rot, ax, ay, az, dx, dy, dz);
+        sign = dot3(dx, dy, dz, E.g[0], E.g[1], E.g[2]) < 0.0 ? 1u : 0u;
+    } else {
+        // EmitBoundary::drawPos / drawDir / emitSign boundary.cpp:418-431 ; shapes :147-152,:182-187
+        double r1 = g.u01(), r2 = g.u01();
+        if (E.shape == MCB_SHAPE_TRIANGLE && !(r1 + r2 < 1.0)) { r1 = 1.0 - r1; r2 = 1.0 - r2; }
+        px = E.o[0] + (r1 * E.a[0] + r2 * E.a[3]);
+        py = E.o[1] + (r1 * E.a[1] + r2 * E.a[4]);
+        pz = E.o[2] + (r1 * E.a[2] + r2 * E.a[5]);
+        double ax, ay, az; draw_aniso(g, false, ax, ay, az);
+        matvec(E.rot, ax, ay, az, dx, dy, dz);
+        sign = E.g[0] >= 0.0 ? 1u : 0u;
+    }
+    normalize3(dx, dy, dz);                                  // Phonon ctor phonon.cpp:33-37
+    ph.px = px; ph.py = py; ph.pz = pz; ph.dx = dx; ph.dy = dy; ph.dz = dz;
+    ph.wp = wp; ph.sign = sign; ph.active = P.maxloop > 0 ? 1u : 0u; ph.killed = 0; ph.sdom = (uint32_t)E.sdom; ph.nscat = 0; ph.step = 0;
+    ph.pid = pid;
+    ph.sn = draw_scat_next(g, T.lambda[wp]);
+}
+
+// Subdomain::isInside subdomain.cpp:108-116
+__device__ __forceinline__ bool is_inside(const Tables& T, const DSdom& sd, double x, double y, double z) {
+    bool in = true;
+    for (int b = 0; b < sd.plane_count; ++b) {
+        const DPlaneHot h = T.hot[sd.plane_begin + b];
+        in = in && !(dot3(h.nx, h.ny, h.nz, x, y, z) + h.off < -sd.eps);
+    }
+    return in;
+}
+
+// One trip of the loop body problem.cpp:401-435.  Returns the number of escapes (0/1).
+template <int KIND, bool SMEM>
+__device__ __forceinline__ uint32_t step_once(const StepParams& P, const Tables& T, Particle& ph) {
+    constexpr int NCOMP = (KIND == MCB_PROB_TEMP || KIND == MCB_PROB_CUMTEMP) ? 1 : (KIND == MCB_PROB_MULTI ? 4 : 3);
+    const DSdom& sd = T.sdom[ph.sdom];
+    const double inv_vel = T.inv_vel[ph.wp];                                   // Material::vel :405
+    // Subdomain::advect subdomain.cpp:161-192
+    double d = ph.sn; int hit = -1;
+    for (int b = 0; b < sd.plane_count; ++b) {
+        const DPlaneHot h = T.hot[sd.plane_begin + b];
+        const double c = dot3(h.nx, h.ny, h.nz, ph.dx, ph.dy, ph.dz);
+        if (c >= 0.0) continue;
+        const double t = -(h.off + dot3(h.nx, h.ny, h.nz, ph.px, ph.py, ph.pz)) / c;   // boundary.cpp:107-110
+        if (t < d) { d = t; hit = sd.plane_begin + b; }
+    }
+    // Phonon::move phonon.cpp:95-105
+    double sn = ph.sn - d;
+    if (sn < 2.2250738585072014e-308) sn = 0.0;
+    ph.sn = sn;
+    const double bx = ph.px, by = ph.py, bz = ph.pz;
+    const double ex = bx + ph.dx * d, ey = by + ph.dy * d, ez = bz + ph.dz * d;
+    ph.px = ex; ph.py = ey; ph.pz = ez;
+    const uint32_t nscat_before = ph.nscat;
+    ph.step++;
+    if (d < -sd.eps || !is_inside(T, sd, ex, ey, ez)) {                        // subdomain.cpp:182-189
+        ph.killed = 1; ph.active = 0; return 1u;                               // problem.cpp:408-412
+    }
+    if (P.do_tally) {
+        // accumAmt (problem.cpp:473-476,506-509,539-544,581-589,629-637) times sign (:414)
+        const double sg = ph.sign ? 1.0 : -1.0;
+        double amt[NCOMP]; int rbase = 0;
+        if (KIND == MCB_PROB_TEMP || KIND == MCB_PROB_CUMTEMP) amt[0] = sg * (d * inv_vel);
+        else if (KIND == MCB_PROB_MULTI) { amt[0] = sg * (d * inv_vel); amt[1] = sg * (ex - bx); amt[2] = sg * (ey - by); amt[3] = sg * (ez - bz); }
+        else { amt[0] = sg * (ex - bx); amt[NCOMP > 1 ? 1 : 0] = sg * (ey - by); amt[NCOMP > 2 ? 2 : 0] = sg * (ez - bz); }
+        if (KIND == MCB_PROB_CUMTEMP || KIND == MCB_PROB_CUMFLUX)
+            rbase = NCOMP * (int)(((long long)nscat_before + P.cum_step - 1) / P.cum_step);
+        accumulate<NCOMP, SMEM>(sd, T.hist, P.rows, rbase, bx, by, bz, ex, ey, ez, amt);   // Field::accumulate :416
+    }
+    uint32_t esc = 0;
+    if (hit >= 0) {                                                            // problem.cpp:418-429
+        const DPlaneCold& cb = T.cold[hit];
+        const int kind = cb.kind;
+        if (kind == MCB_BDRY_SPEC) {                                           // boundary.cpp:283-287
+            const DPlaneHot h = T.hot[hit];
+            const double c2 = 2.0 * dot3(h.nx, h.ny, h.nz, ph.dx, ph.dy, ph.dz);
+            ph.dx -= c2 * h.nx; ph.dy -= c2 * h.ny; ph.dz -= c2 * h.nz;
+            normalize3(ph.dx, ph.dy, ph.dz);
+        } else if (kind == MCB_BDRY_DIFF) {                                    // boundary.cpp:308-312
+            Rng g; g.begin(P.seed, ph.pid, ph.step);
+            double ax, ay, az; draw_aniso(g, false, ax, ay, az);
+            matvec(cb.m, ax, ay, az, ph.dx, ph.dy, ph.dz);
+            normalize3(ph.dx, ph.dy, ph.dz);
+            ph.nscat++;
+        } else if (kind == MCB_BDRY_PERI) {                                    // boundary.cpp:516-522
+            double nx, ny, nz; matvec(cb.m, ex, ey, ez, nx, ny, nz);
+            ph.px = nx + cb.t[0]; ph.py = ny + cb.t[1]; ph.pz = nz + cb.t[2];
+            matvec(cb.m, ph.dx, ph.dy, ph.dz, nx, ny, nz);
+            ph.dx = nx; ph.dy = ny; ph.dz = nz;
+            normalize3(ph.dx, ph.dy, ph.dz);
+            ph.sdom = (uint32_t)T.cold[T.pairs[cb.pair_begin]].sdom;
+        } else if (kind == MCB_BDRY_INTER) {                                   // boundary.cpp:349-359
+            int target = -1;
+            if (cb.pair_count == 1) target = T.pairs[cb.pair_begin];
+            else for (int q = 0; q < cb.pair_count && target < 0; ++q) {
+                const int cand = T.pairs[cb.pair_begin + q];
+                if (is_inside(T, T.sdom[T.cold[cand].sdom], ex, ey, ez)) target = cand;
+            }
+            if (target < 0) { ph.killed = 1; ph.active = 0; esc = 1; }         // problem.cpp:422-426
+            else ph.sdom = (uint32_t)T.cold[target].sdom;
+        } else {                                                               // Isot boundary.cpp:455-460
+            ph.killed = 1; ph.active = 0;
+        }
+    } else {                                                                   // Material::scatter material.cpp:226-231
+        Rng g; g.begin(P.seed, ph.pid, ph.step);
+        ph.wp = draw_prop(g, T.nw, T.np, T.wprob, T.walias, T.pprob, T.palias);
+        draw_iso(g, ph.dx, ph.dy, ph.dz);
+        normalize3(ph.dx, ph.dy, ph.dz);
+        ph.nscat++;
+        ph.sn = draw_scat_next(g, T.lambda[ph.wp]);
+    }
+    if ((long long)ph.nscat >= P.maxscat || (long long)ph.step >= P.maxloop) ph.active = 0;   // :434, :401
+    return esc;
+}
+
+// ------------------------------------------------------------------------------- k_step
+// Dynamic shared memory: [mbarrier 16 B][material blob][geometry blob][block histogram]
+template <int KIND, bool SMEM>
+__global__ void __launch_bounds__(512, 1) k_step(const StepParams P) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+    unsigned char* s_mat = smem + 16;
+    unsigned char* s_geo = s_mat + P.mv.bytes;
+    double* s_hist = reinterpret_cast<double*>(s_geo + P.gv.bytes);
+
+    // --- stage tables: one elected thread arms the mbarrier and issues the TMA bulk copies
+    if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, P.mv.bytes + P.gv.bytes);
+        const uint32_t CH = 32768;
+        for (uint32_t o = 0; o < P.mv.bytes; o += CH) tma_bulk_g2s(s_mat + o, P.mat_blob + o, min(CH, P.mv.bytes - o), bar);
+        for (uint32_t o = 0; o < P.gv.bytes; o += CH) tma_bulk_g2s(s_geo + o, P.geo_blob + o, min(CH, P.gv.bytes - o), bar);
+    }
+    if (SMEM) for (long long i = threadIdx.x; i < P.field_len; i += blockDim.x) s_hist[i] = 0.0;
+    while (!mbar_try_wait(bar, 0)) {}
+    __syncthreads();
+
+    Tables T;
+    T.lambda = reinterpret_cast<const double*>(s_mat + P.mv.off_lambda);
+    T.inv_vel = reinterpret_cast<const double*>(s_mat + P.mv.off_inv_vel);
+    T.wprob = reinterpret_cast<const double*>(s_mat + P.mv.off_wprob);
+    T.pprob = reinterpret_cast<const double*>(s_mat + P.mv.off_pprob);
+    T.walias = reinterpret_cast<const uint16_t*>(s_mat + P.mv.off_walias);
+    T.palias = reinterpret_cast<const uint8_t*>(s_mat + P.mv.off_palias);
+    T.hot = reinterpret_cast<const DPlaneHot*>(s_geo + P.gv.off_hot);
+    T.cold = reinterpret_cast<const DPlaneCold*>(s_geo + P.gv.off_cold);
+    T.sdom = reinterpret_cast<const DSdom*>(s_geo + P.gv.off_sdom);
+    T.pairs = reinterpret_cast<const int32_t*>(s_geo + P.gv.off_pairs);
+    T.nw = P.mv.nw; T.np = P.mv.np;
+    T.hist = SMEM ? s_hist : P.field;
+
+    unsigned long long my_steps = 0, my_esc = 0, my_emitted = 0, my_live = 0;
+    bool exhausted = false;
+    const unsigned lane = threadIdx.x & 31u;
+
+    for (long long base = (long long)blockIdx.x * blockDim.x; base < P.nslots; base += (long long)gridDim.x * blockDim.x) {
+        const long long i = base + threadIdx.x;
+        const bool valid = i < P.nslots;
+        Particle ph; ph.active = 0; ph.killed = 0;
+        unsigned long long meta = 0, ps = 0;
+        if (valid) {
+            meta = ld_stream(P.st.meta + i);
+            ps = ld_stream(P.st.pidstep + i);
+            ph.active = MCB_META_ACTIVE(meta);
+            if (ph.active) {
+                ph.px = ld_stream(P.st.px + i); ph.py = ld_stream(P.st.py + i); ph.pz = ld_stream(P.st.pz + i);
+                ph.dx = ld_stream(P.st.dx + i); ph.dy = ld_stream(P.st.dy + i); ph.dz = ld_stream(P.st.dz + i);
+                ph.sn = ld_stream(P.st.sn + i);
+                ph.wp = MCB_META_WP(meta); ph.sign = MCB_META_SIGN(meta); ph.killed = 0;
+                ph.sdom = MCB_META_SDOM(meta); ph.nscat = MCB_META_NSCAT(meta);
+                ph.pid = MCB_PID(ps); ph.step = MCB_STEP(ps);
+            }
+        }
+        bool dirty = false;
+        for (int s = 0; s < P.steps_per_launch; ++s) {
+            // refill: a freed slot takes the next particle id (warp-aggregated ticket)
+            const bool want = valid && !ph.active && !exhausted && (P.refill || s == 0);
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, want);
+            if (m) {
+                unsigned long long ticket = 0;
+                const int leader = __ffs(m) - 1;
+                if ((int)lane == leader) ticket = atomicAdd(&P.ctr->next, (unsigned long long)__popc(m));
+                ticket = __shfl_sync(0xFFFFFFFFu, ticket, leader);
+                if (want) {
+                    const unsigned long long pid = ticket + __popc(m & ((1u << lane) - 1u));
+                    if (pid < P.n_end) { emit_particle(P, T, pid, ph); my_emitted++; dirty = true; }
+                    else exhausted = true;
+                }
+            }
+            if (ph.active) { my_esc += step_once<KIND, SMEM>(P, T, ph); my_steps++; dirty = true; }
+            if (__all_sync(0xFFFFFFFFu, !ph.active && (exhausted || !valid || !P.refill))) break;
+        }
+        if (valid && dirty) {
+            st_stream(P.st.px + i, ph.px); st_stream(P.st.py + i, ph.py); st_stream(P.st.pz + i, ph.pz);
+            st_stream(P.st.dx + i, ph.dx); st_stream(P.st.dy + i, ph.dy); st_stream(P.st.dz + i, ph.dz);
+            st_stream(P.st.sn + i, ph.sn);
+            st_stream(P.st.meta + i, pack_meta(ph.wp, ph.sign, ph.active, ph.killed, ph.sdom, ph.nscat));
+            st_stream(P.st.pidstep + i, (ph.pid << 24) | (unsigned long long)ph.step);
+        }
+        if (ph.active) my_live++;
+    }
+
+    // --- block-level reduction of the counters, one atomic per CTA
+    __shared__ unsigned long long s_red[4];
+    if (threadIdx.x < 4) s_red[threadIdx.x] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        my_steps += __shfl_down_sync(0xFFFFFFFFu, my_steps, o); my_esc += __shfl_down_sync(0xFFFFFFFFu, my_esc, o);
+        my_emitted += __shfl_down_sync(0xFFFFFFFFu, my_emitted, o); my_live += __shfl_down_sync(0xFFFFFFFFu, my_live, o);
+    }
+    if (lane == 0) {
+        if (my_steps) atomicAdd(&s_red[0], my_steps);
+        if (my_esc) atomicAdd(&s_red[1], my_esc);
+        if (my_emitted) atomicAdd(&s_red[2], my_emitted);
+        if (my_live) atomicAdd(&s_red[3], my_live);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_red[0]) atomicAdd(&P.ctr->steps, s_red[0]);
+        if (s_red[1]) atomicAdd(&P.ctr->esc, s_red[1]);
+        if (s_red[2]) atomicAdd(&P.ctr->emitted, s_red[2]);
+        if (s_red[3]) atomicAdd(&P.ctr->live, s_red[3]);
+    }
+    // --- flush the block histogram (fp64 RED to L2)
+    if (SMEM && P.do_tally)
+        for (long long i = threadIdx.x; i < P.field_len; i += blockDim.x) {
+            const double v = s_hist[i];
+            if (v != 0.0) atomicAdd(P.field + i, v);
+        }
+}
+
+// ---------------------------------------------------------------------------- k_compact
+// Unordered stream compaction of active slots from `src` into `dst` (tail of the solve).
+__global__ void k_compact(StateSoA src, StateSoA dst, long long n, Counters* ctr) {
+    const unsigned lane = threadIdx.x & 31u;
+    for (long long base = (long long)blockIdx.x * blockDim.x; base < n; base += (long long)gridDim.x * blockDim.x) {
+        const long long i = base + threadIdx.x;
+        unsigned long long meta = 0;
+        if (i < n) meta = src.meta[i];
+        const bool act = (i < n) && MCB_META_ACTIVE(meta);
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, act);
+        if (!m) continue;
+        unsigned long long pos = 0;
+        const int leader = __ffs(m) - 1;
+        if ((int)lane == leader) pos = atomicAdd(&ctr->compact_cursor, (unsigned long long)__popc(m));
+        pos = __shfl_sync(0xFFFFFFFFu, pos, leader);
+        if (act) {
+            const long long o = (long long)(pos + __popc(m & ((1u << lane) - 1u)));
+            dst.px[o] = src.px[i]; dst.py[o] = src.py[i]; dst.pz[o] = src.pz[i];
+            dst.dx[o] = src.dx[i]; dst.dy[o] = src.dy[i]; dst.dz[o] = src.dz[i];
+            dst.sn[o] = src.sn[i]; dst.meta[o] = meta; dst.pidstep[o] = src.pidstep[i];
+        }
+    }
+}
+
+// --------------------------------------------------------------------------- k_finalize
+// problem.cpp:439-444: postProc (problem.cpp:478-481,511-514,546-551,591-599,639-648), / cellVol, * power_
+__global__ void k_finalize(double* field, int rows, long long cols, int kind, long long size,
+                           double energy_sum, double power, const double* cell_vol) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    double* f = field + c * rows;
+    const double vol = cell_vol[c];
+    if (kind == MCB_PROB_CUMTEMP) {
+        for (long long i = 0; i < size; ++i) f[i + 1] += f[i];
+    } else if (kind == MCB_PROB_CUMFLUX) {
+        for (long long i = 0; i < size; ++i) for (int q = 0; q < 3; ++q) f[3 * (i + 1) + q] += f[3 * i + q];
+    }
+    for (int r = 0; r < rows; ++r) {
+        double v = f[r];
+        if (kind == MCB_PROB_TEMP || kind == MCB_PROB_CUMTEMP || (kind == MCB_PROB_MULTI && r == 0)) v = v / energy_sum;
+        f[r] = power * (v / vol);
+    }
+}
+
+// ------------------------------------------------------------------------- diagnostics
+__global__ void k_cell_index(const unsigned char* geo_blob, GeometryView gv, long long n, const double* pos,
+                             const int32_t* sdom, long long* index) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const DSdom* sds = reinterpret_cast<const DSdom*>(geo_blob + gv.off_sdom);
+    const DSdom& sd = sds[sdom[i]];
+    double c[3]; sdom_coord(sd, pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], c);
+    for (int d = 0; d < 3; ++d) index[3 * i + d] = coord2index1(c[d], sd.max[d]);
+}
+
+__global__ void k_accumulate(const unsigned char* geo_blob, GeometryView gv, int rows, long long n, const int32_t* sdom,
+                             const double* bpos, const double* epos, const double* amount, double* field) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const DSdom* sds = reinterpret_cast<const DSdom*>(geo_blob + gv.off_sdom);
+    const DSdom& sd = sds[sdom[i]];
+    const double* a = amount + (long long)rows * i;
+    // generic row count: deposit one component at a time (same weights, same order per component)
+    for (int r = 0; r < rows; ++r)
+        accumulate<1, false>(sd, field, rows, r, bpos[3 * i], bpos[3 * i + 1], bpos[3 * i + 2],
+                      epos[3 * i], epos[3 * i + 1], epos[3 * i + 2], a + r);
+}
+
+// the device generator's words for one (seed, particle, event, block) — behind mcb_philox_words
+__global__ void k_philox(unsigned long long seed, unsigned long long pid, uint32_t event, uint32_t block, uint32_t* out) {
+    uint32_t w[4];
+    philox4x32_10((uint32_t)pid, (uint32_t)(pid >> 32), event, block, (uint32_t)seed, (uint32_t)(seed >> 32), w);
+    for (int i = 0; i < 4; ++i) out[i] = w[i];
+}
+
+// scatter the slot state to per-particle trace arrays (slot order is not particle order)
+__global__ void k_gather_trace(StateSoA st, long long nslots, unsigned long long n_begin, long long n, int np,
+                               const unsigned char* geo_blob, GeometryView gv,
+                               double* pos, double* dir, double* sn, long long* w, long long* p, int32_t* sign,
+                               int32_t* alive, int32_t* sdom, long long* nscat, long long* steps, int32_t* cell) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nslots) return;
+    const unsigned long long meta = st.meta[i], ps = st.pidstep[i];
+    const long long o = (long long)(MCB_PID(ps) - n_begin);
+    if (o < 0 || o >= n) return;
+    pos[3 * o] = st.px[i]; pos[3 * o + 1] = st.py[i]; pos[3 * o + 2] = st.pz[i];
+    dir[3 * o] = st.dx[i]; dir[3 * o + 1] = st.dy[i]; dir[3 * o + 2] = st.dz[i];
+    sn[o] = st.sn[i];
+    const uint32_t wp = MCB_META_WP(meta);
+    w[o] = wp / np; p[o] = wp % np;
+    sign[o] = MCB_META_SIGN(meta) ? 1 : -1;
+    alive[o] = MCB_META_KILLED(meta) ? 0 : 1;
+    sdom[o] = (int32_t)MCB_META_SDOM(meta);
+    nscat[o] = MCB_META_NSCAT(meta);
+    steps[o] = MCB_STEP(ps);
+    const DSdom* sds = reinterpret_cast<const DSdom*>(geo_blob + gv.off_sdom);
+    const DSdom& sd = sds[MCB_META_SDOM(meta)];
+    double c[3]; sdom_coord(sd, st.px[i], st.py[i], st.pz[i], c);
+    for (int d = 0; d < 3; ++d) cell[3 * o + d] = (int32_t)coord2index1(c[d], sd.max[d]);
+}
+
+} // namespace mcb

@@ -1,0 +1,55 @@
+"""Shared problem zoo for the parity tests: every shipped box domain of the reference
+(domain.cpp: Bulk, Film, Jct, Tee, Tube) plus the two box variants BASELINE.json's configs need
+(isothermal-wall slab, diffuse wire)."""
+import numpy as np
+
+from montecarlocpp_b200 import abi
+from oracle import pyoracle as orc
+
+S, D, I, ISO, P = abi.BDRY_SPEC, abi.BDRY_DIFF, abi.BDRY_INTER, abi.BDRY_ISOT, abi.BDRY_PERI
+
+
+def slab(L=100e-9, W=100e-9, ncell=20, dT=1.0):
+    """C2: Parallelepiped<IsotP,Spec,Spec> between walls at +-dT/2."""
+    return orc.Domain.box([0, 0, 0], [L, W, W], [ncell, 0, 0], [0, 0, 0], [ISO, S, S, ISO, S, S],
+                          [dT / 2, 0, 0, -dT / 2, 0, 0])
+
+
+def wire(L=1e-6, W=100e-9, n=8):
+    """C3: Parallelepiped<PeriP,Diff,Diff> with a 2-D tally grid over the cross-section."""
+    return orc.Domain.box([0, 0, 0], [L, W, W], [0, n, n], [-1e6, 0, 0], [P, D, D, P, D, D])
+
+
+def skew(ncell=(3, 4, 5)):
+    """A sheared parallelepiped (non-diagonal mat_) with a 3-D tally grid and mixed walls."""
+    mat = np.array([[1e-7, 2e-8, 1e-8], [0, 1.2e-7, 3e-8], [0, 0, 0.9e-7]])
+    return orc.Domain.box([1e-8, -2e-8, 3e-8], mat, list(ncell), [-2e6, 1e6, 5e5], [D, S, D, S, D, S])
+
+
+def bulk(L=1e-6, div=(10, 0, 0)):
+    return orc.Domain.create("bulk", [L, L, L], list(div), 1e6 * L)
+
+
+def film(L=1e-6, t=100e-9, ncell=20):
+    return orc.Domain.create("film", [L, t, L], [0, ncell, 0], 1e6 * L)
+
+
+def jct(a=1e-7, h=5e-8, div=(2, 3, 2, 2)):
+    return orc.Domain.create("jct", [a, a, a, h], list(div), 2e6 * a)
+
+
+def tee(a=1e-7, h=5e-8, div=(2, 2, 2, 2, 0)):
+    return orc.Domain.create("tee", [a, a, a, a, h], list(div), 3e6 * a)
+
+
+def tube(L=1e-6, a=5e-8, t=2e-8, div=(0, 8, 8, 4)):
+    return orc.Domain.create("tube", [L, a, a, t], list(div), 1e6 * L)
+
+
+DOMAINS = {"slab": slab, "wire": wire, "skew": skew, "bulk": bulk, "film": film, "jct": jct, "tee": tee, "tube": tube}
+
+
+def upload(ctx, mat, dom):
+    ctx.upload_material(mat.desc)
+    ctx.upload_domain(dom.desc)
+    return ctx

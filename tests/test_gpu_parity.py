@@ -1,0 +1,216 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (include/mcb.h), against the CPU oracle
+on the same seeded inputs.  Bars: integer work bit-exact; fp64 state within 1e-11
+relative in Philox mode (libm vs CUDA log/sincos and FMA contraction differ by ulps); tally fields
+within 1e-9 of the field scale (atomic summation order)."""
+import numpy as np
+import pytest
+
+from montecarlocpp_b200 import abi, capi
+from oracle import pyoracle as orc
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+SEED = 0x5EED0000
+
+
+def test_philox_device_words_match_random123_kat():
+    # Random123 kat_vectors: philox4x32-10
+    assert capi.philox_words(0, 0, 0, 0) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert capi.philox_words(0xffffffffffffffff, 0xffffffffffffffff, 0xffffffff, 0xffffffff) == \
+        [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert capi.philox_words(0x299f31d0a4093822, 0x85a308d3243f6a88, 0x13198a2e, 0x03707344) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    assert capi.philox_words(SEED, 12345, 7, 1) == orc.philox_words(SEED, 12345, 7, 1)
+
+
+@pytest.mark.parametrize("mname", ["grey", "silicon"])
+def test_alias_tables_bit_exact(gpu_ctx, omats, mname):
+    mat = omats[mname]
+    gpu_ctx.upload_material(mat.desc)
+    for which in (0, 1):
+        a, b = gpu_ctx.alias(which), mat.alias(which)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("dname", ["film", "skew", "tube", "wire"])
+def test_cell_index_bit_exact(gpu_ctx, omats, dname):
+    dom = cases.DOMAINS[dname]()
+    cases.upload(gpu_ctx, omats["grey"], dom)
+    rng = np.random.default_rng(1)
+    n = 200000
+    nsd = dom.desc.nsdom
+    sd = rng.integers(0, nsd, n).astype(np.int32)
+    pos = np.zeros((n, 3))
+    for s in range(nsd):
+        S = dom.desc.sdoms[s]
+        o = np.array(S.origin[:]); m = np.array(S.mat[:]).reshape(3, 3).T
+        k = sd == s
+        u = rng.uniform(-0.05, 1.05, (k.sum(), 3))
+        # a third of the points exactly on cell faces (the floor() boundary)
+        shape = np.array(S.shape[:], float)
+        snap = rng.random(k.sum()) < 0.33
+        u[snap] = np.round(u[snap] * shape) / shape
+        pos[k] = o + u @ m.T
+    assert np.array_equal(gpu_ctx.cell_index(pos, sd), dom.cell_index(pos, sd))
+
+
+@pytest.mark.parametrize("dname,rows", [("film", 4), ("slab", 1), ("wire", 4), ("skew", 3), ("tube", 4), ("bulk", 3)])
+def test_accumulate_matches_oracle(gpu_ctx, omats, dname, rows):
+    """Field::accumulate (field.cpp:92-220): 1-D shares and the N-D crossing walk."""
+    dom = cases.DOMAINS[dname]()
+    cases.upload(gpu_ctx, omats["grey"], dom)
+    rng = np.random.default_rng(2)
+    n = 20000
+    nsd = dom.desc.nsdom
+    sd = rng.integers(0, nsd, n).astype(np.int32)
+    b = np.zeros((n, 3)); e = np.zeros((n, 3))
+    for s in range(nsd):
+        S = dom.desc.sdoms[s]
+        o = np.array(S.origin[:]); m = np.array(S.mat[:]).reshape(3, 3).T
+        k = sd == s
+        ub = rng.uniform(0, 1, (k.sum(), 3)); ue = rng.uniform(0, 1, (k.sum(), 3))
+        short = rng.random(k.sum()) < 0.5
+        ue[short] = np.clip(ub[short] + rng.normal(0, 0.03, (short.sum(), 3)), 0, 1)
+        axis = rng.random(k.sum()) < 0.1          # axis-aligned segments: dcoord == 0 on two axes
+        ue[axis, 1:] = ub[axis, 1:]
+        b[k] = o + ub @ m.T; e[k] = o + ue @ m.T
+    amt = rng.normal(0, 1, (n, rows))
+    got = gpu_ctx.accumulate(rows, sd, b, e, amt)
+    ref = dom.accumulate(rows, sd, b, e, amt)
+    scale = np.abs(ref).max()
+    assert np.abs(got - ref).max() <= 1e-11 * scale
+    # the tally conserves the deposited amount (field.cpp:134-154 shares sum to `amount`)
+    assert np.allclose(got.sum(axis=1), amt.sum(axis=0), rtol=1e-9, atol=1e-9 * np.abs(amt).sum())
+
+
+TRACE_CASES = [("grey", "slab", "multi", 50), ("silicon", "film", "multi", 40), ("grey", "bulk", "flux", 30),
+               ("silicon", "jct", "temp", 60), ("grey", "tee", "multi", 60), ("silicon", "tube", "multi", 60),
+               ("grey", "wire", "flux", 40), ("silicon_small", "skew", "multi", 40)]
+
+
+@pytest.mark.parametrize("mname,dname,pkind,nsteps", TRACE_CASES)
+def test_trace_state_parity(gpu_ctx, omats, mname, dname, pkind, nsteps):
+    """KA6: per-particle (sdom, cell, nscat, alive, steps, w, p, sign) identical, fp state to ulps."""
+    mat, dom = omats[mname], cases.DOMAINS[dname]()
+    cases.upload(gpu_ctx, mat, dom)
+    prob = orc.Problem(mat, dom, pkind, 4000, 20)
+    for k in (0, 1, nsteps):
+        ref = prob.trace(SEED, 0, prob.nemit, k)
+        got = gpu_ctx.trace(prob.desc, SEED, 0, prob.nemit, k)
+        for key in ("w", "p", "sign", "alive", "sdom", "nscat", "steps", "cell"):
+            assert np.array_equal(got[key], ref[key]), (key, k)
+        scale = np.abs(ref["pos"]).max()
+        assert np.abs(got["pos"] - ref["pos"]).max() <= 1e-11 * scale, k
+        assert np.abs(got["dir"] - ref["dir"]).max() <= 1e-11, k
+        assert np.allclose(got["scat_next"], ref["scat_next"], rtol=1e-10, atol=1e-11 * scale), k
+
+
+SOLVE_CASES = [("grey", "slab", "multi", 0), ("grey", "slab", "temp", 0), ("silicon", "film", "multi", 0),
+               ("grey", "bulk", "flux", 0), ("silicon", "jct", "multi", 0), ("grey", "tee", "multi", 0),
+               ("silicon", "tube", "multi", 0), ("grey", "wire", "multi", 0), ("silicon_small", "skew", "flux", 0),
+               ("grey", "film", "cumtemp", 4), ("silicon", "slab", "cumflux", 3)]
+
+
+@pytest.mark.parametrize("mname,dname,pkind,size", SOLVE_CASES)
+def test_solve_matches_oracle_philox(gpu_ctx, omats, mname, dname, pkind, size):
+    """FieldProblem::solve end to end with the shared Philox streams: counters exact, field to 1e-9."""
+    mat, dom = omats[mname], cases.DOMAINS[dname]()
+    cases.upload(gpu_ctx, mat, dom)
+    gpu_ctx.set_options(slots=0, steps_per_launch=0, tally_mode=0)
+    prob = orc.Problem(mat, dom, pkind, 20000, 30, size=size)
+    ref, rst = prob.solve(rng=orc.RNG_PHILOX, seed=SEED)
+    got, gst = gpu_ctx.solve(prob.desc, seed=SEED)
+    assert gst["emitted"] == rst["emitted"] == prob.nemit
+    assert gst["steps"] == rst["steps"]
+    assert gst["esc"] == rst["esc"]
+    if dname in ("slab", "wire", "skew", "bulk", "film"):
+        assert gst["esc"] == 0                     # KA5: no escapes on single-box domains
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    assert (np.abs(got - ref) <= 1e-9 * scale).all()
+
+
+@pytest.mark.parametrize("opts", [dict(steps_per_launch=1, slots=4096), dict(steps_per_launch=7, slots=1000),
+                                  dict(steps_per_launch=64, slots=0, tally_mode=2), dict(block=128, ctas_per_sm=4, slots=30000)])
+def test_schedule_options_do_not_change_results(gpu_ctx, omats, opts):
+    """Slots / S / tally mode are scheduling only: Philox keyed by particle id makes the result
+    independent of them (up to fp summation order)."""
+    mat, dom = omats["silicon"], cases.film()
+    cases.upload(gpu_ctx, mat, dom)
+    prob = orc.Problem(mat, dom, "multi", 30000, 25)
+    gpu_ctx.set_options(slots=0, steps_per_launch=0, block=0, ctas_per_sm=0, tally_mode=0)
+    base, bst = gpu_ctx.solve(prob.desc, seed=SEED)
+    gpu_ctx.set_options(**{**dict(slots=0, steps_per_launch=0, block=0, ctas_per_sm=0, tally_mode=0), **opts})
+    got, gst = gpu_ctx.solve(prob.desc, seed=SEED)
+    gpu_ctx.set_options(slots=0, steps_per_launch=0, block=0, ctas_per_sm=0, tally_mode=0)
+    assert (gst["steps"], gst["esc"], gst["emitted"]) == (bst["steps"], bst["esc"], bst["emitted"])
+    scale = np.abs(base).max(axis=1, keepdims=True)
+    assert (np.abs(got - base) <= 1e-9 * scale).all()
+
+
+def test_particle_ranges_add_up(gpu_ctx, omats):
+    """solve([0,n)) == solve([0,k)) + solve([k,n)): the per-thread partial sums of main.cpp:162-165
+    and the per-GPU shards of the multi-GPU path."""
+    mat, dom = omats["grey"], cases.slab()
+    cases.upload(gpu_ctx, mat, dom)
+    prob = orc.Problem(mat, dom, "multi", 40000, 50)
+    full, fst = gpu_ctx.solve(prob.desc, seed=SEED)
+    k = 12345
+    a, ast = gpu_ctx.solve(prob.desc, seed=SEED, n_begin=0, n_end=k)
+    b, bst = gpu_ctx.solve(prob.desc, seed=SEED, n_begin=k, n_end=prob.nemit)
+    assert ast["steps"] + bst["steps"] == fst["steps"]
+    assert ast["emitted"] == k and bst["emitted"] == prob.nemit - k
+    scale = np.abs(full).max(axis=1, keepdims=True)
+    assert (np.abs(a + b - full) <= 1e-9 * scale).all()
+    empty, est = gpu_ctx.solve(prob.desc, seed=SEED, n_begin=7, n_end=7)
+    assert est["steps"] == 0 and not empty.any()
+
+
+def test_statistical_parity_with_mt19937_oracle(gpu_ctx, omats):
+    """North-star bar: T and q profiles within 3 sigma of batch-means error against the oracle run
+    with the reference's own RNG family (mt19937), k_eff within 1 %."""
+    mat, dom = omats["grey"], cases.slab(ncell=10)
+    cases.upload(gpu_ctx, mat, dom)
+    prob = orc.Problem(mat, dom, "multi", 100000, 200)
+    B = 8
+    g = np.stack([gpu_ctx.solve(prob.desc, seed=SEED + b)[0] for b in range(B)])
+    r = np.stack([prob.solve(rng=orc.RNG_MT19937, seed=1000 + 17 * b)[0] for b in range(B)])
+    mg, mr = g.mean(0), r.mean(0)
+    se = np.sqrt(g.var(0, ddof=1) / B + r.var(0, ddof=1) / B)
+    z = np.abs(mg - mr)[:2] / se[:2]              # T and q_x rows
+    assert (z < 4.0).all() and (z < 3.0).mean() > 0.9
+    qg, qr = mg[1].mean(), mr[1].mean()
+    assert abs(qg / qr - 1.0) < 0.01
+
+
+def test_bulk_conductivity_within_one_percent(gpu_ctx, omats):
+    """KA1: <q_x>/|grad T| -> Material::cond() (material.cpp:160-161)."""
+    for mname in ("grey", "silicon"):
+        mat, dom = omats[mname], cases.bulk()
+        cases.upload(gpu_ctx, mat, dom)
+        # maxscat = 1: only the first flight carries signal (later flights are isotropic, zero-mean noise)
+        prob = orc.Problem(mat, dom, "flux", 16000000, 1)
+        sol, st = gpu_ctx.solve(prob.desc, seed=SEED)
+        k = sol[0].mean() / 1e6
+        assert st["esc"] == 0
+        assert abs(k / mat.cond() - 1.0) < 0.01, (mname, k, mat.cond())
+
+
+def test_error_behaviour(omats):
+    ctx = capi.Context(0)
+    mat, dom = omats["grey"], cases.slab()
+    prob = orc.Problem(mat, dom, "multi", 1000, 10)
+    ctx.cols = 1
+    with pytest.raises(capi.McbError) as e:       # solve before upload
+        ctx.solve(prob.desc)
+    assert e.value.code == abi.MCB_ESTATE
+    cases.upload(ctx, mat, dom)
+    bad = abi.ProblemDesc.from_buffer_copy(prob.desc)
+    bad.rows = 3
+    with pytest.raises(capi.McbError) as e:
+        ctx.solve(bad)
+    assert e.value.code == abi.MCB_EINVAL
+    with pytest.raises(capi.McbError):
+        ctx.solve(prob.desc, n_begin=5, n_end=2)
+    ctx.close()
