@@ -1,0 +1,279 @@
+#!/usr/bin/env python
+"""bench.py — phonon-steps/s of the FieldProblem::solve hot path on N B200s (one process per GPU).
+
+A "step" of this benchmark is ONE pass of the hot path over one batch of synthetic phonons: a full
+`FieldProblem::solve` of BASELINE.json configs[1] ("1D cross-plane Si thin film 100 nm at 300 K, 1e7
+phonons", pinned in SURVEY.md §8d as C2: slab between isothermal walls at +-0.5 K, 100 cells, Multi
+tally, maxscat 1000, Si-like full dispersion nw=1000 x np=3).  The metric is phonon-steps/s where one
+phonon-step is one trip of the loop body problem.cpp:401-435.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode resident|streaming]
+
+Arms
+  ours       the CUDA path through the C++ host mirror + C ABI (no oracle on this path).
+  reference  the reference's CPU algorithm (the oracle port; the reference itself cannot be built here:
+             Eigen + Boost are absent) on all host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_ALG = 128.0            # algorithmic bytes per phonon-step (64 B state read + 64 B write)
+WORKLOADS = {
+    # name: (domain kind, dim, div, dT, problem, maxscat, material)
+    "C2-slab100nm-si": ("slab", [100e-9, 100e-9, 100e-9], [100, 0, 0], 1.0, "multi", 1000, "silicon"),
+    "C2-slab100nm-grey": ("slab", [100e-9, 100e-9, 100e-9], [100, 0, 0], 1.0, "multi", 1000, "grey"),
+    "C1-film100nm-si": ("film", [1e-6, 100e-9, 1e-6], [0, 20, 0], 1.0, "multi", 100, "silicon"),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2-slab100nm-si", choices=sorted(WORKLOADS))
+    ap.add_argument("--nemit", type=int, default=10_000_000, help="phonons per GPU per step")
+    ap.add_argument("--mode", default="resident", choices=["resident", "streaming"],
+                    help="resident: S loop trips per state load/store (library default); streaming: S=1")
+    ap.add_argument("--cpu-sample", type=int, default=500_000, help="phonons in the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def material_files(kind):
+    from montecarlocpp_b200 import materials
+    d = tempfile.mkdtemp(prefix="mcb_mat_")
+    return materials.write_grey(d) if kind == "grey" else materials.write_silicon(d, nw=1000)
+
+
+def cpu_reference_rate(workload, nemit_total, sample, seed, threads=0):
+    """The reference's CPU algorithm (oracle port, OpenMP like main.cpp:155 + problem.cpp:383) on a bounded
+    sample [0, sample) of the same problem.  Only this leg (and tests / smoke) may touch oracle/."""
+    from oracle import pyoracle as orc
+    kind, dim, div, dT, pkind, maxscat, mkind = WORKLOADS[workload]
+    mat = orc.Material(*material_files(mkind))
+    if kind == "slab":
+        from montecarlocpp_b200 import abi
+        dom = orc.Domain.box([0, 0, 0], dim, div, [0, 0, 0], [abi.BDRY_ISOT, abi.BDRY_SPEC, abi.BDRY_SPEC] * 2,
+                             [dT / 2, 0, 0, -dT / 2, 0, 0])
+    else:
+        dom = orc.Domain.create(kind, dim, div, dT)
+    prob = orc.Problem(mat, dom, pkind, nemit_total, maxscat)
+    n = min(sample, prob.nemit)
+    t0 = time.perf_counter()
+    _, st = prob.solve(rng=orc.RNG_MT19937, seed=seed, n_begin=0, n_end=n, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return st["steps"] / dt, dt, st["steps"], orc.max_threads() if threads == 0 else threads, n
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    rates, t_all = [], []
+    cores = None
+    for i in range(args.warmup + args.steps):
+        rate, dt, steps, cores, n = cpu_reference_rate(args.workload, args.nemit * args.gpus, args.cpu_sample, 1000 + i)
+        if i >= args.warmup:
+            rates.append(rate); t_all.append(dt)
+    total_rate = sum(rates) / len(rates)
+    sample = f"{n} of {args.nemit * args.gpus} phonons of {args.workload} per step, mt19937, OpenMP static, {cores} threads"
+    line = {
+        "impl": "reference", "metric": "phonon_steps_per_s", "value": total_rate, "unit": "phonon-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(t_all) / len(t_all),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "nemit_per_gpu": args.nemit, "note": "CPU port of the reference algorithm "
+                   "(oracle); the reference itself needs Eigen+Boost and cannot be built in this image"},
+        "cpu_baseline": {"value": total_rate, "unit": "phonon-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": total_rate, "unit": "phonon-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from montecarlocpp_b200 import capi, hostapi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    kind, dim, div, dT, pkind, maxscat, mkind = WORKLOADS[args.workload]
+    disp, relax = material_files(mkind)
+    mat = hostapi.Material(disp, relax, 300.0)
+    dom = hostapi.Domain(kind, dim, div, dT)
+    n_total = args.nemit * world                       # weak scaling: per-GPU work fixed
+    prob = hostapi.FieldProblem(mat, dom, pkind, n_total, maxscat)
+    per = (prob.nemit + world - 1) // world
+    n_begin, n_end = rank * per, min(prob.nemit, (rank + 1) * per)
+
+    ctx = capi.Context(local)
+    ctx.upload_material(mat.desc)
+    ctx.upload_domain(dom.desc)
+    S = 1 if args.mode == "streaming" else 16
+    ctx.set_options(steps_per_launch=S)
+    raw = torch.zeros(prob.rows * dom.cols, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+
+    def one_step(seed):
+        raw.zero_()
+        torch.cuda.synchronize()
+        st = ctx.solve_raw_dev(prob.desc, raw.data_ptr(), seed=seed, n_begin=n_begin, n_end=n_end)
+        if world > 1:
+            dist.all_reduce(raw)                       # the per-solve field reduction (main.cpp:162-165) over NCCL
+        ctx.finalize_dev(prob.desc, raw.data_ptr())
+        return st
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        one_step(100 + i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    tot = {"steps": 0, "launches": 0, "step_ms": 0.0, "step_launches": 0, "state_stores": 0, "device_ms": 0.0, "esc": 0}
+    for i in range(args.steps):
+        st = one_step(1000 + i)
+        for k in tot:
+            tot[k] += st[k]
+        tot["launches"] += 1                            # finalize kernel
+    barrier()
+    elapsed = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end-to-end arm: the call a user makes, with HOST buffers: tables uploaded, solve, field read back
+    def e2e_step(seed):
+        ctx.upload_material(mat.desc); ctx.upload_domain(dom.desc)
+        sol, st = ctx.solve(prob.desc, seed=seed, n_begin=n_begin, n_end=n_end)
+        return st
+    e2e_step(7)
+    barrier()
+    t1 = time.perf_counter()
+    e2e_steps = 0
+    ke = max(1, min(args.steps, 5))
+    for i in range(ke):
+        e2e_steps += e2e_step(2000 + i)["steps"]
+    barrier()
+    e2e_elapsed = time.perf_counter() - t1
+
+    vals = torch.tensor([elapsed, e2e_elapsed, float(tot["steps"]), float(e2e_steps), float(tot["launches"])],
+                        dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = vals.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = vals.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        elapsed, e2e_elapsed = mx[0].item(), mx[1].item()
+        all_steps, all_e2e_steps, all_launches = sm[2].item(), sm[3].item(), sm[4].item()
+    else:
+        all_steps, all_e2e_steps, all_launches = float(tot["steps"]), float(e2e_steps), float(tot["launches"])
+
+    if rank == 0:
+        nw, npol = mat.desc.nw, mat.desc.np
+        h2d = nw * npol * (8 * 3 + 1) + nw * 10 + nw * npol * 12 + nw * 12 + 2048     # tables + alias + geometry (approx, bytes)
+        d2h = prob.rows * dom.cols * 8
+        # roofline of the dominant kernel (k_step): algorithmic bytes moved / CUDA-event duration, where the
+        # algorithmic bytes are B_alg = 128 B per state round trip (one per phonon-step when S = 1)
+        step_s = tot["step_ms"] * 1e-3
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = tot["state_stores"] * B_ALG / step_s / 1e9 if step_s > 0 else 0.0
+        line = {
+            "metric": "phonon_steps_per_s", "value": all_steps / elapsed, "unit": "phonon-steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "nemit_per_gpu": args.nemit, "maxscat": maxscat, "problem": pkind,
+                       "material": f"{mkind} nw={nw} np={npol}", "mode": args.mode, "steps_per_launch": S,
+                       "l2": "resident state 2.4M slots x 72 B = 175 MB > 126 MB L2 (no flush needed)",
+                       "parallelism": f"phonons sharded over {world} GPU(s); one fp64 all-reduce of the {prob.rows}x{dom.cols} tally per solve"},
+            "clocks": clocks,
+            "e2e": {"value": all_e2e_steps / e2e_elapsed, "unit": "phonon-steps/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "calls": "mcb_upload_material + mcb_upload_domain + mcb_solve (host buffers)"},
+            "gpu_launches": int(all_launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "k_step", "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
+                         "bytes_per_phonon_step": tot["state_stores"] * B_ALG / max(1, tot["steps"]), "kernel_ms_per_launch": tot["step_ms"] / max(1, tot["step_launches"]),
+                         "kernel_share_of_step": tot["step_ms"] * 1e-3 / elapsed,
+                         "note": "B_alg = 128 B per state round trip (SURVEY 8d); resident mode amortises it over S loop trips"},
+            "phonon_steps_per_solve": tot["steps"] / args.steps, "esc": tot["esc"],
+        }
+        if not args.no_cpu_baseline:
+            rate, dt, steps, cores, n = cpu_reference_rate(args.workload, n_total, args.cpu_sample, 4242)
+            line["cpu_baseline"] = {"value": rate, "unit": "phonon-steps/s", "cores": cores, "kind": "port",
+                                    "sample": f"{n} of {n_total} phonons ({steps} phonon-steps, {dt:.1f} s), oracle port, OpenMP"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+    return 0
+
+
+if __name__ == "__main__":
+    a = parse()
+    sys.exit(run_reference(a) if a.impl == "reference" else run_ours(a))

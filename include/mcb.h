@@ -176,7 +176,8 @@ typedef struct mcb_stats {
     double  device_ms;         /* CUDA-event time of the device work                  */
     double  step_ms;           /* CUDA-event time spent in the move-collide kernel    */
     int64_t step_launches;     /* launches of the move-collide kernel                 */
-    int64_t slot_steps;        /* slots visited by the move-collide kernel (>= steps) */
+    int64_t slot_steps;        /* slots visited by the move-collide kernel x S (>= steps) */
+    int64_t state_stores;      /* slot state write-backs (each: <= 72 B load + 72 B store) */
 } mcb_stats;
 
 /* Tunables of the device schedule (not part of the physics). 0 = library default. */

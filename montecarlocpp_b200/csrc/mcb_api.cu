@@ -281,7 +281,7 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
         float ms = 0.f; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
         stats->emitted = (int64_t)c->h_ctr->emitted; stats->steps = (int64_t)c->h_ctr->steps; stats->esc = (int64_t)c->h_ctr->esc;
         stats->launches = launches; stats->cols = c->cols; stats->device_ms = ms; stats->step_ms = step_ms_total;
-        stats->step_launches = step_launches; stats->slot_steps = slot_steps;
+        stats->step_launches = step_launches; stats->slot_steps = slot_steps; stats->state_stores = (int64_t)c->h_ctr->stores;
     }
     return MCB_OK;
 }

@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(512, 1) k_step(const StepParams P) {
     T.nw = P.mv.nw; T.np = P.mv.np;
     T.hist = SMEM ? s_hist : P.field;
 
-    unsigned long long my_steps = 0, my_esc = 0, my_emitted = 0, my_live = 0;
+    unsigned long long my_steps = 0, my_esc = 0, my_emitted = 0, my_live = 0, my_stores = 0;
     bool exhausted = false;
     const unsigned lane = threadIdx.x & 31u;
 
@@ -284,6 +284,7 @@ __global__ void __launch_bounds__(512, 1) k_step(const StepParams P) {
             if (__all_sync(0xFFFFFFFFu, !ph.active && (exhausted || !valid || !P.refill))) break;
         }
         if (valid && dirty) {
+            my_stores++;
             st_stream(P.st.px + i, ph.px); st_stream(P.st.py + i, ph.py); st_stream(P.st.pz + i, ph.pz);
             st_stream(P.st.dx + i, ph.dx); st_stream(P.st.dy + i, ph.dy); st_stream(P.st.dz + i, ph.dz);
             st_stream(P.st.sn + i, ph.sn);
@@ -294,19 +295,21 @@ __global__ void __launch_bounds__(512, 1) k_step(const StepParams P) {
     }
 
     // --- block-level reduction of the counters, one atomic per CTA
-    __shared__ unsigned long long s_red[4];
-    if (threadIdx.x < 4) s_red[threadIdx.x] = 0;
+    __shared__ unsigned long long s_red[5];
+    if (threadIdx.x < 5) s_red[threadIdx.x] = 0;
     __syncthreads();
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         my_steps += __shfl_down_sync(0xFFFFFFFFu, my_steps, o); my_esc += __shfl_down_sync(0xFFFFFFFFu, my_esc, o);
         my_emitted += __shfl_down_sync(0xFFFFFFFFu, my_emitted, o); my_live += __shfl_down_sync(0xFFFFFFFFu, my_live, o);
+        my_stores += __shfl_down_sync(0xFFFFFFFFu, my_stores, o);
     }
     if (lane == 0) {
         if (my_steps) atomicAdd(&s_red[0], my_steps);
         if (my_esc) atomicAdd(&s_red[1], my_esc);
         if (my_emitted) atomicAdd(&s_red[2], my_emitted);
         if (my_live) atomicAdd(&s_red[3], my_live);
+        if (my_stores) atomicAdd(&s_red[4], my_stores);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -314,6 +317,7 @@ __global__ void __launch_bounds__(512, 1) k_step(const StepParams P) {
         if (s_red[1]) atomicAdd(&P.ctr->esc, s_red[1]);
         if (s_red[2]) atomicAdd(&P.ctr->emitted, s_red[2]);
         if (s_red[3]) atomicAdd(&P.ctr->live, s_red[3]);
+        if (s_red[4]) atomicAdd(&P.ctr->stores, s_red[4]);
     }
     // --- flush the block histogram (fp64 RED to L2)
     if (SMEM && P.do_tally)

@@ -1,0 +1,95 @@
+// host_capi.cpp — a small C surface over the C++ host mirror so that tests and bench.py (Python, ctypes)
+// can drive the SAME objects a C++ caller would: Material, the Domain classes, the FieldProblem family.
+// Not part of the reference API; every call maps 1:1 to a constructor or method of the mirror.
+#include <cstring>
+#include <memory>
+#include <string>
+#include "domain.h"
+#include "material.h"
+#include "problem.h"
+
+namespace { thread_local std::string g_err; }
+#define MCBH_TRY(body, fail) try { body } catch (const std::exception& e) { g_err = e.what(); return fail; }
+
+struct mcbh_domain { std::unique_ptr<Domain> dom; FlatDomain flat; };
+struct mcbh_problem { std::unique_ptr<FieldProblem> prob; };
+
+extern "C" {
+
+const char* mcbh_last_error(void) { return g_err.c_str(); }
+
+Material* mcbh_material_create(const char* disp, const char* relax, double temp) {
+    MCBH_TRY(return new Material(disp, relax, temp);, nullptr)
+}
+void mcbh_material_free(Material* m) { delete m; }
+int mcbh_material_desc(const Material* m, mcb_material_desc* out) { if (!m || !out) return MCB_EINVAL; *out = m->desc(); return MCB_OK; }
+double mcbh_material_cond(const Material* m) { return m->cond(); }
+
+// kind: bulk film slab wire (3 dims, 3 divs) | jct tube (4, 4) | tee (5, 5): the constructor vectors
+mcbh_domain* mcbh_domain_create(const char* kind, const double* dim, int ndim, const int64_t* div, int ndiv, double dT) {
+    MCBH_TRY(
+        std::string k(kind);
+        VectorXd d(dim, dim + ndim); VectorXl v(div, div + ndiv);
+        std::unique_ptr<mcbh_domain> h(new mcbh_domain);
+        auto need = [&](size_t nd, size_t nv) { MC_ASSERT_MSG(d.size() == nd && v.size() == nv, "wrong number of dims/divs for domain " + k); };
+        if (k == "bulk" || k == "film" || k == "slab" || k == "wire") {
+            need(3, 3);
+            Vector3d D(d[0], d[1], d[2]); Vector3l V(v[0], v[1], v[2]);
+            if (k == "bulk") h->dom.reset(new BulkDomain(D, V, dT));
+            else if (k == "film") h->dom.reset(new FilmDomain(D, V, dT));
+            else if (k == "slab") h->dom.reset(new SlabDomain(D, V, dT));
+            else h->dom.reset(new WireDomain(D, V, dT));
+        } else if (k == "jct") { need(4, 4); h->dom.reset(new JctDomain(d, v, dT)); }
+        else if (k == "tee") { need(5, 5); h->dom.reset(new TeeDomain(d, v, dT)); }
+        else if (k == "tube") { need(4, 4); h->dom.reset(new TubeDomain(d, v, dT)); }
+        else MC_ASSERT_MSG(false, "Invalid domain");
+        h->flat = flattenDomain(h->dom.get());
+        return h.release();
+    , nullptr)
+}
+void mcbh_domain_free(mcbh_domain* d) { delete d; }
+int mcbh_domain_desc(const mcbh_domain* d, mcb_domain_desc* out) { if (!d || !out) return MCB_EINVAL; *out = d->flat.desc(); return MCB_OK; }
+int64_t mcbh_domain_cols(const mcbh_domain* d) { return d->flat.cols; }
+
+mcbh_problem* mcbh_problem_create(const Material* mat, const mcbh_domain* dom, int kind, int64_t nemit, int64_t size,
+                                  int64_t maxscat, int64_t maxloop) {
+    MCBH_TRY(
+        MC_ASSERT_MSG(mat && dom, "Null material or domain");
+        std::unique_ptr<mcbh_problem> h(new mcbh_problem);
+        const Domain* D = dom->dom.get();
+        switch (kind) {
+        case MCB_PROB_TEMP: h->prob.reset(new TempProblem(mat, D, nemit, maxscat, maxloop)); break;
+        case MCB_PROB_FLUX: h->prob.reset(new FluxProblem(mat, D, nemit, maxscat, maxloop)); break;
+        case MCB_PROB_MULTI: h->prob.reset(new MultiProblem(mat, D, nemit, maxscat, maxloop)); break;
+        case MCB_PROB_CUMTEMP: h->prob.reset(new CumTempProblem(mat, D, nemit, size, maxscat, maxloop)); break;
+        case MCB_PROB_CUMFLUX: h->prob.reset(new CumFluxProblem(mat, D, nemit, size, maxscat, maxloop)); break;
+        default: MC_ASSERT_MSG(false, "Invalid problem");
+        }
+        return h.release();
+    , nullptr)
+}
+void mcbh_problem_free(mcbh_problem* p) { delete p; }
+int mcbh_problem_desc(const mcbh_problem* p, mcb_problem_desc* out) { if (!p || !out) return MCB_EINVAL; *out = p->prob->desc(); return MCB_OK; }
+
+// FieldProblem::solve(gen, prog) with gen = mt19937(mt_seed), exactly as a C++ caller would invoke it
+int mcbh_problem_solve(const mcbh_problem* p, int device, uint32_t mt_seed, double* out, mcb_stats* stats) {
+    MCBH_TRY(
+        FieldProblem::device(device);
+        Rng gen(mt_seed);
+        ArrayXXd sol = p->prob->solve(gen, nullptr);
+        std::memcpy(out, sol.data(), sizeof(double) * (size_t)sol.size());
+        if (stats) *stats = FieldProblem::lastStats();
+        return MCB_OK;
+    , MCB_EINVAL)
+}
+int mcbh_problem_solve_seeded(const mcbh_problem* p, int device, uint64_t seed, int64_t n_begin, int64_t n_end, double* out, mcb_stats* stats) {
+    MCBH_TRY(
+        FieldProblem::device(device);
+        ArrayXXd sol = p->prob->solveSeeded(seed, n_begin, n_end, nullptr);
+        std::memcpy(out, sol.data(), sizeof(double) * (size_t)sol.size());
+        if (stats) *stats = FieldProblem::lastStats();
+        return MCB_OK;
+    , MCB_EINVAL)
+}
+
+} // extern "C"

@@ -1,0 +1,145 @@
+// main.cpp — command-line driver with the reference's positional grammar and stdout blocks
+// (main.cpp:67-84 printSolution, :146-210 solveField / calcStats, :216-479 argument grammar).
+//
+//   <dir> <material> [T] <domain> <dims...> <divs...> <problem> <nemit> [size] <maxscat> <maxloop> <nsim>
+//
+//   grey|silicon [T] | custom [T] disp relax
+//   bulk dim div0 | film dim0 dim1 div1 | jct dim0 dim3 | tee dim0 dim4 div0 | tube dim0 dim1 dim3 div1 div3
+//   slab dim0 dim1 div0 dT | wire dim0 dim1 div1        (not in the reference; see domain.h)
+//   temp|flux|multi nemit maxscat maxloop nsim | cumtemp|cumflux nemit size maxscat maxloop nsim
+//
+// Differences from the reference driver: the solve runs on the GPU and is called once per repetition from
+// the main thread (the reference opens an OpenMP region and sums per-thread partials); `check`/`traj`
+// (TrajProblem) and the hex/pyr/octet domains are not built.
+#include <unistd.h>
+#include <iomanip>
+#include <iostream>
+#include <sstream>
+#include <vector>
+#include "domain.h"
+#include "field.h"
+#include "material.h"
+#include "problem.h"
+#include "random.h"
+
+typedef Dev::result_type Seed;
+
+#ifdef DEBUG
+static Seed getSeed() { static Seed s(0); return s++; }
+#else
+static Seed getSeed() { static Dev urandom; return urandom(); }
+#endif
+
+static void printSolution(const ArrayXXd& sol) {
+    std::ios_base::fmtflags mask = std::cout.flags();
+    std::cout << std::scientific << std::setprecision(9);
+    for (long i = 0; i < sol.rows(); ++i) {
+        for (long j = 0; j < sol.cols(); ++j) std::cout << std::setw(16) << sol(i, j) << ' ';
+        std::cout << std::endl;
+    }
+    std::cout << std::endl;
+    std::cout.flags(mask);
+}
+
+static ArrayXXd solveField(const FieldProblem* prob, const Clock& clk) {
+    static long n = 0;
+    std::cout << "Solution " << n++ << std::endl;
+    Progress prog = prob->initProgress();
+    prog.clock(clk);
+    Seed s = getSeed();
+    std::cout << "  seeds: " << s << ' ' << std::endl;
+    Rng gen(s);
+    ArrayXXd sol = prob->solve(gen, &prog);
+    std::cout << "Output" << std::endl;
+    printSolution(sol);
+    ArrayXXd avg = prob->dom()->average(sol);
+    if (avg != sol) { std::cout << "Averaged" << std::endl; printSolution(avg); }
+    return avg;
+}
+
+static Statistics<ArrayXXd> calcStats(const std::vector<ArrayXXd>& sol) {
+    Statistics<ArrayXXd> stats(ArrayXXd::Zero(sol.front().rows(), sol.front().cols()));
+    for (const ArrayXXd& s : sol) stats.add(s);
+    std::cout << "Mean" << std::endl;
+    printSolution(stats.mean());
+    std::cout << "Standard Deviation" << std::endl;
+    printSolution(stats.variance().sqrt());
+    return stats;
+}
+
+int main(int argc, const char* argv[]) {
+    std::stringstream argss;
+    for (int i = 1; i < argc; ++i) argss << argv[i] << ' ';
+    std::cout << std::string(40, '-') << std::endl;
+    Clock clk;
+    std::cout << clk.timestamp() << std::endl;
+#ifdef DEBUG
+    std::cout << "DEBUG" << std::endl;
+#endif
+    std::cout << argss.str() << std::endl << std::endl;
+    try {
+        std::string prefix; argss >> prefix;
+        MC_ASSERT_MSG(chdir(prefix.c_str()) == 0, "Invalid directory");
+
+        std::string matStr; argss >> matStr;
+        double T = 300.; argss >> T;
+        std::unique_ptr<Material> mat;
+        if (matStr == "grey") mat.reset(new Material("grey_disp.txt", "grey_relax2.txt", T));
+        else if (matStr == "silicon") mat.reset(new Material("Si_disp.txt", "Si_relax2.txt", T));
+        else if (matStr == "custom") { std::string disp, relax; argss >> disp >> relax; mat.reset(new Material(disp, relax, T)); }
+        else MC_ASSERT_MSG(false, "Invalid material");
+        MC_ASSERT_MSG(!argss.fail(), "Invalid material arguments");
+        std::cout << *mat << std::endl << std::endl;
+
+        std::string domStr; argss >> domStr;
+        std::unique_ptr<Domain> dom;
+        if (domStr == "bulk") {
+            double d0; long v0; argss >> d0 >> v0;
+            dom.reset(new BulkDomain(Vector3d(d0, d0, d0), Vector3l(v0, 0, 0), 1e6 * d0));
+        } else if (domStr == "film") {
+            double d0, d1; long v1; argss >> d0 >> d1 >> v1;
+            dom.reset(new FilmDomain(Vector3d(d0, d1, d0), Vector3l(0, v1, 0), 1e6 * d0));
+        } else if (domStr == "slab") {
+            double d0, d1, dT; long v0; argss >> d0 >> d1 >> v0 >> dT;
+            dom.reset(new SlabDomain(Vector3d(d0, d1, d1), Vector3l(v0, 0, 0), dT));
+        } else if (domStr == "wire") {
+            double d0, d1; long v1; argss >> d0 >> d1 >> v1;
+            dom.reset(new WireDomain(Vector3d(d0, d1, d1), Vector3l(0, v1, v1), 1e6 * d0));
+        } else if (domStr == "jct") {
+            double d0, d3; argss >> d0 >> d3;
+            dom.reset(new JctDomain(VectorXd{d0, d0, d0, d3}, VectorXl{0, 0, 0, 0}, 2e6 * d0));
+        } else if (domStr == "tee") {
+            double d0, d4; long v0; argss >> d0 >> d4 >> v0;
+            dom.reset(new TeeDomain(VectorXd{d0, d0, d0, d0, d4}, VectorXl{v0, v0, v0, v0, 0}, 3e6 * d0));
+        } else if (domStr == "tube") {
+            double d0, d1, d3; long v1, v3; argss >> d0 >> d1 >> d3 >> v1 >> v3;
+            dom.reset(new TubeDomain(VectorXd{d0, d1, d1, d3}, VectorXl{0, v1, v1, v3}, 1e6 * d0));
+        } else MC_ASSERT_MSG(false, "Invalid domain");
+        MC_ASSERT_MSG(!argss.fail(), "Invalid domain arguments");
+        std::cout << *dom << std::endl << std::endl;
+
+        std::string probStr; argss >> probStr;
+        long nemit = 0, size = 0, maxscat = 0, maxloop = 0, nsim = 0;
+        std::unique_ptr<FieldProblem> prob;
+        if (probStr == "temp") { argss >> nemit >> maxscat >> maxloop >> nsim; prob.reset(new TempProblem(mat.get(), dom.get(), nemit, maxscat, maxloop)); }
+        else if (probStr == "flux") { argss >> nemit >> maxscat >> maxloop >> nsim; prob.reset(new FluxProblem(mat.get(), dom.get(), nemit, maxscat, maxloop)); }
+        else if (probStr == "multi") { argss >> nemit >> maxscat >> maxloop >> nsim; prob.reset(new MultiProblem(mat.get(), dom.get(), nemit, maxscat, maxloop)); }
+        else if (probStr == "cumtemp") { argss >> nemit >> size >> maxscat >> maxloop >> nsim; prob.reset(new CumTempProblem(mat.get(), dom.get(), nemit, size, maxscat, maxloop)); }
+        else if (probStr == "cumflux") { argss >> nemit >> size >> maxscat >> maxloop >> nsim; prob.reset(new CumFluxProblem(mat.get(), dom.get(), nemit, size, maxscat, maxloop)); }
+        else MC_ASSERT_MSG(false, "Invalid problem");
+        MC_ASSERT_MSG(!argss.fail(), "Invalid problem arguments");
+
+        std::cout << *prob << std::endl << std::endl;
+        if (nsim == 1) solveField(prob.get(), clk);
+        else {
+            std::vector<ArrayXXd> sol;
+            for (long i = 0; i < nsim; ++i) sol.push_back(solveField(prob.get(), clk));
+            if (!sol.empty()) calcStats(sol);
+        }
+    } catch (const std::exception& e) {
+        std::cerr << "montecarlo: " << e.what() << std::endl;
+        return 1;
+    }
+    std::cout << "Total time: " << clk.stopwatch() << std::endl << std::endl;
+    return 0;
+}

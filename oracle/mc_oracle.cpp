@@ -617,10 +617,13 @@ void finishDomain(orc_domain& D) {
         std::memcpy(p.rot, B.rot.m, sizeof p.rot);
         std::memcpy(p.peri_rot, B.periRot.m, sizeof p.peri_rot);
         p.peri_transl[0] = B.periTransl.x; p.peri_transl[1] = B.periTransl.y; p.peri_transl[2] = B.periTransl.z;
-        p.T = B.T; p.origin[0] = B.o.x; p.origin[1] = B.o.y; p.origin[2] = B.o.z;
-        p.shape = B.shape; p.nvert = (int32_t)B.verts.size();
-        for (size_t v = 0; v < B.verts.size() && v < MCB_MAX_VERTS; ++v) {
-            p.verts[3 * v] = B.verts[v].x; p.verts[3 * v + 1] = B.verts[v].y; p.verts[3 * v + 2] = B.verts[v].z;
+        /* only EmitBoundary (Isot, Peri) keeps T_, o_ and its shape (boundary.h:203-223) */
+        if (B.kind == MCB_BDRY_ISOT || B.kind == MCB_BDRY_PERI) {
+            p.T = B.T; p.origin[0] = B.o.x; p.origin[1] = B.o.y; p.origin[2] = B.o.z;
+            p.shape = B.shape; p.nvert = (int32_t)B.verts.size();
+            for (size_t v = 0; v < B.verts.size() && v < MCB_MAX_VERTS; ++v) {
+                p.verts[3 * v] = B.verts[v].x; p.verts[3 * v + 1] = B.verts[v].y; p.verts[3 * v + 2] = B.verts[v].z;
+            }
         }
         D.fp.push_back(p);
     }

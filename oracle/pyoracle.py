@@ -188,7 +188,7 @@ class Problem:
         return out.reshape(self.dom.cols, self.rows).T.copy(), st.asdict()
 
     def finalize(self, raw):
-        f = np.ascontiguousarray(raw.T.reshape(-1))
+        f = np.array(raw.T.reshape(-1), dtype=np.float64, copy=True)     # never alias the caller's array
         lib().orc_finalize(self.h, _dp(f))
         return f.reshape(self.dom.cols, self.rows).T.copy()
 
