@@ -186,7 +186,8 @@ typedef struct mcb_options {
     int32_t steps_per_launch;  /* S: loop-body trips per state load/store             */
     int32_t block;             /* threads per CTA                                     */
     int32_t ctas_per_sm;       /* persistent grid = ctas_per_sm * SM count            */
-    int32_t tally_mode;        /* 0 auto, 1 block shared-memory histogram, 2 global   */
+    int32_t tally_mode;        /* 0 auto, 1 warp-private smem histograms, 2 global    */
+                               /* field (fp64 RED in L2), 3 one smem histogram per CTA */
     int32_t sort_every;        /* launches between compaction/sort passes (0 = auto)  */
     int32_t reserved_[2];
 } mcb_options;

@@ -93,7 +93,7 @@ struct mcb_ctx {
     DevBuf<double> f_wprob, f_pprob; DevBuf<int32_t> f_walias, f_palias;
     // geometry
     bool has_dom = false; GeometryView gv{}; DevBuf<unsigned char> geo_blob;
-    std::vector<DSdom> h_sdom; int nemitter = 0;
+    std::vector<DSdom> h_sdom; int nemitter = 0; bool any_nd = false;
     DevBuf<DEmitter> emitters; DevBuf<double> cell_vol; long long cols = 0;
     // problem / run state
     DevBuf<long long> emit_cdf;
@@ -138,27 +138,31 @@ int check_problem(mcb_ctx* c, const mcb_problem_desc* p) {
     return MCB_OK;
 }
 
-template <int KIND>
-cudaError_t launch_step_kind(const StepParams& P, bool smem_tally, int grid, int block, size_t smem, cudaStream_t s) {
-    if (smem_tally) {
-        cudaError_t e = cudaFuncSetAttribute(k_step<KIND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        k_step<KIND, true><<<grid, block, smem, s>>>(P);
-    } else {
-        cudaError_t e = cudaFuncSetAttribute(k_step<KIND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        k_step<KIND, false><<<grid, block, smem, s>>>(P);
-    }
+template <int NCOMP, int TM, bool ND>
+cudaError_t launch_step_inst(const StepParams& P, int grid, int block, size_t smem, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(k_step<NCOMP, TM, ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_step<NCOMP, TM, ND><<<grid, block, smem, s>>>(P);
     return cudaGetLastError();
 }
-
-cudaError_t launch_step(const StepParams& P, bool smem_tally, int grid, int block, size_t smem, cudaStream_t s) {
+template <int NCOMP, int TM>
+cudaError_t launch_step_nd(const StepParams& P, bool nd, int grid, int block, size_t smem, cudaStream_t s) {
+    return nd ? launch_step_inst<NCOMP, TM, true>(P, grid, block, smem, s) : launch_step_inst<NCOMP, TM, false>(P, grid, block, smem, s);
+}
+template <int NCOMP>
+cudaError_t launch_step_tm(const StepParams& P, int tm, bool nd, int grid, int block, size_t smem, cudaStream_t s) {
+    switch (tm) {
+    case MCB_TM_WARP: return launch_step_nd<NCOMP, MCB_TM_WARP>(P, nd, grid, block, smem, s);
+    case MCB_TM_BLOCK: return launch_step_nd<NCOMP, MCB_TM_BLOCK>(P, nd, grid, block, smem, s);
+    default: return launch_step_nd<NCOMP, MCB_TM_GLOBAL>(P, nd, grid, block, smem, s);
+    }
+}
+// payload rows per deposit: Temp/CumTemp 1 (dt), Flux/CumFlux 3 (dpos), Multi 4 (dt, dpos)
+cudaError_t launch_step(const StepParams& P, int tm, bool nd, int grid, int block, size_t smem, cudaStream_t s) {
     switch (P.kind) {
-    case MCB_PROB_TEMP: return launch_step_kind<MCB_PROB_TEMP>(P, smem_tally, grid, block, smem, s);
-    case MCB_PROB_FLUX: return launch_step_kind<MCB_PROB_FLUX>(P, smem_tally, grid, block, smem, s);
-    case MCB_PROB_MULTI: return launch_step_kind<MCB_PROB_MULTI>(P, smem_tally, grid, block, smem, s);
-    case MCB_PROB_CUMTEMP: return launch_step_kind<MCB_PROB_CUMTEMP>(P, smem_tally, grid, block, smem, s);
-    default: return launch_step_kind<MCB_PROB_CUMFLUX>(P, smem_tally, grid, block, smem, s);
+    case MCB_PROB_TEMP: case MCB_PROB_CUMTEMP: return launch_step_tm<1>(P, tm, nd, grid, block, smem, s);
+    case MCB_PROB_FLUX: case MCB_PROB_CUMFLUX: return launch_step_tm<3>(P, tm, nd, grid, block, smem, s);
+    default: return launch_step_tm<4>(P, tm, nd, grid, block, smem, s);
     }
 }
 
@@ -172,7 +176,7 @@ int ensure_slots(mcb_ctx* c, long long slots) {
     return MCB_OK;
 }
 
-struct RunPlan { long long slots; int S, block, grid; bool smem_tally; size_t smem; };
+struct RunPlan { long long slots; int S, block, grid; int tm; size_t smem; };
 
 int plan_run(mcb_ctx* c, const mcb_problem_desc* prob, long long nparticles, RunPlan* r) {
     const mcb_options& o = c->opt;
@@ -188,11 +192,16 @@ int plan_run(mcb_ctx* c, const mcb_problem_desc* prob, long long nparticles, Run
     const size_t base = 16 + (size_t)c->mv.bytes + (size_t)c->gv.bytes;
     const size_t hist = (size_t)prob->rows * (size_t)c->cols * sizeof(double);
     const size_t budget = c->smem_optin / (size_t)per_sm > 1024 ? c->smem_optin / (size_t)per_sm - 1024 : 0;
-    bool smem_tally = (o.tally_mode == 1) || (o.tally_mode == 0 && base + hist <= budget && hist <= 96 * 1024);
-    if (o.tally_mode == 2) smem_tally = false;
-    if (smem_tally && base + hist > c->smem_optin) { c->err = "tally_mode=1 but the field does not fit in shared memory"; return MCB_ELIMIT; }
-    r->smem_tally = smem_tally;
-    r->smem = base + (smem_tally ? hist : 0);
+    const size_t nwarps = (size_t)r->block / 32;
+    // tally placement: warp-private histograms when they fit, else one per CTA, else the global field in L2
+    int tm = MCB_TM_GLOBAL;
+    if (base + hist * nwarps <= budget) tm = MCB_TM_WARP;
+    else if (base + hist <= budget) tm = MCB_TM_BLOCK;
+    if (o.tally_mode == 1) { tm = MCB_TM_WARP; if (base + hist * nwarps > c->smem_optin) { c->err = "tally_mode=1 (warp histograms) does not fit in shared memory"; return MCB_ELIMIT; } }
+    if (o.tally_mode == 3) { tm = MCB_TM_BLOCK; if (base + hist > c->smem_optin) { c->err = "tally_mode=3 (CTA histogram) does not fit in shared memory"; return MCB_ELIMIT; } }
+    if (o.tally_mode == 2) tm = MCB_TM_GLOBAL;
+    r->tm = tm;
+    r->smem = base + (tm == MCB_TM_WARP ? hist * nwarps : (tm == MCB_TM_BLOCK ? hist : 0));
     if (r->smem > c->smem_optin) { c->err = "material + geometry tables exceed the shared-memory staging area"; return MCB_ELIMIT; }
     return MCB_OK;
 }
@@ -234,7 +243,7 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
     if (rc) return rc;
 
     StepParams P; fill_params(c, prob, seed, &P);
-    P.field = raw_field_dev; P.tally_smem = plan.smem_tally ? 1 : 0; P.do_tally = 1; P.refill = 1;
+    P.field = raw_field_dev; P.tally_smem = plan.tm; P.do_tally = 1; P.refill = 1;
     P.steps_per_launch = plan.S; P.n_end = (unsigned long long)n_end;
 
     Counters init{}; init.next = (unsigned long long)n_begin;
@@ -253,7 +262,7 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
         const long long tiles = (nslots + plan.block - 1) / plan.block;
         const int grid = (int)std::min<long long>(plan.grid, std::max<long long>(tiles, 1));
         CUDA_TRY(c, cudaEventRecord(c->ev2, c->stream));
-        CUDA_TRY(c, launch_step(P, plan.smem_tally, grid, plan.block, plan.smem, c->stream));
+        CUDA_TRY(c, launch_step(P, plan.tm, c->any_nd, grid, plan.block, plan.smem, c->stream));
         CUDA_TRY(c, cudaEventRecord(c->ev3, c->stream));
         launches++; step_launches++; slot_steps += nslots * plan.S;
         CUDA_TRY(c, cudaMemcpyAsync(c->h_ctr, c->ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
@@ -342,7 +351,7 @@ void mcb_destroy(mcb_ctx* c) {
 
 int mcb_set_options(mcb_ctx* c, const mcb_options* o) {
     if (!c || !o) return MCB_EINVAL;
-    if (o->slots < 0 || o->steps_per_launch < 0 || o->block < 0 || o->ctas_per_sm < 0 || o->tally_mode < 0 || o->tally_mode > 2) {
+    if (o->slots < 0 || o->steps_per_launch < 0 || o->block < 0 || o->ctas_per_sm < 0 || o->tally_mode < 0 || o->tally_mode > 3) {
         c->err = "negative / unknown option"; return MCB_EINVAL;
     }
     c->opt = *o;
@@ -372,6 +381,8 @@ int mcb_upload_material(mcb_ctx* c, const mcb_material_desc* m) {
     v.off_walias = off;  off = align16(off + (uint32_t)(nw * 2));
     v.off_palias = off;  off = align16(off + (uint32_t)(n * 1));
     v.bytes = off;
+    auto bucket_of = [](uint32_t n) { uint32_t b = 0xFFFFFFFFu / n; if (0xFFFFFFFFu % n == n - 1u) ++b; return b; };   // uniform_int_distribution, random.h:25
+    v.inv_bucket_w = 1.0 / (double)bucket_of((uint32_t)nw); v.inv_bucket_p = 1.0 / (double)bucket_of((uint32_t)np);
     if ((size_t)v.bytes + 16 > c->smem_optin) { c->err = "material tables exceed the shared-memory staging area"; return MCB_ELIMIT; }
     std::vector<unsigned char> blob(v.bytes, 0);
     double* lambda = reinterpret_cast<double*>(&blob[v.off_lambda]);
@@ -432,7 +443,7 @@ int mcb_upload_domain(mcb_ctx* c, const mcb_domain_desc* d) {
         for (int k = 0; k < 3; ++k) q.t[k] = p.peri_transl[k];
     }
     for (int i = 0; i < d->npair; ++i) if (d->pairs[i] < 0 || d->pairs[i] >= d->nplane) { c->err = "pair id out of range"; return MCB_EINVAL; }
-    std::vector<DSdom> sd(d->nsdom); std::vector<double> cell_vol;
+    std::vector<DSdom> sd(d->nsdom); std::vector<double> cell_vol; bool any_nd = false;
     long long cols = 0;
     for (int s = 0; s < d->nsdom; ++s) {
         const mcb_sdom_desc& S = d->sdoms[s]; DSdom& D = sd[s]; std::memset(&D, 0, sizeof D);
@@ -442,6 +453,11 @@ int mcb_upload_domain(mcb_ctx* c, const mcb_domain_desc* d) {
         for (int k = 0; k < 9; ++k) D.inv[k] = S.inv[k];
         D.eps = S.eps; D.accum = S.accum; D.plane_begin = S.plane_begin; D.plane_count = S.plane_count;
         D.stride1 = (int32_t)S.shape[0]; D.stride2 = (int32_t)(S.shape[0] * S.shape[1]);
+        D.is_box = (S.cell == MCB_CELL_PARALLELEPIPED && S.plane_count == 6) ? 1 : 0;
+        for (int b = 0; b < 3 && D.is_box; ++b)
+            for (int k = 0; k < 3; ++k)
+                if (d->planes[S.plane_begin + b + 3].normal[k] != -d->planes[S.plane_begin + b].normal[k]) D.is_box = 0;
+        if (S.accum >= 3) any_nd = true;
         const long long sp = S.shape[0] * S.shape[1] * S.shape[2];
         if (S.accum < -2 || S.accum > 4 || sp < 0) { c->err = "bad accum flag / shape"; return MCB_EINVAL; }
         if (sp == 0) D.col_offset = -1;                                                                    // field.cpp:34
@@ -492,7 +508,7 @@ int mcb_upload_domain(mcb_ctx* c, const mcb_domain_desc* d) {
     CUDA_TRY(c, cudaMemcpy(c->emitters.p, em.data(), em.size() * sizeof(DEmitter), cudaMemcpyHostToDevice));
     CUDA_TRY(c, c->cell_vol.alloc(cell_vol.size()));
     if (!cell_vol.empty()) CUDA_TRY(c, cudaMemcpy(c->cell_vol.p, cell_vol.data(), cell_vol.size() * 8, cudaMemcpyHostToDevice));
-    c->gv = v; c->h_sdom = sd; c->nemitter = d->nemitter; c->cols = cols; c->has_dom = true;
+    c->gv = v; c->h_sdom = sd; c->nemitter = d->nemitter; c->cols = cols; c->any_nd = any_nd; c->has_dom = true;
     return MCB_OK;
 }
 
@@ -553,7 +569,7 @@ int mcb_trace(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
     if (n == 0) return MCB_OK;
     CUDA_TRY(c, cudaSetDevice(c->device));
     RunPlan plan;
-    mcb_options saved = c->opt; c->opt.slots = n; c->opt.tally_mode = 2;
+    mcb_options saved = c->opt; c->opt.slots = n; c->opt.tally_mode = 2; c->opt.block = 0;
     rc = plan_run(c, prob, n, &plan);
     c->opt = saved;
     if (rc) return rc;
@@ -567,7 +583,7 @@ int mcb_trace(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
     Counters init{}; init.next = (unsigned long long)n_begin;
     CUDA_TRY(c, cudaMemcpyAsync(c->ctr.p, &init, sizeof init, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaMemsetAsync(c->imeta[0].p, 0, (size_t)c->slots_alloc * 2 * sizeof(unsigned long long), c->stream));
-    CUDA_TRY(c, launch_step(P, false, plan.grid, plan.block, plan.smem, c->stream));
+    CUDA_TRY(c, launch_step(P, MCB_TM_GLOBAL, c->any_nd, plan.grid, plan.block, plan.smem, c->stream));
     DevBuf<double> dpos, ddir, dsn; DevBuf<long long> dw, dp, dnscat, dsteps; DevBuf<int32_t> dsign, dalive, dsdom, dcell;
     CUDA_TRY(c, dpos.alloc(3 * n)); CUDA_TRY(c, ddir.alloc(3 * n)); CUDA_TRY(c, dsn.alloc(n));
     CUDA_TRY(c, dw.alloc(n)); CUDA_TRY(c, dp.alloc(n)); CUDA_TRY(c, dnscat.alloc(n)); CUDA_TRY(c, dsteps.alloc(n));

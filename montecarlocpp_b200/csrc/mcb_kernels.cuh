@@ -59,15 +59,15 @@ struct Particle {
 
 // Material::Dist::drawProp (material.cpp:71-75) on the two-level Walker tables; entry (w,p) at w*np+p
 template <typename WA, typename PA>
-__device__ __forceinline__ uint32_t draw_prop(Rng& g, int nw, int np, const double* wprob, const WA* walias,
+__device__ __forceinline__ uint32_t draw_prop(Rng& g, const Tables& T, const double* wprob, const WA* walias,
                                               const double* pprob, const PA* palias) {
-    uint32_t r = g.uint_below((uint32_t)nw);
-    double t = g.u01();
-    uint32_t w = t < wprob[r] ? r : (uint32_t)walias[r];
-    uint32_t q = g.uint_below((uint32_t)np);
-    double u = g.u01();
-    uint32_t p = u < pprob[w * np + q] ? q : (uint32_t)palias[w * np + q];
-    return w * (uint32_t)np + p;
+    const uint32_t r = g.uint_below((uint32_t)T.nw, T.inv_bucket_w);
+    const double t = g.u01();
+    const uint32_t w = t < wprob[r] ? r : (uint32_t)walias[r];
+    const uint32_t q = g.uint_below((uint32_t)T.np, T.inv_bucket_p);
+    const double u = g.u01();
+    const uint32_t p = u < pprob[w * T.np + q] ? q : (uint32_t)palias[w * T.np + q];
+    return w * (uint32_t)T.np + p;
 }
 // Material::drawScatNext (material.cpp:215-224); lambda = vel*tau
 __device__ __forceinline__ double draw_scat_next(Rng& g, double lambda) {
@@ -83,7 +83,7 @@ __device__ __noinline__ void emit_particle(const StepParams& P, const Tables& T,
     while (lo < hi) { int mid = (lo + hi) >> 1; if ((long long)pid < P.emit_cdf[mid]) hi = mid; else lo = mid + 1; }
     const DEmitter& E = P.emitters[lo];
     Rng g; g.begin(P.seed, pid, 0u);
-    uint32_t wp = draw_prop(g, T.nw, T.np, P.f_wprob, P.f_walias, P.f_pprob, P.f_palias);
+    uint32_t wp = draw_prop(g, T, P.f_wprob, P.f_walias, P.f_pprob, P.f_palias);
     double px, py, pz, dx, dy, dz; uint32_t sign;
     if (E.kind == MCB_EMIT_SDOM) {
         // ParallelepipedImpl::drawPos subdomain.cpp:275-281 ; drawDir :255-258 ; emitSign :260-263
@@ -114,6 +114,16 @@ __device__ __noinline__ void emit_particle(const StepParams& P, const Tables& T,
 // Subdomain::isInside subdomain.cpp:108-116
 __device__ __forceinline__ bool is_inside(const Tables& T, const DSdom& sd, double x, double y, double z) {
     bool in = true;
+    if (sd.is_box) {                 // planes b and b+3 share n.pos up to sign: three dot products
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            const DPlaneHot h = T.hot[sd.plane_begin + b];
+            const double s = dot3(h.nx, h.ny, h.nz, x, y, z);
+            const double off3 = T.hot[sd.plane_begin + b + 3].off;
+            in = in && !(s + h.off < -sd.eps) && !(off3 - s < -sd.eps);
+        }
+        return in;
+    }
     for (int b = 0; b < sd.plane_count; ++b) {
         const DPlaneHot h = T.hot[sd.plane_begin + b];
         in = in && !(dot3(h.nx, h.ny, h.nz, x, y, z) + h.off < -sd.eps);
@@ -121,45 +131,66 @@ __device__ __forceinline__ bool is_inside(const Tables& T, const DSdom& sd, doub
     return in;
 }
 
-// One trip of the loop body problem.cpp:401-435.  Returns the number of escapes (0/1).
-template <int KIND, bool SMEM>
-__device__ __forceinline__ uint32_t step_once(const StepParams& P, const Tables& T, Particle& ph) {
-    constexpr int NCOMP = (KIND == MCB_PROB_TEMP || KIND == MCB_PROB_CUMTEMP) ? 1 : (KIND == MCB_PROB_MULTI ? 4 : 3);
+struct Segment {                  // what one advect produced
+    double bx, by, bz, ex, ey, ez, d;
+    int hit; uint32_t nscat_before; bool ok;
+};
+
+// First half of a loop trip (problem.cpp:403-412): Subdomain::advect + Phonon::move.  Returns escapes (0/1).
+__device__ __forceinline__ uint32_t advect_move(const Tables& T, Particle& ph, Segment& sg) {
     const DSdom& sd = T.sdom[ph.sdom];
-    const double inv_vel = T.inv_vel[ph.wp];                                   // Material::vel :405
     // Subdomain::advect subdomain.cpp:161-192
     double d = ph.sn; int hit = -1;
-    for (int b = 0; b < sd.plane_count; ++b) {
-        const DPlaneHot h = T.hot[sd.plane_begin + b];
-        const double c = dot3(h.nx, h.ny, h.nz, ph.dx, ph.dy, ph.dz);
-        if (c >= 0.0) continue;
-        const double t = -(h.off + dot3(h.nx, h.ny, h.nz, ph.px, ph.py, ph.pz)) / c;   // boundary.cpp:107-110
-        if (t < d) { d = t; hit = sd.plane_begin + b; }
+    if (sd.is_box) {
+        // A parallelepiped's faces b and b+3 have exactly opposite normals, so n.dir < 0 holds for at most one
+        // of each pair: three divisions, no divergence.  Candidates are then compared in the reference's
+        // declaration order (faces 0,1,2 then 3,4,5) with its strict `<`.
+        double t3[3]; int id3[3];
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            const DPlaneHot h = T.hot[sd.plane_begin + b];
+            const double c = dot3(h.nx, h.ny, h.nz, ph.dx, ph.dy, ph.dz);
+            const double s = dot3(h.nx, h.ny, h.nz, ph.px, ph.py, ph.pz);
+            const double off3 = T.hot[sd.plane_begin + b + 3].off;
+            const bool front = c < 0.0;                     // face b is approached; else face b+3 (if c > 0)
+            const double num = front ? -(h.off + s) : -(off3 - s);
+            const double den = front ? c : -c;
+            t3[b] = num / den;                              // boundary.cpp:107-110
+            id3[b] = c == 0.0 ? -1 : (front ? b : b + 3);
+        }
+#pragma unroll
+        for (int b = 0; b < 3; ++b) if (id3[b] == b && t3[b] < d) { d = t3[b]; hit = sd.plane_begin + b; }
+#pragma unroll
+        for (int b = 0; b < 3; ++b) if (id3[b] == b + 3 && t3[b] < d) { d = t3[b]; hit = sd.plane_begin + b + 3; }
+    } else {
+        for (int b = 0; b < sd.plane_count; ++b) {
+            const DPlaneHot h = T.hot[sd.plane_begin + b];
+            const double c = dot3(h.nx, h.ny, h.nz, ph.dx, ph.dy, ph.dz);
+            if (c >= 0.0) continue;
+            const double t = -(h.off + dot3(h.nx, h.ny, h.nz, ph.px, ph.py, ph.pz)) / c;   // boundary.cpp:107-110
+            if (t < d) { d = t; hit = sd.plane_begin + b; }
+        }
     }
     // Phonon::move phonon.cpp:95-105
     double sn = ph.sn - d;
     if (sn < 2.2250738585072014e-308) sn = 0.0;
     ph.sn = sn;
-    const double bx = ph.px, by = ph.py, bz = ph.pz;
-    const double ex = bx + ph.dx * d, ey = by + ph.dy * d, ez = bz + ph.dz * d;
-    ph.px = ex; ph.py = ey; ph.pz = ez;
-    const uint32_t nscat_before = ph.nscat;
+    sg.bx = ph.px; sg.by = ph.py; sg.bz = ph.pz;
+    sg.ex = sg.bx + ph.dx * d; sg.ey = sg.by + ph.dy * d; sg.ez = sg.bz + ph.dz * d;
+    ph.px = sg.ex; ph.py = sg.ey; ph.pz = sg.ez;
+    sg.d = d; sg.hit = hit; sg.nscat_before = ph.nscat;
     ph.step++;
-    if (d < -sd.eps || !is_inside(T, sd, ex, ey, ez)) {                        // subdomain.cpp:182-189
-        ph.killed = 1; ph.active = 0; return 1u;                               // problem.cpp:408-412
+    if (d < -sd.eps || !is_inside(T, sd, sg.ex, sg.ey, sg.ez)) {              // subdomain.cpp:182-189
+        ph.killed = 1; ph.active = 0; sg.ok = false; return 1u;               // problem.cpp:408-412
     }
-    if (P.do_tally) {
-        // accumAmt (problem.cpp:473-476,506-509,539-544,581-589,629-637) times sign (:414)
-        const double sg = ph.sign ? 1.0 : -1.0;
-        double amt[NCOMP]; int rbase = 0;
-        if (KIND == MCB_PROB_TEMP || KIND == MCB_PROB_CUMTEMP) amt[0] = sg * (d * inv_vel);
-        else if (KIND == MCB_PROB_MULTI) { amt[0] = sg * (d * inv_vel); amt[1] = sg * (ex - bx); amt[2] = sg * (ey - by); amt[3] = sg * (ez - bz); }
-        else { amt[0] = sg * (ex - bx); amt[NCOMP > 1 ? 1 : 0] = sg * (ey - by); amt[NCOMP > 2 ? 2 : 0] = sg * (ez - bz); }
-        if (KIND == MCB_PROB_CUMTEMP || KIND == MCB_PROB_CUMFLUX)
-            rbase = NCOMP * (int)(((long long)nscat_before + P.cum_step - 1) / P.cum_step);
-        accumulate<NCOMP, SMEM>(sd, T.hist, P.rows, rbase, bx, by, bz, ex, ey, ez, amt);   // Field::accumulate :416
-    }
+    sg.ok = true;
+    return 0u;
+}
+
+// Second half of a loop trip (problem.cpp:418-434): Boundary::scatter or Material::scatter, then the stop test.
+__device__ __forceinline__ uint32_t collide(const StepParams& P, const Tables& T, Particle& ph, const Segment& sg) {
     uint32_t esc = 0;
+    const int hit = sg.hit;
     if (hit >= 0) {                                                            // problem.cpp:418-429
         const DPlaneCold& cb = T.cold[hit];
         const int kind = cb.kind;
@@ -175,7 +206,7 @@ __device__ __forceinline__ uint32_t step_once(const StepParams& P, const Tables&
             normalize3(ph.dx, ph.dy, ph.dz);
             ph.nscat++;
         } else if (kind == MCB_BDRY_PERI) {                                    // boundary.cpp:516-522
-            double nx, ny, nz; matvec(cb.m, ex, ey, ez, nx, ny, nz);
+            double nx, ny, nz; matvec(cb.m, sg.ex, sg.ey, sg.ez, nx, ny, nz);
             ph.px = nx + cb.t[0]; ph.py = ny + cb.t[1]; ph.pz = nz + cb.t[2];
             matvec(cb.m, ph.dx, ph.dy, ph.dz, nx, ny, nz);
             ph.dx = nx; ph.dy = ny; ph.dz = nz;
@@ -186,7 +217,7 @@ __device__ __forceinline__ uint32_t step_once(const StepParams& P, const Tables&
             if (cb.pair_count == 1) target = T.pairs[cb.pair_begin];
             else for (int q = 0; q < cb.pair_count && target < 0; ++q) {
                 const int cand = T.pairs[cb.pair_begin + q];
-                if (is_inside(T, T.sdom[T.cold[cand].sdom], ex, ey, ez)) target = cand;
+                if (is_inside(T, T.sdom[T.cold[cand].sdom], sg.ex, sg.ey, sg.ez)) target = cand;
             }
             if (target < 0) { ph.killed = 1; ph.active = 0; esc = 1; }         // problem.cpp:422-426
             else ph.sdom = (uint32_t)T.cold[target].sdom;
@@ -195,7 +226,7 @@ __device__ __forceinline__ uint32_t step_once(const StepParams& P, const Tables&
         }
     } else {                                                                   // Material::scatter material.cpp:226-231
         Rng g; g.begin(P.seed, ph.pid, ph.step);
-        ph.wp = draw_prop(g, T.nw, T.np, T.wprob, T.walias, T.pprob, T.palias);
+        ph.wp = draw_prop(g, T, T.wprob, T.walias, T.pprob, T.palias);
         draw_iso(g, ph.dx, ph.dy, ph.dz);
         normalize3(ph.dx, ph.dy, ph.dz);
         ph.nscat++;
@@ -206,14 +237,18 @@ __device__ __forceinline__ uint32_t step_once(const StepParams& P, const Tables&
 }
 
 // ------------------------------------------------------------------------------- k_step
-// Dynamic shared memory: [mbarrier 16 B][material blob][geometry blob][block histogram]
-template <int KIND, bool SMEM>
+// NCOMP: payload rows per deposit (1: Temp/CumTemp dt ; 3: Flux/CumFlux dpos ; 4: Multi dt,dpos)
+// TM   : MCB_TM_WARP / MCB_TM_BLOCK / MCB_TM_GLOBAL ; ND: some subdomain has a 2-D/3-D tally grid
+// Dynamic shared memory: [mbarrier 16 B][material blob][geometry blob][histogram(s)]
+template <int NCOMP, int TM, bool ND>
 __global__ void __launch_bounds__(512, 1) k_step(const StepParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
     unsigned char* s_mat = smem + 16;
     unsigned char* s_geo = s_mat + P.mv.bytes;
     double* s_hist = reinterpret_cast<double*>(s_geo + P.gv.bytes);
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const long long hist_elems = TM == MCB_TM_WARP ? P.field_len * nwarps : (TM == MCB_TM_BLOCK ? P.field_len : 0);
 
     // --- stage tables: one elected thread arms the mbarrier and issues the TMA bulk copies
     if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
@@ -224,7 +259,7 @@ __global__ void __launch_bounds__(512, 1) k_step(const StepParams P) {
         for (uint32_t o = 0; o < P.mv.bytes; o += CH) tma_bulk_g2s(s_mat + o, P.mat_blob + o, min(CH, P.mv.bytes - o), bar);
         for (uint32_t o = 0; o < P.gv.bytes; o += CH) tma_bulk_g2s(s_geo + o, P.geo_blob + o, min(CH, P.gv.bytes - o), bar);
     }
-    if (SMEM) for (long long i = threadIdx.x; i < P.field_len; i += blockDim.x) s_hist[i] = 0.0;
+    for (long long i = threadIdx.x; i < hist_elems; i += blockDim.x) s_hist[i] = 0.0;
     while (!mbar_try_wait(bar, 0)) {}
     __syncthreads();
 
@@ -239,23 +274,23 @@ __global__ void __launch_bounds__(512, 1) k_step(const StepParams P) {
     T.cold = reinterpret_cast<const DPlaneCold*>(s_geo + P.gv.off_cold);
     T.sdom = reinterpret_cast<const DSdom*>(s_geo + P.gv.off_sdom);
     T.pairs = reinterpret_cast<const int32_t*>(s_geo + P.gv.off_pairs);
-    T.nw = P.mv.nw; T.np = P.mv.np;
-    T.hist = SMEM ? s_hist : P.field;
+    T.nw = P.mv.nw; T.np = P.mv.np; T.inv_bucket_w = P.mv.inv_bucket_w; T.inv_bucket_p = P.mv.inv_bucket_p;
+    T.hist = TM == MCB_TM_WARP ? s_hist + (long long)warp * P.field_len : (TM == MCB_TM_BLOCK ? s_hist : P.field);
+    const bool cum = P.kind == MCB_PROB_CUMTEMP || P.kind == MCB_PROB_CUMFLUX;
 
     unsigned long long my_steps = 0, my_esc = 0, my_emitted = 0, my_live = 0, my_stores = 0;
     bool exhausted = false;
-    const unsigned lane = threadIdx.x & 31u;
 
     for (long long base = (long long)blockIdx.x * blockDim.x; base < P.nslots; base += (long long)gridDim.x * blockDim.x) {
         const long long i = base + threadIdx.x;
         const bool valid = i < P.nslots;
-        Particle ph; ph.active = 0; ph.killed = 0;
-        unsigned long long meta = 0, ps = 0;
+        Particle ph; ph.active = 0; ph.killed = 0; ph.sdom = 0; ph.wp = 0; ph.sign = 0; ph.nscat = 0; ph.step = 0; ph.pid = 0;
+        ph.px = ph.py = ph.pz = ph.dx = ph.dy = ph.dz = ph.sn = 0.0;
         if (valid) {
-            meta = ld_stream(P.st.meta + i);
-            ps = ld_stream(P.st.pidstep + i);
+            const unsigned long long meta = ld_stream(P.st.meta + i);
             ph.active = MCB_META_ACTIVE(meta);
             if (ph.active) {
+                const unsigned long long ps = ld_stream(P.st.pidstep + i);
                 ph.px = ld_stream(P.st.px + i); ph.py = ld_stream(P.st.py + i); ph.pz = ld_stream(P.st.pz + i);
                 ph.dx = ld_stream(P.st.dx + i); ph.dy = ld_stream(P.st.dy + i); ph.dz = ld_stream(P.st.dz + i);
                 ph.sn = ld_stream(P.st.sn + i);
@@ -280,7 +315,23 @@ __global__ void __launch_bounds__(512, 1) k_step(const StepParams P) {
                     else exhausted = true;
                 }
             }
-            if (ph.active) { my_esc += step_once<KIND, SMEM>(P, T, ph); my_steps++; dirty = true; }
+            // one loop trip (problem.cpp:401-435) in three phases; the tally phase is warp-synchronous
+            const bool run = ph.active != 0;
+            Segment sg; sg.ok = false; sg.hit = -1; sg.d = 0.0; sg.nscat_before = 0;
+            sg.bx = sg.by = sg.bz = sg.ex = sg.ey = sg.ez = 0.0;
+            if (run) { my_esc += advect_move(T, ph, sg); my_steps++; dirty = true; }
+            if (P.do_tally) {
+                __syncwarp();
+                // accumAmt (problem.cpp:473-476,506-509,539-544,581-589,629-637) times sign (:414)
+                const double sg_ = ph.sign ? 1.0 : -1.0;
+                double amt[NCOMP];
+                if (NCOMP == 1) amt[0] = sg_ * (sg.d * T.inv_vel[ph.wp]);
+                else if (NCOMP == 4) { amt[0] = sg_ * (sg.d * T.inv_vel[ph.wp]); amt[1 % NCOMP] = sg_ * (sg.ex - sg.bx); amt[2 % NCOMP] = sg_ * (sg.ey - sg.by); amt[3 % NCOMP] = sg_ * (sg.ez - sg.bz); }
+                else { amt[0] = sg_ * (sg.ex - sg.bx); amt[1 % NCOMP] = sg_ * (sg.ey - sg.by); amt[2 % NCOMP] = sg_ * (sg.ez - sg.bz); }
+                const int rbase = cum ? NCOMP * (int)(((long long)sg.nscat_before + P.cum_step - 1) / P.cum_step) : 0;
+                tally_segments<NCOMP, TM, ND>(T.sdom[ph.sdom], T.hist, P.rows, rbase, sg.ok, sg.bx, sg.by, sg.bz, sg.ex, sg.ey, sg.ez, amt, lane);
+            }
+            if (sg.ok) my_esc += collide(P, T, ph, sg);
             if (__all_sync(0xFFFFFFFFu, !ph.active && (exhausted || !valid || !P.refill))) break;
         }
         if (valid && dirty) {
@@ -319,10 +370,12 @@ __global__ void __launch_bounds__(512, 1) k_step(const StepParams P) {
         if (s_red[3]) atomicAdd(&P.ctr->live, s_red[3]);
         if (s_red[4]) atomicAdd(&P.ctr->stores, s_red[4]);
     }
-    // --- flush the block histogram (fp64 RED to L2)
-    if (SMEM && P.do_tally)
+    // --- flush the shared-memory histogram(s): sum the warp copies, one fp64 RED per non-zero entry
+    if (TM != MCB_TM_GLOBAL && P.do_tally)
         for (long long i = threadIdx.x; i < P.field_len; i += blockDim.x) {
-            const double v = s_hist[i];
+            double v = 0.0;
+            if (TM == MCB_TM_WARP) for (unsigned w = 0; w < nwarps; ++w) v += s_hist[(long long)w * P.field_len + i];
+            else v = s_hist[i];
             if (v != 0.0) atomicAdd(P.field + i, v);
         }
 }
@@ -391,8 +444,8 @@ __global__ void k_accumulate(const unsigned char* geo_blob, GeometryView gv, int
     const double* a = amount + (long long)rows * i;
     // generic row count: deposit one component at a time (same weights, same order per component)
     for (int r = 0; r < rows; ++r)
-        accumulate<1, false>(sd, field, rows, r, bpos[3 * i], bpos[3 * i + 1], bpos[3 * i + 2],
-                      epos[3 * i], epos[3 * i + 1], epos[3 * i + 2], a + r);
+        tally_segments<1, MCB_TM_GLOBAL, true>(sd, field, rows, r, true, bpos[3 * i], bpos[3 * i + 1], bpos[3 * i + 2],
+                                               epos[3 * i], epos[3 * i + 1], epos[3 * i + 2], a + r, threadIdx.x & 31u);
 }
 
 // the device generator's words for one (seed, particle, event, block) — behind mcb_philox_words
