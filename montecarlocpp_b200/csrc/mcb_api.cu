@@ -83,7 +83,8 @@ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 struct mcb_ctx {
     int device = 0; int sm_count = 148; size_t smem_optin = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t evA[2] = {nullptr, nullptr}, evB[2] = {nullptr, nullptr}, evC[2] = {nullptr, nullptr};
     std::string err;
     mcb_options opt{};
     // material
@@ -180,8 +181,8 @@ struct RunPlan { long long slots; int S, block, grid; int tm; size_t smem; };
 
 int plan_run(mcb_ctx* c, const mcb_problem_desc* prob, long long nparticles, RunPlan* r) {
     const mcb_options& o = c->opt;
-    r->block = o.block > 0 ? o.block : 512;
-    if (r->block % 32 != 0 || r->block > 512) { c->err = "block must be a multiple of 32, <= 512"; return MCB_EINVAL; }
+    r->block = o.block > 0 ? o.block : MCB_BLOCK_MAX;
+    if (r->block % 32 != 0 || r->block > MCB_BLOCK_MAX) { c->err = "block must be a multiple of 32, <= " + std::to_string(MCB_BLOCK_MAX); return MCB_EINVAL; }
     const int per_sm = o.ctas_per_sm > 0 ? o.ctas_per_sm : 1;
     r->S = o.steps_per_launch > 0 ? o.steps_per_launch : 16;
     long long slots = o.slots > 0 ? o.slots : (long long)c->sm_count * r->block * 32;   // ~2.4 M resident phonons
@@ -255,42 +256,63 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
     CUDA_TRY(c, cudaEventRecord(c->ev0, c->stream));
     float step_ms_total = 0.f;
     const long long total = n_end - n_begin;
-    if (total > 0) for (;;) {
-        P.st = soa_of(c, cur, c->slots_alloc); P.nslots = nslots;
-        // live counter is rewritten by every launch
-        CUDA_TRY(c, cudaMemsetAsync(&c->ctr.p->live, 0, sizeof(unsigned long long), c->stream));
+    // The host runs one launch AHEAD of the counters it reads (depth-2 ring of events + pinned counters), so the
+    // GPU always has the next launch queued.  Decisions (stop, compaction, tail mode) use the counters of the
+    // previous launch; after the last particle dies one extra, empty launch has already been queued.
+    const long long tail_slots = (long long)plan.grid * plan.block;      // one tile per CTA: finish in one launch
+    int S_cur = plan.S;
+    long long nslots_of[2] = {0, 0}; int S_of[2] = {0, 0};
+    if (total > 0) for (long long it = 0;; ++it) {
+        const int slot = (int)(it & 1);
+        P.st = soa_of(c, cur, c->slots_alloc); P.nslots = nslots; P.steps_per_launch = S_cur;
+        CUDA_TRY(c, cudaMemsetAsync(&c->ctr.p->live, 0, sizeof(unsigned long long), c->stream));   // rewritten by every launch
         const long long tiles = (nslots + plan.block - 1) / plan.block;
         const int grid = (int)std::min<long long>(plan.grid, std::max<long long>(tiles, 1));
-        CUDA_TRY(c, cudaEventRecord(c->ev2, c->stream));
+        CUDA_TRY(c, cudaEventRecord(c->evA[slot], c->stream));
         CUDA_TRY(c, launch_step(P, plan.tm, c->any_nd, grid, plan.block, plan.smem, c->stream));
-        CUDA_TRY(c, cudaEventRecord(c->ev3, c->stream));
-        launches++; step_launches++; slot_steps += nslots * plan.S;
-        CUDA_TRY(c, cudaMemcpyAsync(c->h_ctr, c->ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-        float ms = 0.f; cudaEventElapsedTime(&ms, c->ev2, c->ev3); step_ms_total += ms;
-        const unsigned long long live = c->h_ctr->live, next = c->h_ctr->next;
+        CUDA_TRY(c, cudaEventRecord(c->evB[slot], c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(&c->h_ctr[slot], c->ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaEventRecord(c->evC[slot], c->stream));
+        nslots_of[slot] = nslots; S_of[slot] = S_cur;
+        launches++; step_launches++; slot_steps += nslots * (long long)std::min<long long>(S_cur, prob->maxloop);
+        if (it == 0) continue;
+        const int prev = slot ^ 1;
+        CUDA_TRY(c, cudaEventSynchronize(c->evC[prev]));
+        float ms = 0.f; cudaEventElapsedTime(&ms, c->evA[prev], c->evB[prev]); step_ms_total += ms;
+        const unsigned long long live = c->h_ctr[prev].live, next = c->h_ctr[prev].next;
         const bool all_emitted = next >= (unsigned long long)n_end;
-        if (all_emitted && live == 0) break;
-        if (all_emitted && (long long)live * 2 < nslots && nslots > (long long)plan.block * 64) {
-            // tail: compact the survivors so later launches stream only live state
+        if (all_emitted && live == 0) {
+            CUDA_TRY(c, cudaEventSynchronize(c->evC[slot]));
+            cudaEventElapsedTime(&ms, c->evA[slot], c->evB[slot]); step_ms_total += ms;
+            break;
+        }
+        if (all_emitted && (long long)live * 2 < nslots && nslots > tail_slots) {
+            // tail: compact the survivors so later launches stream only live state.  `live` is one launch old,
+            // i.e. an upper bound (nothing is emitted any more); unused destination slots stay inactive.
             const int other = cur ^ 1;
+            const long long bound = std::max<long long>((long long)live, 1);
             CUDA_TRY(c, cudaMemsetAsync(&c->ctr.p->compact_cursor, 0, sizeof(unsigned long long), c->stream));
-            k_compact<<<std::min<long long>((nslots + 255) / 256, (long long)c->sm_count * 8), 256, 0, c->stream>>>(
+            CUDA_TRY(c, cudaMemsetAsync(c->imeta[other].p, 0, (size_t)bound * sizeof(unsigned long long), c->stream));
+            k_compact<<<(unsigned)std::min<long long>((nslots + 255) / 256, (long long)c->sm_count * 8), 256, 0, c->stream>>>(
                 soa_of(c, cur, c->slots_alloc), soa_of(c, other, c->slots_alloc), nslots, c->ctr.p);
             CUDA_TRY(c, cudaGetLastError());
             launches++;
-            cur = other; nslots = (long long)live;
+            cur = other; nslots = bound;
         }
+        // few survivors left: HBM traffic no longer matters, let every thread run its phonon to termination
+        if (all_emitted && (long long)live <= tail_slots && c->opt.sort_every != -1)
+            S_cur = (int)std::min<long long>(std::max<long long>(prob->maxloop, 1), 1 << 22);
     }
+    (void)nslots_of; (void)S_of;
     CUDA_TRY(c, cudaEventRecord(c->ev1, c->stream));
-    CUDA_TRY(c, cudaMemcpyAsync(c->h_ctr, c->ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(&c->h_ctr[0], c->ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     if (stats) {
         std::memset(stats, 0, sizeof *stats);
         float ms = 0.f; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
-        stats->emitted = (int64_t)c->h_ctr->emitted; stats->steps = (int64_t)c->h_ctr->steps; stats->esc = (int64_t)c->h_ctr->esc;
+        stats->emitted = (int64_t)c->h_ctr[0].emitted; stats->steps = (int64_t)c->h_ctr[0].steps; stats->esc = (int64_t)c->h_ctr[0].esc;
         stats->launches = launches; stats->cols = c->cols; stats->device_ms = ms; stats->step_ms = step_ms_total;
-        stats->step_launches = step_launches; stats->slot_steps = slot_steps; stats->state_stores = (int64_t)c->h_ctr->stores;
+        stats->step_launches = step_launches; stats->slot_steps = slot_steps; stats->state_stores = (int64_t)c->h_ctr[0].stores;
     }
     return MCB_OK;
 }
@@ -326,8 +348,10 @@ int mcb_create(int device, mcb_ctx** out) {
     c->device = device; c->sm_count = prop.multiProcessorCount; c->smem_optin = prop.sharedMemPerBlockOptin;
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess ||
-        (e = cudaEventCreate(&c->ev2)) != cudaSuccess || (e = cudaEventCreate(&c->ev3)) != cudaSuccess ||
-        (e = c->ctr.alloc(1)) != cudaSuccess || (e = cudaMallocHost(&c->h_ctr, sizeof(Counters))) != cudaSuccess) {
+        (e = cudaEventCreate(&c->evA[0])) != cudaSuccess || (e = cudaEventCreate(&c->evA[1])) != cudaSuccess ||
+        (e = cudaEventCreate(&c->evB[0])) != cudaSuccess || (e = cudaEventCreate(&c->evB[1])) != cudaSuccess ||
+        (e = cudaEventCreate(&c->evC[0])) != cudaSuccess || (e = cudaEventCreate(&c->evC[1])) != cudaSuccess ||
+        (e = c->ctr.alloc(1)) != cudaSuccess || (e = cudaMallocHost(&c->h_ctr, 2 * sizeof(Counters))) != cudaSuccess) {
         g_create_err = cudaGetErrorString(e); delete c; return MCB_ECUDA;
     }
     *out = c;
@@ -344,7 +368,7 @@ void mcb_destroy(mcb_ctx* c) {
     c->ctr.release(); c->field.release();
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
     if (c->ev0) cudaEventDestroy(c->ev0); if (c->ev1) cudaEventDestroy(c->ev1);
-    if (c->ev2) cudaEventDestroy(c->ev2); if (c->ev3) cudaEventDestroy(c->ev3);
+    for (int k = 0; k < 2; ++k) { if (c->evA[k]) cudaEventDestroy(c->evA[k]); if (c->evB[k]) cudaEventDestroy(c->evB[k]); if (c->evC[k]) cudaEventDestroy(c->evC[k]); }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }

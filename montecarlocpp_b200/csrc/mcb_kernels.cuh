@@ -225,12 +225,37 @@ __device__ __forceinline__ uint32_t collide(const StepParams& P, const Tables& T
             ph.killed = 1; ph.active = 0;
         }
     } else {                                                                   // Material::scatter material.cpp:226-231
-        Rng g; g.begin(P.seed, ph.pid, ph.step);
-        ph.wp = draw_prop(g, T, T.wprob, T.walias, T.pprob, T.palias);
-        draw_iso(g, ph.dx, ph.dy, ph.dz);
+        // Fast path: the event's seven words (w int, w real, p int, p real, iso mu, iso phi, free path) come from two
+        // Philox blocks at fixed positions, valid when no draw is rejected (probability ~ nw / 2^32); any rejection
+        // replays the event through the sequential generator so the stream stays identical to the CPU's.
+        bool fast = T.nw > 1 && T.np > 1;
+        if (fast) {
+            uint32_t a[4], b[4];
+            philox4x32_10((uint32_t)ph.pid, (uint32_t)(ph.pid >> 32), ph.step, 0u, (uint32_t)P.seed, (uint32_t)(P.seed >> 32), a);
+            philox4x32_10((uint32_t)ph.pid, (uint32_t)(ph.pid >> 32), ph.step, 1u, (uint32_t)P.seed, (uint32_t)(P.seed >> 32), b);
+            uint32_t r = (uint32_t)(((double)a[0] + 0.5) * T.inv_bucket_w);
+            uint32_t q = (uint32_t)(((double)a[2] + 0.5) * T.inv_bucket_p);
+            fast = r < (uint32_t)T.nw && q < (uint32_t)T.np;
+            r = min(r, (uint32_t)T.nw - 1u); q = min(q, (uint32_t)T.np - 1u);
+            const uint32_t w = (double)a[1] * (1.0 / 4294967296.0) < T.wprob[r] ? r : (uint32_t)T.walias[r];
+            const uint32_t k = w * (uint32_t)T.np + q;
+            const uint32_t wp = (double)a[3] * (1.0 / 4294967296.0) < T.pprob[k] ? k : w * (uint32_t)T.np + (uint32_t)T.palias[k];
+            const double c = (double)b[0] * (1.0 / 2147483648.0) - 1.0;       // drawIso random.cpp:16-27
+            const double sth = sqrt(1.0 - c * c);
+            const double phi = 3.141592653589793 * ((double)b[1] * (1.0 / 2147483648.0) - 1.0);
+            double sp, cp; sincos(phi, &sp, &cp);
+            const double dist = T.lambda[wp] * -log(1.0 - (double)b[2] * (1.0 / 4294967296.0));
+            fast = fast && !(dist < 2.2250738585072014e-308);
+            if (fast) { ph.wp = wp; ph.dx = sth * cp; ph.dy = sth * sp; ph.dz = c; ph.sn = dist; }
+        }
+        if (!fast) {
+            Rng g; g.begin(P.seed, ph.pid, ph.step);
+            ph.wp = draw_prop(g, T, T.wprob, T.walias, T.pprob, T.palias);
+            draw_iso(g, ph.dx, ph.dy, ph.dz);
+            ph.sn = draw_scat_next(g, T.lambda[ph.wp]);
+        }
         normalize3(ph.dx, ph.dy, ph.dz);
         ph.nscat++;
-        ph.sn = draw_scat_next(g, T.lambda[ph.wp]);
     }
     if ((long long)ph.nscat >= P.maxscat || (long long)ph.step >= P.maxloop) ph.active = 0;   // :434, :401
     return esc;
@@ -240,8 +265,11 @@ __device__ __forceinline__ uint32_t collide(const StepParams& P, const Tables& T
 // NCOMP: payload rows per deposit (1: Temp/CumTemp dt ; 3: Flux/CumFlux dpos ; 4: Multi dt,dpos)
 // TM   : MCB_TM_WARP / MCB_TM_BLOCK / MCB_TM_GLOBAL ; ND: some subdomain has a 2-D/3-D tally grid
 // Dynamic shared memory: [mbarrier 16 B][material blob][geometry blob][histogram(s)]
+#ifndef MCB_BLOCK_MAX
+#define MCB_BLOCK_MAX 768
+#endif
 template <int NCOMP, int TM, bool ND>
-__global__ void __launch_bounds__(512, 1) k_step(const StepParams P) {
+__global__ void __launch_bounds__(MCB_BLOCK_MAX, 1) k_step(const StepParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
     unsigned char* s_mat = smem + 16;
