@@ -145,7 +145,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from montecarlocpp_b200 import capi, hostapi
+    from montecarlocpp_b200 import capi, hostapi, sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -162,8 +162,7 @@ def run_ours(args):
     dom = hostapi.Domain(kind, dim, div, dT)
     n_total = args.nemit * world                       # weak scaling: per-GPU work fixed
     prob = hostapi.FieldProblem(mat, dom, pkind, n_total, maxscat)
-    per = (prob.nemit + world - 1) // world
-    n_begin, n_end = rank * per, min(prob.nemit, (rank + 1) * per)
+    n_begin, n_end = sharding.shard_range(prob.nemit, world, rank)
 
     ctx = capi.Context(local)
     ctx.upload_material(mat.desc)
@@ -177,8 +176,7 @@ def run_ours(args):
         raw.zero_()
         torch.cuda.synchronize()
         st = ctx.solve_raw_dev(prob.desc, raw.data_ptr(), seed=seed, n_begin=n_begin, n_end=n_end)
-        if world > 1:
-            dist.all_reduce(raw)                       # the per-solve field reduction (main.cpp:162-165) over NCCL
+        sharding.allreduce_raw_field(raw)              # the per-solve field reduction (main.cpp:162-165) over NCCL
         ctx.finalize_dev(prob.desc, raw.data_ptr())
         return st
 
@@ -207,7 +205,14 @@ def run_ours(args):
     # ---- end-to-end arm: the call a user makes, with HOST buffers: tables uploaded, solve, field read back
     def e2e_step(seed):
         ctx.upload_material(mat.desc); ctx.upload_domain(dom.desc)
-        sol, st = ctx.solve(prob.desc, seed=seed, n_begin=n_begin, n_end=n_end)
+        if world == 1:
+            sol, st = ctx.solve(prob.desc, seed=seed, n_begin=n_begin, n_end=n_end)      # host field out
+            return st
+        raw.zero_(); torch.cuda.synchronize()
+        st = ctx.solve_raw_dev(prob.desc, raw.data_ptr(), seed=seed, n_begin=n_begin, n_end=n_end)
+        sharding.allreduce_raw_field(raw)
+        ctx.finalize_dev(prob.desc, raw.data_ptr())
+        raw.cpu()                                                                        # field D2H on every rank
         return st
     e2e_step(7)
     barrier()

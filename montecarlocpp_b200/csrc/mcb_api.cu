@@ -177,7 +177,7 @@ int ensure_slots(mcb_ctx* c, long long slots) {
     return MCB_OK;
 }
 
-struct RunPlan { long long slots; int S, block, grid; int tm; size_t smem; };
+struct RunPlan { long long slots; int S, block, grid; int tm, copies; size_t smem; };
 
 int plan_run(mcb_ctx* c, const mcb_problem_desc* prob, long long nparticles, RunPlan* r) {
     const mcb_options& o = c->opt;
@@ -201,8 +201,9 @@ int plan_run(mcb_ctx* c, const mcb_problem_desc* prob, long long nparticles, Run
     if (o.tally_mode == 1) { tm = MCB_TM_WARP; if (base + hist * nwarps > c->smem_optin) { c->err = "tally_mode=1 (warp histograms) does not fit in shared memory"; return MCB_ELIMIT; } }
     if (o.tally_mode == 3) { tm = MCB_TM_BLOCK; if (base + hist > c->smem_optin) { c->err = "tally_mode=3 (CTA histogram) does not fit in shared memory"; return MCB_ELIMIT; } }
     if (o.tally_mode == 2) tm = MCB_TM_GLOBAL;
-    r->tm = tm;
-    r->smem = base + (tm == MCB_TM_WARP ? hist * nwarps : (tm == MCB_TM_BLOCK ? hist : 0));
+    r->tm = tm; r->copies = 1;
+    if (tm == MCB_TM_WARP) for (int cp = 4; cp > 1; cp >>= 1) if (base + hist * nwarps * cp <= budget) { r->copies = cp; break; }
+    r->smem = base + (tm == MCB_TM_WARP ? hist * nwarps * r->copies : (tm == MCB_TM_BLOCK ? hist : 0));
     if (r->smem > c->smem_optin) { c->err = "material + geometry tables exceed the shared-memory staging area"; return MCB_ELIMIT; }
     return MCB_OK;
 }
@@ -244,7 +245,7 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
     if (rc) return rc;
 
     StepParams P; fill_params(c, prob, seed, &P);
-    P.field = raw_field_dev; P.tally_smem = plan.tm; P.do_tally = 1; P.refill = 1;
+    P.field = raw_field_dev; P.tally_smem = plan.tm; P.hist_copies = plan.copies; P.do_tally = 1; P.refill = 1;
     P.steps_per_launch = plan.S; P.n_end = (unsigned long long)n_end;
 
     Counters init{}; init.next = (unsigned long long)n_begin;
@@ -601,7 +602,7 @@ int mcb_trace(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
     if ((rc = upload_cdf(c, prob))) return rc;
     StepParams P; fill_params(c, prob, seed, &P);
     P.maxloop = std::min<long long>(prob->maxloop, nsteps);
-    P.field = nullptr; P.tally_smem = 0; P.do_tally = 0; P.refill = 0;
+    P.field = nullptr; P.tally_smem = 0; P.hist_copies = 1; P.do_tally = 0; P.refill = 0;
     P.steps_per_launch = (int)std::max<long long>(1, std::min<long long>(P.maxloop, 0x7FFFFFFF)); P.n_end = (unsigned long long)n_end;
     P.st = soa_of(c, 0, c->slots_alloc); P.nslots = n;
     Counters init{}; init.next = (unsigned long long)n_begin;

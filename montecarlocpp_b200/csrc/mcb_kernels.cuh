@@ -242,8 +242,7 @@ __device__ __forceinline__ uint32_t collide(const StepParams& P, const Tables& T
             const uint32_t wp = (double)a[3] * (1.0 / 4294967296.0) < T.pprob[k] ? k : w * (uint32_t)T.np + (uint32_t)T.palias[k];
             const double c = (double)b[0] * (1.0 / 2147483648.0) - 1.0;       // drawIso random.cpp:16-27
             const double sth = sqrt(1.0 - c * c);
-            const double phi = 3.141592653589793 * ((double)b[1] * (1.0 / 2147483648.0) - 1.0);
-            double sp, cp; sincos(phi, &sp, &cp);
+            double sp, cp; sincospi((double)b[1] * (1.0 / 2147483648.0) - 1.0, &sp, &cp);
             const double dist = T.lambda[wp] * -log(1.0 - (double)b[2] * (1.0 / 4294967296.0));
             fast = fast && !(dist < 2.2250738585072014e-308);
             if (fast) { ph.wp = wp; ph.dx = sth * cp; ph.dy = sth * sp; ph.dz = c; ph.sn = dist; }
@@ -276,7 +275,7 @@ __global__ void __launch_bounds__(MCB_BLOCK_MAX, 1) k_step(const StepParams P) {
     unsigned char* s_geo = s_mat + P.mv.bytes;
     double* s_hist = reinterpret_cast<double*>(s_geo + P.gv.bytes);
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const long long hist_elems = TM == MCB_TM_WARP ? P.field_len * nwarps : (TM == MCB_TM_BLOCK ? P.field_len : 0);
+    const long long hist_elems = TM == MCB_TM_WARP ? P.field_len * nwarps * P.hist_copies : (TM == MCB_TM_BLOCK ? P.field_len : 0);
 
     // --- stage tables: one elected thread arms the mbarrier and issues the TMA bulk copies
     if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
@@ -303,7 +302,9 @@ __global__ void __launch_bounds__(MCB_BLOCK_MAX, 1) k_step(const StepParams P) {
     T.sdom = reinterpret_cast<const DSdom*>(s_geo + P.gv.off_sdom);
     T.pairs = reinterpret_cast<const int32_t*>(s_geo + P.gv.off_pairs);
     T.nw = P.mv.nw; T.np = P.mv.np; T.inv_bucket_w = P.mv.inv_bucket_w; T.inv_bucket_p = P.mv.inv_bucket_p;
-    T.hist = TM == MCB_TM_WARP ? s_hist + (long long)warp * P.field_len : (TM == MCB_TM_BLOCK ? s_hist : P.field);
+    // warp-private histograms, `hist_copies` interleaved copies per warp (by lane) to thin out same-cell collisions
+    T.hist = TM == MCB_TM_WARP ? s_hist + ((long long)warp * P.hist_copies + (lane & (unsigned)(P.hist_copies - 1))) * P.field_len
+                               : (TM == MCB_TM_BLOCK ? s_hist : P.field);
     const bool cum = P.kind == MCB_PROB_CUMTEMP || P.kind == MCB_PROB_CUMFLUX;
 
     unsigned long long my_steps = 0, my_esc = 0, my_emitted = 0, my_live = 0, my_stores = 0;
@@ -402,7 +403,7 @@ __global__ void __launch_bounds__(MCB_BLOCK_MAX, 1) k_step(const StepParams P) {
     if (TM != MCB_TM_GLOBAL && P.do_tally)
         for (long long i = threadIdx.x; i < P.field_len; i += blockDim.x) {
             double v = 0.0;
-            if (TM == MCB_TM_WARP) for (unsigned w = 0; w < nwarps; ++w) v += s_hist[(long long)w * P.field_len + i];
+            if (TM == MCB_TM_WARP) for (unsigned w = 0; w < nwarps * (unsigned)P.hist_copies; ++w) v += s_hist[(long long)w * P.field_len + i];
             else v = s_hist[i];
             if (v != 0.0) atomicAdd(P.field + i, v);
         }

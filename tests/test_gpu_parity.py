@@ -216,3 +216,46 @@ def test_error_behaviour(omats):
     with pytest.raises(capi.McbError):
         ctx.solve(prob.desc, n_begin=5, n_end=2)
     ctx.close()
+
+
+def test_host_mirror_solve_matches_oracle(matfiles, omats):
+    """The C++ mirror of the reference API (Material -> FilmDomain/TubeDomain -> MultiProblem::solve) drives the
+    same device path: identical counters and field as the oracle on the same Philox seed."""
+    from montecarlocpp_b200 import hostapi
+    for dname, dim, div, dT, odom in (("film", [1e-6, 1e-7, 1e-6], [0, 20, 0], 1.0, cases.film()),
+                                      ("tube", [1e-6, 5e-8, 5e-8, 2e-8], [0, 8, 8, 4], 1.0, cases.tube())):
+        hm, hd = hostapi.Material(*matfiles["silicon"]), hostapi.Domain(dname, dim, div, dT)
+        hp = hostapi.FieldProblem(hm, hd, "multi", 20000, 30)
+        got, gst = hp.solve_seeded(SEED)
+        op = orc.Problem(omats["silicon"], odom, "multi", 20000, 30)
+        ref, rst = op.solve(rng=orc.RNG_PHILOX, seed=SEED)
+        assert (gst["emitted"], gst["steps"], gst["esc"]) == (rst["emitted"], rst["steps"], rst["esc"])
+        scale = np.abs(ref).max(axis=1, keepdims=True)
+        assert (np.abs(got - ref) <= 1e-9 * scale).all()
+        # the reference signature solve(Rng& gen, Progress*): the seed is (gen() << 32) | gen() of mt19937(7)
+        raw = np.random.RandomState(7).randint(0, 2**32, size=2, dtype=np.uint64)
+        a, _ = hp.solve(mt_seed=7)
+        b, _ = hp.solve_seeded(int((int(raw[0]) << 32) | int(raw[1])))
+        assert np.allclose(a, b, rtol=1e-9, atol=1e-12 * np.abs(b).max())
+
+
+def test_cli_driver_keeps_the_reference_stdout_blocks(matfiles, tmp_path):
+    """main.cpp grammar + printSolution format (main.cpp:67-84, 146-210)."""
+    import os, shutil, subprocess
+    from montecarlocpp_b200 import capi
+    exe = os.path.join(os.path.dirname(capi.LIB_PATH), "montecarlo")
+    for f in matfiles["grey"]:
+        shutil.copy(f, tmp_path)
+    r = subprocess.run([exe, str(tmp_path), "grey", "300", "film", "1e-6", "1e-7", "10", "multi", "20000", "20", "0", "3"],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    out = r.stdout
+    for token in ("Material ", "FilmDomain ", "MultiProblem ", "  nemit:   20000", "  maxloop: 2000", "Solution 0", "Solution 2",
+                  "  seeds: ", "Output", "Mean", "Standard Deviation", "Total time: ", "esc: 0"):
+        assert token in out, token
+    block = out.split("Mean\n")[1].split("\n\n")[0].strip().split("\n")
+    assert len(block) == 4 and all(len(row.split()) == 10 for row in block)
+    vals = np.array([[float(x) for x in row.split()] for row in block])
+    assert (vals[1] > 0).all()                      # heat flows down the gradient in every cell
+    bad = subprocess.run([exe, str(tmp_path), "grey", "300", "octet", "1"], capture_output=True, text=True)
+    assert bad.returncode != 0 and "Invalid domain" in bad.stderr
