@@ -178,6 +178,12 @@ typedef struct mcb_stats {
     int64_t step_launches;     /* launches of the move-collide kernel                 */
     int64_t slot_steps;        /* slots visited by the move-collide kernel x S (>= steps) */
     int64_t state_stores;      /* slot state write-backs (each: <= 72 B load + 72 B store) */
+    /* the same four counters restricted to the STEADY phase: launches issued while particles were still
+     * being emitted, i.e. with a full resident population (the launches a streaming roofline refers to) */
+    int64_t steady_launches;
+    int64_t steady_steps;
+    int64_t steady_stores;
+    double  steady_ms;
 } mcb_stats;
 
 /* Tunables of the device schedule (not part of the physics). 0 = library default. */

@@ -72,7 +72,9 @@ class Stats(C.Structure):
     _fields_ = [("emitted", C.c_int64), ("steps", C.c_int64), ("esc", C.c_int64),
                 ("launches", C.c_int64), ("cols", C.c_int64),
                 ("device_ms", C.c_double), ("step_ms", C.c_double),
-                ("step_launches", C.c_int64), ("slot_steps", C.c_int64), ("state_stores", C.c_int64)]
+                ("step_launches", C.c_int64), ("slot_steps", C.c_int64), ("state_stores", C.c_int64),
+                ("steady_launches", C.c_int64), ("steady_steps", C.c_int64), ("steady_stores", C.c_int64),
+                ("steady_ms", C.c_double)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

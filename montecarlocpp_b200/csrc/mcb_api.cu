@@ -262,7 +262,8 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
     // previous launch; after the last particle dies one extra, empty launch has already been queued.
     const long long tail_slots = (long long)plan.grid * plan.block;      // one tile per CTA: finish in one launch
     int S_cur = plan.S;
-    long long nslots_of[2] = {0, 0}; int S_of[2] = {0, 0};
+    long long steady_launches = 0; float steady_ms = 0.f;
+    unsigned long long steady_steps = 0, steady_stores = 0, prev_steps = 0, prev_stores = 0;
     if (total > 0) for (long long it = 0;; ++it) {
         const int slot = (int)(it & 1);
         P.st = soa_of(c, cur, c->slots_alloc); P.nslots = nslots; P.steps_per_launch = S_cur;
@@ -274,7 +275,6 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
         CUDA_TRY(c, cudaEventRecord(c->evB[slot], c->stream));
         CUDA_TRY(c, cudaMemcpyAsync(&c->h_ctr[slot], c->ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(c, cudaEventRecord(c->evC[slot], c->stream));
-        nslots_of[slot] = nslots; S_of[slot] = S_cur;
         launches++; step_launches++; slot_steps += nslots * (long long)std::min<long long>(S_cur, prob->maxloop);
         if (it == 0) continue;
         const int prev = slot ^ 1;
@@ -282,6 +282,11 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
         float ms = 0.f; cudaEventElapsedTime(&ms, c->evA[prev], c->evB[prev]); step_ms_total += ms;
         const unsigned long long live = c->h_ctr[prev].live, next = c->h_ctr[prev].next;
         const bool all_emitted = next >= (unsigned long long)n_end;
+        if (!all_emitted) {          // launch it-1 ran with a full population: steady-phase accounting
+            steady_launches++; steady_ms += ms;
+            steady_steps += c->h_ctr[prev].steps - prev_steps; steady_stores += c->h_ctr[prev].stores - prev_stores;
+        }
+        prev_steps = c->h_ctr[prev].steps; prev_stores = c->h_ctr[prev].stores;
         if (all_emitted && live == 0) {
             CUDA_TRY(c, cudaEventSynchronize(c->evC[slot]));
             cudaEventElapsedTime(&ms, c->evA[slot], c->evB[slot]); step_ms_total += ms;
@@ -300,11 +305,13 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
             launches++;
             cur = other; nslots = bound;
         }
-        // few survivors left: HBM traffic no longer matters, let every thread run its phonon to termination
-        if (all_emitted && (long long)live <= tail_slots && c->opt.sort_every != -1)
-            S_cur = (int)std::min<long long>(std::max<long long>(prob->maxloop, 1), 1 << 22);
+        // decay phase (nothing left to emit): launches are no longer full, so amortise them over >= 16 loop trips;
+        // once the survivors fit one tile per CTA let every thread run its phonon to termination
+        if (all_emitted && c->opt.sort_every != -1) {
+            S_cur = std::max(plan.S, 16);
+            if ((long long)live <= tail_slots) S_cur = (int)std::min<long long>(std::max<long long>(prob->maxloop, 1), 1 << 22);
+        }
     }
-    (void)nslots_of; (void)S_of;
     CUDA_TRY(c, cudaEventRecord(c->ev1, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(&c->h_ctr[0], c->ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -314,6 +321,8 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
         stats->emitted = (int64_t)c->h_ctr[0].emitted; stats->steps = (int64_t)c->h_ctr[0].steps; stats->esc = (int64_t)c->h_ctr[0].esc;
         stats->launches = launches; stats->cols = c->cols; stats->device_ms = ms; stats->step_ms = step_ms_total;
         stats->step_launches = step_launches; stats->slot_steps = slot_steps; stats->state_stores = (int64_t)c->h_ctr[0].stores;
+        stats->steady_launches = steady_launches; stats->steady_steps = (int64_t)steady_steps;
+        stats->steady_stores = (int64_t)steady_stores; stats->steady_ms = steady_ms;
     }
     return MCB_OK;
 }
