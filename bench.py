@@ -283,7 +283,7 @@ def run_ours(args):
                        "k_step_share_of_step": tot["step_ms"] * 1e-3 / elapsed},
             "phonon_steps_per_solve": tot["steps"] / args.steps, "esc": tot["esc"],
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # reported on rank 0 at N=1 only
             rate, dt, steps, cores, n = cpu_reference_rate(args.workload, n_total, args.cpu_sample, 4242)
             line["cpu_baseline"] = {"value": rate, "unit": "phonon-steps/s", "cores": cores, "kind": "port",
                                     "sample": f"{n} of {n_total} phonons ({steps} phonon-steps, {dt:.1f} s), oracle port, OpenMP"}
