@@ -216,6 +216,10 @@ void fill_params(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, StepPa
     P->kind = prob->kind; P->rows = prob->rows; P->cum_step = prob->step > 0 ? prob->step : 1;
     P->maxscat = prob->maxscat; P->maxloop = prob->maxloop; P->seed = seed;
     P->ctr = c->ctr.p; P->field_len = (long long)prob->rows * c->cols;
+    P->so_mat = 16; P->so_geo = 16 + c->mv.bytes; P->so_hist = 16 + c->mv.bytes + c->gv.bytes;
+    P->so_lambda = P->so_mat + c->mv.off_lambda; P->so_inv_vel = P->so_mat + c->mv.off_inv_vel; P->so_wprob = P->so_mat + c->mv.off_wprob;
+    P->so_pprob = P->so_mat + c->mv.off_pprob; P->so_walias = P->so_mat + c->mv.off_walias; P->so_palias = P->so_mat + c->mv.off_palias;
+    P->so_hot = P->so_geo + c->gv.off_hot; P->so_cold = P->so_geo + c->gv.off_cold; P->so_sdom = P->so_geo + c->gv.off_sdom; P->so_pairs = P->so_geo + c->gv.off_pairs;
 }
 
 int upload_cdf(mcb_ctx* c, const mcb_problem_desc* prob) {

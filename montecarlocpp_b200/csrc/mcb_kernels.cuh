@@ -271,9 +271,9 @@ template <int NCOMP, int TM, bool ND>
 __global__ void __launch_bounds__(MCB_BLOCK_MAX, 1) k_step(const StepParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
-    unsigned char* s_mat = smem + 16;
-    unsigned char* s_geo = s_mat + P.mv.bytes;
-    double* s_hist = reinterpret_cast<double*>(s_geo + P.gv.bytes);
+    unsigned char* s_mat = smem + P.so_mat;
+    unsigned char* s_geo = smem + P.so_geo;
+    double* s_hist = reinterpret_cast<double*>(smem + P.so_hist);
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const long long hist_elems = TM == MCB_TM_WARP ? P.field_len * nwarps * P.hist_copies : (TM == MCB_TM_BLOCK ? P.field_len : 0);
 
@@ -291,16 +291,16 @@ __global__ void __launch_bounds__(MCB_BLOCK_MAX, 1) k_step(const StepParams P) {
     __syncthreads();
 
     Tables T;
-    T.lambda = reinterpret_cast<const double*>(s_mat + P.mv.off_lambda);
-    T.inv_vel = reinterpret_cast<const double*>(s_mat + P.mv.off_inv_vel);
-    T.wprob = reinterpret_cast<const double*>(s_mat + P.mv.off_wprob);
-    T.pprob = reinterpret_cast<const double*>(s_mat + P.mv.off_pprob);
-    T.walias = reinterpret_cast<const uint16_t*>(s_mat + P.mv.off_walias);
-    T.palias = reinterpret_cast<const uint8_t*>(s_mat + P.mv.off_palias);
-    T.hot = reinterpret_cast<const DPlaneHot*>(s_geo + P.gv.off_hot);
-    T.cold = reinterpret_cast<const DPlaneCold*>(s_geo + P.gv.off_cold);
-    T.sdom = reinterpret_cast<const DSdom*>(s_geo + P.gv.off_sdom);
-    T.pairs = reinterpret_cast<const int32_t*>(s_geo + P.gv.off_pairs);
+    T.lambda = reinterpret_cast<const double*>(smem + P.so_lambda);
+    T.inv_vel = reinterpret_cast<const double*>(smem + P.so_inv_vel);
+    T.wprob = reinterpret_cast<const double*>(smem + P.so_wprob);
+    T.pprob = reinterpret_cast<const double*>(smem + P.so_pprob);
+    T.walias = reinterpret_cast<const uint16_t*>(smem + P.so_walias);
+    T.palias = reinterpret_cast<const uint8_t*>(smem + P.so_palias);
+    T.hot = reinterpret_cast<const DPlaneHot*>(smem + P.so_hot);
+    T.cold = reinterpret_cast<const DPlaneCold*>(smem + P.so_cold);
+    T.sdom = reinterpret_cast<const DSdom*>(smem + P.so_sdom);
+    T.pairs = reinterpret_cast<const int32_t*>(smem + P.so_pairs);
     T.nw = P.mv.nw; T.np = P.mv.np; T.inv_bucket_w = P.mv.inv_bucket_w; T.inv_bucket_p = P.mv.inv_bucket_p;
     // warp-private histograms, `hist_copies` interleaved copies per warp (by lane) to thin out same-cell collisions
     T.hist = TM == MCB_TM_WARP ? s_hist + ((long long)warp * P.hist_copies + (lane & (unsigned)(P.hist_copies - 1))) * P.field_len
