@@ -495,6 +495,12 @@ int mcb_upload_domain(mcb_ctx* c, const mcb_domain_desc* d) {
         for (int b = 0; b < 3 && D.is_box; ++b)
             for (int k = 0; k < 3; ++k)
                 if (d->planes[S.plane_begin + b + 3].normal[k] != -d->planes[S.plane_begin + b].normal[k]) D.is_box = 0;
+        D.aabb = D.is_box;
+        for (int b = 0; b < 3 && D.aabb; ++b) {
+            const mcb_plane_desc& pl = d->planes[S.plane_begin + b];
+            for (int k = 0; k < 3; ++k) if (pl.normal[k] != (k == b ? 1.0 : 0.0)) D.aabb = 0;
+        }
+        for (int b = 0; b < 3; ++b) { D.offl[b] = d->planes[S.plane_begin + b].offset; D.offh[b] = D.is_box ? d->planes[S.plane_begin + b + 3].offset : 0.0; }
         if (S.accum >= 3) any_nd = true;
         const long long sp = S.shape[0] * S.shape[1] * S.shape[2];
         if (S.accum < -2 || S.accum > 4 || sp < 0) { c->err = "bad accum flag / shape"; return MCB_EINVAL; }

@@ -114,6 +114,12 @@ __device__ __noinline__ void emit_particle(const StepParams& P, const Tables& T,
 // Subdomain::isInside subdomain.cpp:108-116
 __device__ __forceinline__ bool is_inside(const Tables& T, const DSdom& sd, double x, double y, double z) {
     bool in = true;
+    if (sd.aabb) {                   // axis-aligned box: n_b.x is x[b]
+        const double p3[3] = {x, y, z};
+#pragma unroll
+        for (int b = 0; b < 3; ++b) in = in && !(p3[b] + sd.offl[b] < -sd.eps) && !(sd.offh[b] - p3[b] < -sd.eps);
+        return in;
+    }
     if (sd.is_box) {                 // planes b and b+3 share n.pos up to sign: three dot products
 #pragma unroll
         for (int b = 0; b < 3; ++b) {
@@ -141,7 +147,25 @@ __device__ __forceinline__ uint32_t advect_move(const Tables& T, Particle& ph, S
     const DSdom& sd = T.sdom[ph.sdom];
     // Subdomain::advect subdomain.cpp:161-192
     double d = ph.sn; int hit = -1;
-    if (sd.is_box) {
+    if (sd.aabb) {
+        // axis-aligned box (every shipped domain): n_b = +e_b, n_{b+3} = -e_b, so n.dir and n.pos are single
+        // components -- the same values the dot products produce, without the multiplies by 0 and 1
+        const double dr[3] = {ph.dx, ph.dy, ph.dz}, ps[3] = {ph.px, ph.py, ph.pz};
+        double t3[3]; int id3[3];
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            const double c = dr[b], s = ps[b];
+            const bool front = c < 0.0;
+            const double num = front ? -(sd.offl[b] + s) : -(sd.offh[b] - s);
+            const double den = front ? c : -c;
+            t3[b] = num / den;
+            id3[b] = c == 0.0 ? -1 : (front ? b : b + 3);
+        }
+#pragma unroll
+        for (int b = 0; b < 3; ++b) if (id3[b] == b && t3[b] < d) { d = t3[b]; hit = sd.plane_begin + b; }
+#pragma unroll
+        for (int b = 0; b < 3; ++b) if (id3[b] == b + 3 && t3[b] < d) { d = t3[b]; hit = sd.plane_begin + b + 3; }
+    } else if (sd.is_box) {
         // A parallelepiped's faces b and b+3 have exactly opposite normals, so n.dir < 0 holds for at most one
         // of each pair: three divisions, no divergence.  Candidates are then compared in the reference's
         // declaration order (faces 0,1,2 then 3,4,5) with its strict `<`.
