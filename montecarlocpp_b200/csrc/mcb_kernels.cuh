@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(MCB_BLOCK_MAX, 1) k_step(const StepParams P) {
                 else if (NCOMP == 4) { amt[0] = sg_ * (sg.d * T.inv_vel[ph.wp]); amt[1 % NCOMP] = sg_ * (sg.ex - sg.bx); amt[2 % NCOMP] = sg_ * (sg.ey - sg.by); amt[3 % NCOMP] = sg_ * (sg.ez - sg.bz); }
                 else { amt[0] = sg_ * (sg.ex - sg.bx); amt[1 % NCOMP] = sg_ * (sg.ey - sg.by); amt[2 % NCOMP] = sg_ * (sg.ez - sg.bz); }
                 const int rbase = cum ? NCOMP * (int)(((long long)sg.nscat_before + P.cum_step - 1) / P.cum_step) : 0;
-                tally_segments<NCOMP, TM, ND>(T.sdom[ph.sdom], T.hist, P.rows, rbase, sg.ok, sg.bx, sg.by, sg.bz, sg.ex, sg.ey, sg.ez, amt, lane);
+                tally_segments<NCOMP, TM, ND, true>(T.sdom[ph.sdom], T.hist, P.rows, rbase, sg.ok, sg.bx, sg.by, sg.bz, sg.ex, sg.ey, sg.ez, amt, lane);
             }
             if (sg.ok) my_esc += collide(P, T, ph, sg);
             if (__all_sync(0xFFFFFFFFu, !ph.active && (exhausted || !valid || !P.refill))) break;
@@ -497,7 +497,7 @@ __global__ void k_accumulate(const unsigned char* geo_blob, GeometryView gv, int
     const double* a = amount + (long long)rows * i;
     // generic row count: deposit one component at a time (same weights, same order per component)
     for (int r = 0; r < rows; ++r)
-        tally_segments<1, MCB_TM_GLOBAL, true>(sd, field, rows, r, true, bpos[3 * i], bpos[3 * i + 1], bpos[3 * i + 2],
+        tally_segments<1, MCB_TM_GLOBAL, true, false>(sd, field, rows, r, true, bpos[3 * i], bpos[3 * i + 1], bpos[3 * i + 2],
                                                epos[3 * i], epos[3 * i + 1], epos[3 * i + 2], a + r, threadIdx.x & 31u);
 }
 
