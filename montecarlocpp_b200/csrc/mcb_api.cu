@@ -100,6 +100,7 @@ struct mcb_ctx {
     DevBuf<long long> emit_cdf;
     DevBuf<double> state[2]; DevBuf<unsigned long long> imeta[2]; long long slots_alloc = 0;
     DevBuf<Counters> ctr; Counters* h_ctr = nullptr;     // pinned mirror
+    DevBuf<uint32_t> free_list;
     DevBuf<double> field;
 };
 
@@ -139,16 +140,18 @@ int check_problem(mcb_ctx* c, const mcb_problem_desc* p) {
     return MCB_OK;
 }
 
-template <int NCOMP, int TM, bool ND>
+template <int NCOMP, int TM, bool ND, bool EMIT>
 cudaError_t launch_step_inst(const StepParams& P, int grid, int block, size_t smem, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(k_step<NCOMP, TM, ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_step<NCOMP, TM, ND, EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k_step<NCOMP, TM, ND><<<grid, block, smem, s>>>(P);
+    k_step<NCOMP, TM, ND, EMIT><<<grid, block, smem, s>>>(P);
     return cudaGetLastError();
 }
 template <int NCOMP, int TM>
 cudaError_t launch_step_nd(const StepParams& P, bool nd, int grid, int block, size_t smem, cudaStream_t s) {
-    return nd ? launch_step_inst<NCOMP, TM, true>(P, grid, block, smem, s) : launch_step_inst<NCOMP, TM, false>(P, grid, block, smem, s);
+    const bool emit = P.free_list == nullptr;          // no free list -> emission happens inside k_step
+    if (nd) return emit ? launch_step_inst<NCOMP, TM, true, true>(P, grid, block, smem, s) : launch_step_inst<NCOMP, TM, true, false>(P, grid, block, smem, s);
+    return emit ? launch_step_inst<NCOMP, TM, false, true>(P, grid, block, smem, s) : launch_step_inst<NCOMP, TM, false, false>(P, grid, block, smem, s);
 }
 template <int NCOMP>
 cudaError_t launch_step_tm(const StepParams& P, int tm, bool nd, int grid, int block, size_t smem, cudaStream_t s) {
@@ -266,11 +269,29 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
     // previous launch; after the last particle dies one extra, empty launch has already been queued.
     const long long tail_slots = (long long)plan.grid * plan.block;      // one tile per CTA: finish in one launch
     int S_cur = plan.S;
+    // dense emission (default): k_step only lists free slots, k_emit fills them between launches; reserved_[0] = 1
+    // selects emission inside k_step instead
+    const bool dense = c->opt.reserved_[0] != 1;
+    bool host_all_emitted = false;
+    if (dense) {
+        CUDA_TRY(c, c->free_list.alloc((size_t)c->slots_alloc));
+        P.free_list = c->free_list.p;
+        k_free_init<<<(unsigned)((nslots + 255) / 256), 256, 0, c->stream>>>(c->free_list.p, nslots, c->ctr.p);
+        CUDA_TRY(c, cudaGetLastError());
+        launches++;
+    } else P.free_list = nullptr;
     long long steady_launches = 0; float steady_ms = 0.f;
     unsigned long long steady_steps = 0, steady_stores = 0, prev_steps = 0, prev_stores = 0;
     if (total > 0) for (long long it = 0;; ++it) {
         const int slot = (int)(it & 1);
         P.st = soa_of(c, cur, c->slots_alloc); P.nslots = nslots; P.steps_per_launch = S_cur;
+        if (dense && !host_all_emitted) {
+            // K1: fill the free slots listed by the previous k_step (all of them before the first), with full warps
+            k_emit<<<(unsigned)(c->sm_count * 4), 256, 0, c->stream>>>(P);
+            k_emit_commit<<<1, 1, 0, c->stream>>>(c->ctr.p, (unsigned long long)n_end);
+            CUDA_TRY(c, cudaGetLastError());
+            launches += 2;
+        }
         CUDA_TRY(c, cudaMemsetAsync(&c->ctr.p->live, 0, sizeof(unsigned long long), c->stream));   // rewritten by every launch
         const long long tiles = (nslots + plan.block - 1) / plan.block;
         const int grid = (int)std::min<long long>(plan.grid, std::max<long long>(tiles, 1));
@@ -286,6 +307,7 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
         float ms = 0.f; cudaEventElapsedTime(&ms, c->evA[prev], c->evB[prev]); step_ms_total += ms;
         const unsigned long long live = c->h_ctr[prev].live, next = c->h_ctr[prev].next;
         const bool all_emitted = next >= (unsigned long long)n_end;
+        host_all_emitted = all_emitted;
         if (!all_emitted) {          // launch it-1 ran with a full population: steady-phase accounting
             steady_launches++; steady_ms += ms;
             steady_steps += c->h_ctr[prev].steps - prev_steps; steady_stores += c->h_ctr[prev].stores - prev_stores;
@@ -379,7 +401,7 @@ void mcb_destroy(mcb_ctx* c) {
     c->mat_blob.release(); c->f_wprob.release(); c->f_pprob.release(); c->f_walias.release(); c->f_palias.release();
     c->geo_blob.release(); c->emitters.release(); c->cell_vol.release(); c->emit_cdf.release();
     for (int w = 0; w < 2; ++w) { c->state[w].release(); c->imeta[w].release(); }
-    c->ctr.release(); c->field.release();
+    c->ctr.release(); c->field.release(); c->free_list.release();
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
     if (c->ev0) cudaEventDestroy(c->ev0); if (c->ev1) cudaEventDestroy(c->ev1);
     for (int k = 0; k < 2; ++k) { if (c->evA[k]) cudaEventDestroy(c->evA[k]); if (c->evB[k]) cudaEventDestroy(c->evB[k]); if (c->evC[k]) cudaEventDestroy(c->evC[k]); }

@@ -291,7 +291,7 @@ __device__ __forceinline__ uint32_t collide(const StepParams& P, const Tables& T
 #ifndef MCB_BLOCK_MAX
 #define MCB_BLOCK_MAX 768
 #endif
-template <int NCOMP, int TM, bool ND>
+template <int NCOMP, int TM, bool ND, bool EMIT>
 __global__ void __launch_bounds__(MCB_BLOCK_MAX, 1) k_step(const StepParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
@@ -333,6 +333,9 @@ __global__ void __launch_bounds__(MCB_BLOCK_MAX, 1) k_step(const StepParams P) {
 
     unsigned long long my_steps = 0, my_esc = 0, my_emitted = 0, my_live = 0, my_stores = 0;
     bool exhausted = false;
+    // dense emission (EMIT == false): free slots are only LISTED here; k_emit fills them between launches with full
+    // warps (in-kernel emission of a few dead lanes per warp runs the long emission path at ~5 % lane efficiency)
+    const bool list_free = !EMIT && P.free_list != nullptr && P.ctr->next < P.n_end;
 
     for (long long base = (long long)blockIdx.x * blockDim.x; base < P.nslots; base += (long long)gridDim.x * blockDim.x) {
         const long long i = base + threadIdx.x;
@@ -355,9 +358,9 @@ __global__ void __launch_bounds__(MCB_BLOCK_MAX, 1) k_step(const StepParams P) {
         bool dirty = false;
         for (int s = 0; s < P.steps_per_launch; ++s) {
             // refill: a freed slot takes the next particle id (warp-aggregated ticket)
-            const bool want = valid && !ph.active && !exhausted && (P.refill || s == 0);
-            const unsigned m = __ballot_sync(0xFFFFFFFFu, want);
-            if (m) {
+            const bool want = EMIT && valid && !ph.active && !exhausted && (P.refill || s == 0);
+            const unsigned m = EMIT ? __ballot_sync(0xFFFFFFFFu, want) : 0u;
+            if (EMIT && m) {
                 unsigned long long ticket = 0;
                 const int leader = __ffs(m) - 1;
                 if ((int)lane == leader) ticket = atomicAdd(&P.ctr->next, (unsigned long long)__popc(m));
@@ -385,7 +388,7 @@ __global__ void __launch_bounds__(MCB_BLOCK_MAX, 1) k_step(const StepParams P) {
                 tally_segments<NCOMP, TM, ND, true>(T.sdom[ph.sdom], T.hist, P.rows, rbase, sg.ok, sg.bx, sg.by, sg.bz, sg.ex, sg.ey, sg.ez, amt, lane);
             }
             if (sg.ok) my_esc += collide(P, T, ph, sg);
-            if (__all_sync(0xFFFFFFFFu, !ph.active && (exhausted || !valid || !P.refill))) break;
+            if (__all_sync(0xFFFFFFFFu, !ph.active && (!EMIT || exhausted || !valid || !P.refill))) break;
         }
         if (valid && dirty) {
             my_stores++;
@@ -396,6 +399,17 @@ __global__ void __launch_bounds__(MCB_BLOCK_MAX, 1) k_step(const StepParams P) {
             st_stream(P.st.pidstep + i, (ph.pid << 24) | (unsigned long long)ph.step);
         }
         if (ph.active) my_live++;
+        if (!EMIT && list_free) {
+            const bool fr = valid && !ph.active;
+            const unsigned fm = __ballot_sync(0xFFFFFFFFu, fr);
+            if (fm) {
+                unsigned long long pos = 0;
+                const int leader = __ffs(fm) - 1;
+                if ((int)lane == leader) pos = atomicAdd(&P.ctr->nfree, (unsigned long long)__popc(fm));
+                pos = __shfl_sync(0xFFFFFFFFu, pos, leader);
+                if (fr) P.free_list[pos + __popc(fm & ((1u << lane) - 1u))] = (uint32_t)i;
+            }
+        }
     }
 
     // --- block-level reduction of the counters, one atomic per CTA
@@ -431,6 +445,38 @@ __global__ void __launch_bounds__(MCB_BLOCK_MAX, 1) k_step(const StepParams P) {
             else v = s_hist[i];
             if (v != 0.0) atomicAdd(P.field + i, v);
         }
+}
+
+// ------------------------------------------------------------------------------- k_emit
+// K1, dense: particle next+j is emitted into free slot free_list[j] (problem.cpp:386-399), all lanes busy.
+__global__ void __launch_bounds__(256) k_emit(const StepParams P) {
+    const unsigned long long next = P.ctr->next, nfree = P.ctr->nfree;
+    const unsigned long long room = P.n_end > next ? P.n_end - next : 0ull;
+    const unsigned long long n = nfree < room ? nfree : room;
+    Tables T;
+    T.lambda = reinterpret_cast<const double*>(P.mat_blob + P.mv.off_lambda);
+    T.nw = P.mv.nw; T.np = P.mv.np; T.inv_bucket_w = P.mv.inv_bucket_w; T.inv_bucket_p = P.mv.inv_bucket_p;
+    for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (unsigned long long)gridDim.x * blockDim.x) {
+        const long long i = (long long)P.free_list[j];
+        Particle ph;
+        emit_particle(P, T, next + j, ph);
+        P.st.px[i] = ph.px; P.st.py[i] = ph.py; P.st.pz[i] = ph.pz;
+        P.st.dx[i] = ph.dx; P.st.dy[i] = ph.dy; P.st.dz[i] = ph.dz; P.st.sn[i] = ph.sn;
+        P.st.meta[i] = pack_meta(ph.wp, ph.sign, ph.active, ph.killed, ph.sdom, ph.nscat);
+        P.st.pidstep[i] = (ph.pid << 24) | (unsigned long long)ph.step;
+    }
+}
+// after k_emit: advance the particle counter, empty the free list (one thread)
+__global__ void k_emit_commit(Counters* ctr, unsigned long long n_end) {
+    const unsigned long long room = n_end > ctr->next ? n_end - ctr->next : 0ull;
+    const unsigned long long n = ctr->nfree < room ? ctr->nfree : room;
+    ctr->next += n; ctr->emitted += n; ctr->nfree = 0;
+}
+// all slots free: free_list = 0..n-1
+__global__ void k_free_init(uint32_t* free_list, long long n, Counters* ctr) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) free_list[i] = (uint32_t)i;
+    if (i == 0) ctr->nfree = (unsigned long long)n;
 }
 
 // ---------------------------------------------------------------------------- k_compact
