@@ -227,6 +227,20 @@ def run_ours(args):
     barrier()
     e2e_elapsed = time.perf_counter() - t1
 
+    # ---- the other schedule, for reference: resident mode (S = 16 loop trips per state round trip, 8 tiles per thread)
+    other = None
+    if args.mode == "streaming":
+        ctx.set_options(steps_per_launch=16, slots=148 * 768 * 8)
+        one_step(50)
+        barrier()
+        t2 = time.perf_counter()
+        osteps = 0
+        for i in range(3):
+            osteps += one_step(3000 + i)["steps"]
+        barrier()
+        other = (osteps, time.perf_counter() - t2)
+        ctx.set_options(steps_per_launch=S, slots=args.slots)
+
     vals = torch.tensor([elapsed, e2e_elapsed, float(tot["steps"]), float(e2e_steps), float(tot["launches"])],
                         dtype=torch.float64, device="cuda")
     if world > 1:
@@ -283,6 +297,10 @@ def run_ours(args):
                        "k_step_share_of_step": tot["step_ms"] * 1e-3 / elapsed},
             "phonon_steps_per_solve": tot["steps"] / args.steps, "esc": tot["esc"],
         }
+        if other is not None:
+            line["resident_mode"] = {"value_per_gpu": other[0] / other[1], "unit": "phonon-steps/s", "steps_per_launch": 16,
+                                     "slots": 148 * 768 * 8, "note": "rank-0 rate of the max-throughput schedule (state kept in "
+                                     "registers for 16 loop trips per HBM round trip); not the mode the roofline is quoted on"}
         if not args.no_cpu_baseline and world == 1:      # reported on rank 0 at N=1 only
             rate, dt, steps, cores, n = cpu_reference_rate(args.workload, n_total, args.cpu_sample, 4242)
             line["cpu_baseline"] = {"value": rate, "unit": "phonon-steps/s", "cores": cores, "kind": "port",
