@@ -194,8 +194,12 @@ typedef struct mcb_options {
     int32_t ctas_per_sm;       /* persistent grid = ctas_per_sm * SM count            */
     int32_t tally_mode;        /* 0 auto, 1 warp-private smem histograms, 2 global    */
                                /* field (fp64 RED in L2), 3 one smem histogram per CTA */
-    int32_t sort_every;        /* launches between compaction/sort passes (0 = auto)  */
-    int32_t reserved_[2];
+    int32_t decay_mode;        /* 0: once nothing is left to emit use S >= 16, compact,  */
+                               /*    then run the last survivors to termination;         */
+                               /* 1: keep steps_per_launch throughout (compaction only)  */
+    int32_t emit_mode;         /* 0: dense emission kernel between step launches;        */
+                               /* 1: emit inside the step kernel (slot refilled at once) */
+    int32_t reserved_;
 } mcb_options;
 
 typedef struct mcb_ctx mcb_ctx;

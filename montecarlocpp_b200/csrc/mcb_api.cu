@@ -269,9 +269,9 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
     // previous launch; after the last particle dies one extra, empty launch has already been queued.
     const long long tail_slots = (long long)plan.grid * plan.block;      // one tile per CTA: finish in one launch
     int S_cur = plan.S;
-    // dense emission (default): k_step only lists free slots, k_emit fills them between launches; reserved_[0] = 1
+    // dense emission (default): k_step only lists free slots, k_emit fills them between launches; emit_mode = 1
     // selects emission inside k_step instead
-    const bool dense = c->opt.reserved_[0] != 1;
+    const bool dense = c->opt.emit_mode != 1;
     bool host_all_emitted = false;
     if (dense) {
         CUDA_TRY(c, c->free_list.alloc((size_t)c->slots_alloc));
@@ -333,7 +333,7 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
         }
         // decay phase (nothing left to emit): launches are no longer full, so amortise them over >= 16 loop trips;
         // once the survivors fit one tile per CTA let every thread run its phonon to termination
-        if (all_emitted && c->opt.sort_every != -1) {
+        if (all_emitted && c->opt.decay_mode != 1) {
             S_cur = std::max(plan.S, 16);
             if ((long long)live <= tail_slots) S_cur = (int)std::min<long long>(std::max<long long>(prob->maxloop, 1), 1 << 22);
         }
@@ -411,7 +411,7 @@ void mcb_destroy(mcb_ctx* c) {
 
 int mcb_set_options(mcb_ctx* c, const mcb_options* o) {
     if (!c || !o) return MCB_EINVAL;
-    if (o->slots < 0 || o->steps_per_launch < 0 || o->block < 0 || o->ctas_per_sm < 0 || o->tally_mode < 0 || o->tally_mode > 3) {
+    if (o->slots < 0 || o->steps_per_launch < 0 || o->block < 0 || o->ctas_per_sm < 0 || o->tally_mode < 0 || o->tally_mode > 3 || o->decay_mode < 0 || o->decay_mode > 1 || o->emit_mode < 0 || o->emit_mode > 1) {
         c->err = "negative / unknown option"; return MCB_EINVAL;
     }
     c->opt = *o;

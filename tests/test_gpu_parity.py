@@ -140,11 +140,11 @@ def test_schedule_options_do_not_change_results(gpu_ctx, omats, opts):
     mat, dom = omats["silicon"], cases.film()
     cases.upload(gpu_ctx, mat, dom)
     prob = orc.Problem(mat, dom, "multi", 30000, 25)
-    gpu_ctx.set_options(slots=0, steps_per_launch=0, block=0, ctas_per_sm=0, tally_mode=0)
+    gpu_ctx.set_options(slots=0, steps_per_launch=0, block=0, ctas_per_sm=0, tally_mode=0, emit_mode=0, decay_mode=0)
     base, bst = gpu_ctx.solve(prob.desc, seed=SEED)
-    gpu_ctx.set_options(**{**dict(slots=0, steps_per_launch=0, block=0, ctas_per_sm=0, tally_mode=0), **opts})
+    gpu_ctx.set_options(**{**dict(slots=0, steps_per_launch=0, block=0, ctas_per_sm=0, tally_mode=0, emit_mode=0, decay_mode=0), **opts})
     got, gst = gpu_ctx.solve(prob.desc, seed=SEED)
-    gpu_ctx.set_options(slots=0, steps_per_launch=0, block=0, ctas_per_sm=0, tally_mode=0)
+    gpu_ctx.set_options(slots=0, steps_per_launch=0, block=0, ctas_per_sm=0, tally_mode=0, emit_mode=0, decay_mode=0)
     assert (gst["steps"], gst["esc"], gst["emitted"]) == (bst["steps"], bst["esc"], bst["emitted"])
     scale = np.abs(base).max(axis=1, keepdims=True)
     assert (np.abs(got - base) <= 1e-9 * scale).all()
