@@ -272,6 +272,36 @@ typedef struct mcb_trace_out {
 int  mcb_trace(mcb_ctx* ctx, const mcb_problem_desc* prob, uint64_t seed,
                int64_t n_begin, int64_t n_end, int64_t nsteps, mcb_trace_out* out);
 
+/* ------------------------------------------------------------- trajectories ---
+ * TrajProblem::solve (problem.cpp:226-299): ONE particle traced for up to maxloop loop trips, recording the
+ * polyline TrkPhonon keeps (phonon.cpp:129-170: start position, the position after every move, and the
+ * image position after a periodic wrap) and, per loop trip, the boundary it sat on and the boundary it reached
+ * (what the reference prints as `sdom: bdry type -> bdry type`).  Members of TrajProblem (problem.h:89-119):
+ * optional prop_, pos_, dir_; maxscat_, maxloop_.  `sdom` is Domain::locate(pos) (domain.cpp:59-67) when has_pos.
+ */
+typedef struct mcb_traj_desc {
+    int32_t has_prop, has_pos, has_dir, sdom;
+    int64_t w, p;
+    double  pos[3], dir[3];
+    int64_t maxscat, maxloop;          /* maxloop already defaulted (100 * maxscat when 0, problem.cpp:262) */
+} mcb_traj_desc;
+
+typedef struct mcb_traj_out {
+    int64_t  max_points;  double*  points;     /* [3 * max_points] xyz interleaved; needs >= 2*maxloop + 1 */
+    int64_t  max_steps;                        /* >= maxloop */
+    int32_t* step_sdom;                        /* [max_steps] subdomain index at the start of the trip        */
+    int32_t* step_in;                          /* [max_steps] index of the boundary it sits on within that    */
+    int32_t* step_in_kind;                     /*             subdomain's bdryPtrs(), -1 = none; MCB_BDRY_*   */
+    int32_t* step_out;                         /* [max_steps] boundary reached by advect, -1 = none (scatter) */
+    int32_t* step_out_kind;
+    int64_t  npoints, nsteps;                  /* filled by the call */
+    int32_t  escaped;                          /* 0; 1 = killed inside advect (subdomain.cpp:182-189);   */
+                                               /* 2 = failed Inter hand-off (boundary.cpp:357-358)       */
+    int32_t  pad_;
+} mcb_traj_out;
+
+int  mcb_traj(mcb_ctx* ctx, const mcb_traj_desc* traj, uint64_t seed, mcb_traj_out* out);
+
 /* Subdomain::coord + coord2index (subdomain.cpp:148-159) on caller-supplied
  * positions: bit-exact integer parity probe. pos [3n], sdom [n] -> index [3n]. */
 int  mcb_cell_index(mcb_ctx* ctx, int64_t n, const double* pos, const int32_t* sdom,

@@ -92,6 +92,41 @@ class TraceOut(C.Structure):
                 ("sdom", c_int32_p), ("nscat", c_int64_p), ("steps", c_int64_p), ("cell", c_int32_p)]
 
 
+class TrajDesc(C.Structure):
+    _fields_ = [("has_prop", C.c_int32), ("has_pos", C.c_int32), ("has_dir", C.c_int32), ("sdom", C.c_int32),
+                ("w", C.c_int64), ("p", C.c_int64), ("pos", C.c_double * 3), ("dir", C.c_double * 3),
+                ("maxscat", C.c_int64), ("maxloop", C.c_int64)]
+
+
+class TrajOut(C.Structure):
+    _fields_ = [("max_points", C.c_int64), ("points", c_double_p), ("max_steps", C.c_int64),
+                ("step_sdom", c_int32_p), ("step_in", c_int32_p), ("step_in_kind", c_int32_p),
+                ("step_out", c_int32_p), ("step_out_kind", c_int32_p),
+                ("npoints", C.c_int64), ("nsteps", C.c_int64), ("escaped", C.c_int32), ("pad_", C.c_int32)]
+
+
+def traj_buffers(maxloop):
+    """Buffers for one trajectory of up to `maxloop` loop trips and the TrajOut pointing at them."""
+    import numpy as np
+    bufs = {"points": np.zeros((2 * maxloop + 1, 3), np.float64)}
+    for k in ("step_sdom", "step_in", "step_in_kind", "step_out", "step_out_kind"):
+        bufs[k] = np.full(max(maxloop, 1), -9, np.int32)
+    out = TrajOut()
+    out.max_points, out.max_steps = 2 * maxloop + 1, max(maxloop, 1)
+    out.points = bufs["points"].ctypes.data_as(c_double_p)
+    for k in ("step_sdom", "step_in", "step_in_kind", "step_out", "step_out_kind"):
+        setattr(out, k, bufs[k].ctypes.data_as(c_int32_p))
+    return bufs, out
+
+
+def traj_result(bufs, out):
+    n, m = out.npoints, out.nsteps
+    r = {"points": bufs["points"][:n].copy(), "escaped": bool(out.escaped)}
+    for k in ("step_sdom", "step_in", "step_in_kind", "step_out", "step_out_kind"):
+        r[k] = bufs[k][:m].copy()
+    return r
+
+
 def trace_buffers(n):
     """Allocate numpy buffers for an n-particle trace and the TraceOut that points at them."""
     import numpy as np

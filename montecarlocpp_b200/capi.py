@@ -17,7 +17,7 @@ SYMBOLS = [
     "mcb_create", "mcb_destroy", "mcb_last_error", "mcb_abi_version", "mcb_set_options", "mcb_get_options",
     "mcb_upload_material", "mcb_upload_domain", "mcb_field_cols", "mcb_solve", "mcb_solve_raw_dev",
     "mcb_finalize_dev", "mcb_stream", "mcb_trace", "mcb_cell_index", "mcb_accumulate", "mcb_get_alias",
-    "mcb_philox_words",
+    "mcb_philox_words", "mcb_traj",
 ]
 
 _lib = None
@@ -50,6 +50,7 @@ def lib():
         L.mcb_finalize_dev.argtypes = [vp, C.POINTER(abi.ProblemDesc), vp]
         L.mcb_stream.argtypes = [vp, C.POINTER(vp)]
         L.mcb_trace.argtypes = [vp, C.POINTER(abi.ProblemDesc), C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.POINTER(abi.TraceOut)]
+        L.mcb_traj.argtypes = [vp, C.POINTER(abi.TrajDesc), C.c_uint64, C.POINTER(abi.TrajOut)]
         L.mcb_cell_index.argtypes = [vp, C.c_int64, dp, ip, lp]
         L.mcb_accumulate.argtypes = [vp, C.c_int32, C.c_int64, ip, dp, dp, dp, dp]
         L.mcb_get_alias.argtypes = [vp, C.c_int, dp, ip, dp, ip]
@@ -131,6 +132,11 @@ class Context:
         bufs, out = abi.trace_buffers(n_end - n_begin)
         self._check(lib().mcb_trace(self.h, C.byref(prob_desc), seed, n_begin, n_end, nsteps, C.byref(out)))
         return bufs
+
+    def traj(self, traj_desc, seed):
+        bufs, out = abi.traj_buffers(traj_desc.maxloop)
+        self._check(lib().mcb_traj(self.h, C.byref(traj_desc), seed, C.byref(out)))
+        return abi.traj_result(bufs, out)
 
     def cell_index(self, pos, sdom):
         pos = np.ascontiguousarray(pos, np.float64); sdom = np.ascontiguousarray(sdom, np.int32)

@@ -669,6 +669,36 @@ int mcb_trace(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
     return MCB_OK;
 }
 
+int mcb_traj(mcb_ctx* c, const mcb_traj_desc* t, uint64_t seed, mcb_traj_out* o) {
+    if (!c) return MCB_EINVAL;
+    if (!c->has_mat || !c->has_dom) { c->err = "upload material and domain before solving"; return MCB_ESTATE; }
+    if (!t || !o || !o->points || !o->step_sdom || !o->step_in || !o->step_in_kind || !o->step_out || !o->step_out_kind ||
+        o->max_points < 1 || o->max_steps < 1) { c->err = "bad trajectory buffers"; return MCB_EINVAL; }
+    if (t->maxloop < 0 || t->maxloop > MCB_MAX_LOOP || t->maxscat < 0) { c->err = "maxloop / maxscat out of range"; return MCB_EINVAL; }
+    if (t->has_prop && (t->w < 0 || t->w >= c->nw || t->p < 0 || t->p >= c->np)) { c->err = "prop out of range"; return MCB_EINVAL; }
+    if (t->has_pos && (t->sdom < 0 || t->sdom >= c->gv.nsdom)) { c->err = "Position not inside domain"; return MCB_EINVAL; }   // problem.cpp:242
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    StepParams P; std::memset(&P, 0, sizeof P);
+    P.mat_blob = c->mat_blob.p; P.mv = c->mv; P.geo_blob = c->geo_blob.p; P.gv = c->gv;
+    P.emitters = c->emitters.p; P.nemitter = c->nemitter; P.seed = seed; P.maxscat = t->maxscat; P.maxloop = t->maxloop;
+    DevBuf<double> dpts; DevBuf<int32_t> ds[5]; DevBuf<long long> dcnt;
+    CUDA_TRY(c, dpts.alloc((size_t)o->max_points * 3)); CUDA_TRY(c, dcnt.alloc(3));
+    for (int k = 0; k < 5; ++k) CUDA_TRY(c, ds[k].alloc((size_t)o->max_steps));
+    TrajDev dev{dpts.p, o->max_points, o->max_steps, ds[0].p, ds[1].p, ds[2].p, ds[3].p, ds[4].p, dcnt.p};
+    k_traj<<<1, 32, 0, c->stream>>>(P, *t, dev);
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    long long cnt[3];
+    CUDA_TRY(c, cudaMemcpy(cnt, dcnt.p, sizeof cnt, cudaMemcpyDeviceToHost));
+    o->npoints = cnt[0]; o->nsteps = cnt[1]; o->escaped = (int32_t)cnt[2];
+    const long long np = std::min<long long>(cnt[0], o->max_points), ns = std::min<long long>(cnt[1], o->max_steps);
+    CUDA_TRY(c, cudaMemcpy(o->points, dpts.p, (size_t)np * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    int32_t* host[5] = {o->step_sdom, o->step_in, o->step_in_kind, o->step_out, o->step_out_kind};
+    for (int k = 0; k < 5; ++k) CUDA_TRY(c, cudaMemcpy(host[k], ds[k].p, (size_t)ns * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    dpts.release(); dcnt.release(); for (int k = 0; k < 5; ++k) ds[k].release();
+    return MCB_OK;
+}
+
 int mcb_cell_index(mcb_ctx* c, int64_t n, const double* pos, const int32_t* sdom, int64_t* index) {
     if (!c) return MCB_EINVAL;
     if (!c->has_dom) { c->err = "upload a domain first"; return MCB_ESTATE; }

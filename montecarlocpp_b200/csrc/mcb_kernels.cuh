@@ -76,14 +76,8 @@ __device__ __forceinline__ double draw_scat_next(Rng& g, double lambda) {
     return d;
 }
 
-// problem.cpp:386-399 for particle `pid`: pick emitter, drawFluxProp, Emitter::emit, drawScatNext
-__device__ __noinline__ void emit_particle(const StepParams& P, const Tables& T, unsigned long long pid, Particle& ph) {
-    // emitter = upper_bound(emitCdf, n)  (problem.cpp:386-387)
-    int lo = 0, hi = P.nemitter;
-    while (lo < hi) { int mid = (lo + hi) >> 1; if ((long long)pid < P.emit_cdf[mid]) hi = mid; else lo = mid + 1; }
-    const DEmitter& E = P.emitters[lo];
-    Rng g; g.begin(P.seed, pid, 0u);
-    uint32_t wp = draw_prop(g, T, P.f_wprob, P.f_walias, P.f_pprob, P.f_palias);
+// Emitter::emit (boundary.cpp:378-385): position, direction and sign from one emitter
+__device__ __forceinline__ void emit_from(const DEmitter& E, Rng& g, Particle& ph) {
     double px, py, pz, dx, dy, dz; uint32_t sign;
     if (E.kind == MCB_EMIT_SDOM) {
         // ParallelepipedImpl::drawPos subdomain.cpp:275-281 ; drawDir :255-258 ; emitSign :260-263
@@ -106,8 +100,19 @@ __device__ __noinline__ void emit_particle(const StepParams& P, const Tables& T,
     }
     normalize3(dx, dy, dz);                                  // Phonon ctor phonon.cpp:33-37
     ph.px = px; ph.py = py; ph.pz = pz; ph.dx = dx; ph.dy = dy; ph.dz = dz;
-    ph.wp = wp; ph.sign = sign; ph.active = P.maxloop > 0 ? 1u : 0u; ph.killed = 0; ph.sdom = (uint32_t)E.sdom; ph.nscat = 0; ph.step = 0;
-    ph.pid = pid;
+    ph.sign = sign; ph.killed = 0; ph.sdom = (uint32_t)E.sdom; ph.nscat = 0; ph.step = 0;
+}
+
+// problem.cpp:386-399 for particle `pid`: pick emitter, drawFluxProp, Emitter::emit, drawScatNext
+__device__ __noinline__ void emit_particle(const StepParams& P, const Tables& T, unsigned long long pid, Particle& ph) {
+    // emitter = upper_bound(emitCdf, n)  (problem.cpp:386-387)
+    int lo = 0, hi = P.nemitter;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if ((long long)pid < P.emit_cdf[mid]) hi = mid; else lo = mid + 1; }
+    const DEmitter& E = P.emitters[lo];
+    Rng g; g.begin(P.seed, pid, 0u);
+    const uint32_t wp = draw_prop(g, T, P.f_wprob, P.f_walias, P.f_pprob, P.f_palias);
+    emit_from(E, g, ph);
+    ph.wp = wp; ph.active = P.maxloop > 0 ? 1u : 0u; ph.pid = pid;
     ph.sn = draw_scat_next(g, T.lambda[wp]);
 }
 
@@ -140,6 +145,7 @@ __device__ __forceinline__ bool is_inside(const Tables& T, const DSdom& sd, doub
 struct Segment {                  // what one advect produced
     double bx, by, bz, ex, ey, ez, d;
     int hit; uint32_t nscat_before; bool ok;
+    int next_plane;               // set by collide(): the boundary the particle sits on afterwards (-1: none)
 };
 
 // First half of a loop trip (problem.cpp:403-412): Subdomain::advect + Phonon::move.  Returns escapes (0/1).
@@ -212,9 +218,10 @@ __device__ __forceinline__ uint32_t advect_move(const Tables& T, Particle& ph, S
 }
 
 // Second half of a loop trip (problem.cpp:418-434): Boundary::scatter or Material::scatter, then the stop test.
-__device__ __forceinline__ uint32_t collide(const StepParams& P, const Tables& T, Particle& ph, const Segment& sg) {
+__device__ __forceinline__ uint32_t collide(const StepParams& P, const Tables& T, Particle& ph, Segment& sg) {
     uint32_t esc = 0;
     const int hit = sg.hit;
+    sg.next_plane = hit;
     if (hit >= 0) {                                                            // problem.cpp:418-429
         const DPlaneCold& cb = T.cold[hit];
         const int kind = cb.kind;
@@ -235,7 +242,8 @@ __device__ __forceinline__ uint32_t collide(const StepParams& P, const Tables& T
             matvec(cb.m, ph.dx, ph.dy, ph.dz, nx, ny, nz);
             ph.dx = nx; ph.dy = ny; ph.dz = nz;
             normalize3(ph.dx, ph.dy, ph.dz);
-            ph.sdom = (uint32_t)T.cold[T.pairs[cb.pair_begin]].sdom;
+            sg.next_plane = T.pairs[cb.pair_begin];
+            ph.sdom = (uint32_t)T.cold[sg.next_plane].sdom;
         } else if (kind == MCB_BDRY_INTER) {                                   // boundary.cpp:349-359
             int target = -1;
             if (cb.pair_count == 1) target = T.pairs[cb.pair_begin];
@@ -245,6 +253,7 @@ __device__ __forceinline__ uint32_t collide(const StepParams& P, const Tables& T
             }
             if (target < 0) { ph.killed = 1; ph.active = 0; esc = 1; }         // problem.cpp:422-426
             else ph.sdom = (uint32_t)T.cold[target].sdom;
+            sg.next_plane = target;
         } else {                                                               // Isot boundary.cpp:455-460
             ph.killed = 1; ph.active = 0;
         }
@@ -477,6 +486,75 @@ __global__ void k_free_init(uint32_t* free_list, long long n, Counters* ctr) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) free_list[i] = (uint32_t)i;
     if (i == 0) ctr->nfree = (unsigned long long)n;
+}
+
+// ------------------------------------------------------------------------------- k_traj
+// TrajProblem::solve (problem.cpp:226-299) for ONE particle (id 0), recording TrkPhonon's polyline
+// (phonon.cpp:129-170) and the per-trip boundary trace.  Diagnostic: a single thread, tables read from global memory.
+struct TrajDev {
+    double* points; long long max_points; long long max_steps;
+    int32_t *step_sdom, *step_in, *step_in_kind, *step_out, *step_out_kind;
+    long long* counts;            // [0] npoints, [1] nsteps, [2] escaped
+};
+__global__ void k_traj(const StepParams P, const mcb_traj_desc t, const TrajDev o) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    Tables T;
+    T.lambda = reinterpret_cast<const double*>(P.mat_blob + P.mv.off_lambda);
+    T.inv_vel = reinterpret_cast<const double*>(P.mat_blob + P.mv.off_inv_vel);
+    T.wprob = reinterpret_cast<const double*>(P.mat_blob + P.mv.off_wprob);
+    T.pprob = reinterpret_cast<const double*>(P.mat_blob + P.mv.off_pprob);
+    T.walias = reinterpret_cast<const uint16_t*>(P.mat_blob + P.mv.off_walias);
+    T.palias = reinterpret_cast<const uint8_t*>(P.mat_blob + P.mv.off_palias);
+    T.hot = reinterpret_cast<const DPlaneHot*>(P.geo_blob + P.gv.off_hot);
+    T.cold = reinterpret_cast<const DPlaneCold*>(P.geo_blob + P.gv.off_cold);
+    T.sdom = reinterpret_cast<const DSdom*>(P.geo_blob + P.gv.off_sdom);
+    T.pairs = reinterpret_cast<const int32_t*>(P.geo_blob + P.gv.off_pairs);
+    T.nw = P.mv.nw; T.np = P.mv.np; T.inv_bucket_w = P.mv.inv_bucket_w; T.inv_bucket_p = P.mv.inv_bucket_p; T.hist = nullptr;
+
+    long long npts = 0, nsteps = 0, escaped = 0;
+    auto push = [&](double x, double y, double z) {
+        if (npts < o.max_points) { o.points[3 * npts] = x; o.points[3 * npts + 1] = y; o.points[3 * npts + 2] = z; }
+        npts++;
+    };
+    Particle ph; ph.pid = 0; ph.active = 1; ph.killed = 0; ph.nscat = 0; ph.step = 0; ph.sign = 1;
+    Rng g; g.begin(P.seed, 0ull, 0u);
+    ph.wp = t.has_prop ? (uint32_t)(t.w * T.np + t.p) : draw_prop(g, T, T.wprob, T.walias, T.pprob, T.palias);   // :232
+    int cur = -1;
+    if (t.has_pos) {                                                                                          // :233-243
+        ph.px = t.pos[0]; ph.py = t.pos[1]; ph.pz = t.pos[2];
+        if (t.has_dir) { ph.dx = t.dir[0]; ph.dy = t.dir[1]; ph.dz = t.dir[2]; }
+        else draw_iso(g, ph.dx, ph.dy, ph.dz);
+        normalize3(ph.dx, ph.dy, ph.dz);
+        ph.sdom = (uint32_t)t.sdom;
+    } else {                                                                                                  // :244-253
+        const DEmitter& E = P.emitters[g.uint_below((uint32_t)P.nemitter)];
+        const uint32_t wp = ph.wp;
+        emit_from(E, g, ph);
+        ph.wp = wp; ph.active = 1; ph.pid = 0;
+        cur = E.kind == MCB_EMIT_BDRY ? E.index : -1;
+    }
+    push(ph.px, ph.py, ph.pz);
+    ph.sn = draw_scat_next(g, T.lambda[ph.wp]);                                                               // :254
+    for (long long i = 0; i < P.maxloop; ++i) {                                                               // :258
+        const DSdom& sd = T.sdom[ph.sdom];
+        const long long k = nsteps++;
+        const int in_local = (cur >= sd.plane_begin && cur < sd.plane_begin + sd.plane_count) ? cur - sd.plane_begin : -1;
+        if (k < o.max_steps) {
+            o.step_sdom[k] = (int32_t)ph.sdom; o.step_in[k] = in_local; o.step_in_kind[k] = cur >= 0 ? T.cold[cur].kind : -1;
+            o.step_out[k] = -1; o.step_out_kind[k] = -1;
+        }
+        Segment sg; sg.ok = false; sg.hit = -1; sg.next_plane = -1;
+        const uint32_t esc = advect_move(T, ph, sg);                                                          // :265
+        push(ph.px, ph.py, ph.pz);
+        if (esc) { escaped = 1; break; }                                                                      // :267-271
+        if (k < o.max_steps) { o.step_out[k] = sg.hit >= 0 ? sg.hit - sd.plane_begin : -1; o.step_out_kind[k] = sg.hit >= 0 ? T.cold[sg.hit].kind : -1; }
+        const bool peri = sg.hit >= 0 && T.cold[sg.hit].kind == MCB_BDRY_PERI;
+        if (collide(P, T, ph, sg)) { escaped = 2; break; }                                                    // :277-294
+        if (peri) push(ph.px, ph.py, ph.pz);
+        cur = sg.next_plane;
+        if (!ph.active) break;                                                                                // :295
+    }
+    o.counts[0] = npts; o.counts[1] = nsteps; o.counts[2] = escaped;
 }
 
 // ---------------------------------------------------------------------------- k_compact

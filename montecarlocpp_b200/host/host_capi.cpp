@@ -92,4 +92,29 @@ int mcbh_problem_solve_seeded(const mcbh_problem* p, int device, uint64_t seed, 
     , MCB_EINVAL)
 }
 
+// TrajProblem(mat, dom, [prop], [pos], [dir], maxscat, maxloop).solve(mt19937(mt_seed)): polyline out (3 x npoints,
+// column-major); prints the per-trip lines to stdout like the reference.  Returns npoints or < 0.
+int64_t mcbh_traj(const Material* mat, const mcbh_domain* dom, int has_prop, int64_t w, int64_t p, int has_pos, const double* pos,
+                  int has_dir, const double* dir, int64_t maxscat, int64_t maxloop, int device, uint32_t mt_seed,
+                  double* points, int64_t max_points) {
+    MCBH_TRY(
+        FieldProblem::device(device);
+        const Domain* D = dom->dom.get();
+        std::unique_ptr<TrajProblem> tp;
+        TrajProblem::Prop pr(w, p);
+        Vector3d P = has_pos ? Vector3d(pos[0], pos[1], pos[2]) : Vector3d(); Vector3d Dv = has_dir ? Vector3d(dir[0], dir[1], dir[2]) : Vector3d();
+        if (has_prop && has_pos && has_dir) tp.reset(new TrajProblem(mat, D, pr, P, Dv, maxscat, maxloop));
+        else if (has_prop && has_pos) tp.reset(new TrajProblem(mat, D, pr, P, maxscat, maxloop));
+        else if (has_pos && has_dir) tp.reset(new TrajProblem(mat, D, P, Dv, maxscat, maxloop));
+        else if (has_pos) tp.reset(new TrajProblem(mat, D, P, maxscat, maxloop));
+        else tp.reset(new TrajProblem(mat, D, maxscat, maxloop));
+        Rng gen(mt_seed);
+        Progress prog = tp->initProgress();
+        ArrayXXd sol = tp->solve(gen, &prog);
+        const int64_t n = std::min<int64_t>(sol.cols(), max_points);
+        std::memcpy(points, sol.data(), sizeof(double) * 3 * (size_t)n);
+        return (int64_t)sol.cols();
+    , -1)
+}
+
 } // extern "C"

@@ -7,10 +7,11 @@
 //   bulk dim div0 | film dim0 dim1 div1 | jct dim0 dim3 | tee dim0 dim4 div0 | tube dim0 dim1 dim3 div1 div3
 //   slab dim0 dim1 div0 dT | wire dim0 dim1 div1        (not in the reference; see domain.h)
 //   temp|flux|multi nemit maxscat maxloop nsim | cumtemp|cumflux nemit size maxscat maxloop nsim
+//   check r00 r01 r02 r10 r11 r12 r20 r21 r22 | traj px py pz dx dy dz maxscat maxloop
 //
 // Differences from the reference driver: the solve runs on the GPU and is called once per repetition from
-// the main thread (the reference opens an OpenMP region and sums per-thread partials); `check`/`traj`
-// (TrajProblem) and the hex/pyr/octet domains are not built.
+// the main thread (the reference opens an OpenMP region and sums per-thread partials); the hex/pyr/octet
+// domains (non-box cells) are not built.
 #include <unistd.h>
 #include <iomanip>
 #include <iostream>
@@ -39,6 +40,44 @@ static void printSolution(const ArrayXXd& sol) {
     }
     std::cout << std::endl;
     std::cout.flags(mask);
+}
+
+static ArrayXXd solveTraj(const TrajProblem* prob, const Clock& clk) {          // main.cpp:86-102
+    static long n = 0;
+    std::cout << "Trajectory " << n++ << std::endl;
+    Progress prog = prob->initProgress();
+    prog.clock(clk);
+    Seed s = getSeed();
+    std::cout << "  seeds: " << s << ' ' << std::endl;
+    Rng gen(s);
+    ArrayXXd sol = prob->solve(gen, &prog);
+    printSolution(sol);
+    return sol;
+}
+
+// main.cpp:104-143: from every checkpoint of the domain fire +-rot.col(0..2) with maxscat = maxloop = 2 and join the
+// polylines, NaN-separated, for plotting
+static ArrayXXd checkDomain(const Material* mat, const Domain* dom, const Matrix3d& rot, const Clock& clk) {
+    std::vector<ArrayXXd> traj;
+    std::vector<long> ind(1, 0);
+    const Matrix3Xd pts = dom->checkpoints();
+    for (long p = 0; p < pts.cols(); ++p) {
+        for (int i = 0; i < 6; ++i) {
+            Vector3d dir = rot.col(i % 3);
+            if (i >= 3) dir = -dir;
+            TrajProblem prob(mat, dom, pts.col(p), dir, 2, 2);
+            std::cout << prob << std::endl << std::endl;
+            traj.push_back(solveTraj(&prob, clk));
+            ind.push_back(ind.back() + traj.back().cols() + 1);
+        }
+    }
+    ArrayXXd sol(3, ind.back() - 1);
+    for (long j = 0; j < sol.cols(); ++j) for (int k = 0; k < 3; ++k) sol(k, j) = Dbl::quiet_NaN();
+    for (size_t n = 0; n < traj.size(); ++n)
+        for (long j = 0; j < traj[n].cols(); ++j) for (int k = 0; k < 3; ++k) sol(k, ind[n] + j) = traj[n](k, j);
+    std::cout << "Combined Trajectory" << std::endl;
+    printSolution(sol);
+    return sol;
 }
 
 static ArrayXXd solveField(const FieldProblem* prob, const Clock& clk) {
@@ -121,7 +160,19 @@ int main(int argc, const char* argv[]) {
         std::string probStr; argss >> probStr;
         long nemit = 0, size = 0, maxscat = 0, maxloop = 0, nsim = 0;
         std::unique_ptr<FieldProblem> prob;
-        if (probStr == "temp") { argss >> nemit >> maxscat >> maxloop >> nsim; prob.reset(new TempProblem(mat.get(), dom.get(), nemit, maxscat, maxloop)); }
+        if (probStr == "check") {
+            Matrix3d rot;
+            argss >> rot(0, 0) >> rot(0, 1) >> rot(0, 2) >> rot(1, 0) >> rot(1, 1) >> rot(1, 2) >> rot(2, 0) >> rot(2, 1) >> rot(2, 2);
+            MC_ASSERT_MSG(!argss.fail(), "Invalid problem arguments");
+            checkDomain(mat.get(), dom.get(), rot, clk);
+        } else if (probStr == "traj") {
+            Vector3d pos, dir;
+            argss >> pos(0) >> pos(1) >> pos(2) >> dir(0) >> dir(1) >> dir(2) >> maxscat >> maxloop;
+            MC_ASSERT_MSG(!argss.fail(), "Invalid problem arguments");
+            TrajProblem tp(mat.get(), dom.get(), pos, dir, maxscat, maxloop);
+            std::cout << tp << std::endl << std::endl;
+            solveTraj(&tp, clk);
+        } else if (probStr == "temp") { argss >> nemit >> maxscat >> maxloop >> nsim; prob.reset(new TempProblem(mat.get(), dom.get(), nemit, maxscat, maxloop)); }
         else if (probStr == "flux") { argss >> nemit >> maxscat >> maxloop >> nsim; prob.reset(new FluxProblem(mat.get(), dom.get(), nemit, maxscat, maxloop)); }
         else if (probStr == "multi") { argss >> nemit >> maxscat >> maxloop >> nsim; prob.reset(new MultiProblem(mat.get(), dom.get(), nemit, maxscat, maxloop)); }
         else if (probStr == "cumtemp") { argss >> nemit >> size >> maxscat >> maxloop >> nsim; prob.reset(new CumTempProblem(mat.get(), dom.get(), nemit, size, maxscat, maxloop)); }
@@ -129,8 +180,9 @@ int main(int argc, const char* argv[]) {
         else MC_ASSERT_MSG(false, "Invalid problem");
         MC_ASSERT_MSG(!argss.fail(), "Invalid problem arguments");
 
-        std::cout << *prob << std::endl << std::endl;
-        if (nsim == 1) solveField(prob.get(), clk);
+        if (prob) std::cout << *prob << std::endl << std::endl;
+        if (!prob) {}
+        else if (nsim == 1) solveField(prob.get(), clk);
         else {
             std::vector<ArrayXXd> sol;
             for (long i = 0; i < nsim; ++i) sol.push_back(solveField(prob.get(), clk));

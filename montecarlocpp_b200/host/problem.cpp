@@ -141,6 +141,92 @@ void check(mcb_ctx* c, int rc, const char* what) {
 void FieldProblem::device(int ordinal) { t_device = ordinal; }
 mcb_stats FieldProblem::lastStats() { return t_stats; }
 
+namespace {
+// Runs f(ctx) with the device context of the calling thread's device, after making sure the tables of (mat, dom) are
+// resident.  One GPU stream per device: calls from several host threads are serialised.
+template <typename F>
+void withDevice(const Material* mat, const Domain* dom, F f) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    std::unique_ptr<DeviceContext>& dc = g_ctx[t_device];
+    if (!dc) {
+        dc.reset(new DeviceContext);
+        int rc = mcb_create(t_device, &dc->ctx);
+        if (rc != MCB_OK) { std::string msg = mcb_last_error(0); dc.reset(); g_ctx.erase(t_device); throw std::runtime_error("mcb_create: " + msg); }
+    }
+    if (dc->mat != mat) { mcb_material_desc md = mat->desc(); check(dc->ctx, mcb_upload_material(dc->ctx, &md), "mcb_upload_material"); dc->mat = mat; }
+    if (dc->dom != dom) {
+        FlatDomain fd = flattenDomain(dom); mcb_domain_desc dd = fd.desc();
+        check(dc->ctx, mcb_upload_domain(dc->ctx, &dd), "mcb_upload_domain"); dc->dom = dom; dc->cols = fd.cols;
+    }
+    f(dc->ctx);
+}
+}
+
+
+//---------------------------------------- TrajProblem
+TrajProblem::TrajProblem() : maxscat_(0), maxloop_(0) {}
+TrajProblem::TrajProblem(const Material* m, const Domain* d, const Prop& prop, const Vector3d& pos, const Vector3d& dir, long maxscat, long maxloop)
+    : Problem(m, d), maxscat_(maxscat), maxloop_(maxloop), prop_(prop), pos_(pos), dir_(dir) {}
+TrajProblem::TrajProblem(const Material* m, const Domain* d, const Prop& prop, const Vector3d& pos, long maxscat, long maxloop)
+    : Problem(m, d), maxscat_(maxscat), maxloop_(maxloop), prop_(prop), pos_(pos) {}
+TrajProblem::TrajProblem(const Material* m, const Domain* d, const Vector3d& pos, const Vector3d& dir, long maxscat, long maxloop)
+    : Problem(m, d), maxscat_(maxscat), maxloop_(maxloop), pos_(pos), dir_(dir) {}
+TrajProblem::TrajProblem(const Material* m, const Domain* d, const Vector3d& pos, long maxscat, long maxloop)
+    : Problem(m, d), maxscat_(maxscat), maxloop_(maxloop), pos_(pos) {}
+TrajProblem::TrajProblem(const Material* m, const Domain* d, long maxscat, long maxloop)
+    : Problem(m, d), maxscat_(maxscat), maxloop_(maxloop) {}
+
+std::string TrajProblem::info() const {
+    std::ostringstream ss;
+    ss << "TrajProblem " << static_cast<const Problem*>(this) << std::endl;
+    ss << Problem::info() << std::endl;
+    if (prop_) ss << "  prop:    " << prop_->w << " " << prop_->p << std::endl;
+    if (pos_) ss << "  pos:     [" << (*pos_)(0) << " " << (*pos_)(1) << " " << (*pos_)(2) << "]" << std::endl;
+    if (dir_) ss << "  dir:     [" << (*dir_)(0) << " " << (*dir_)(1) << " " << (*dir_)(2) << "]" << std::endl;
+    ss << "  maxscat: " << maxscat_ << std::endl;
+    ss << "  maxloop: " << maxloop_;
+    return ss.str();
+}
+Progress TrajProblem::initProgress() const { return Progress(); }
+
+ArrayXXd TrajProblem::solve(Rng& gen, Progress* prog) const {
+    unsigned long long hi = gen(), lo = gen();
+    const unsigned long long seed = (hi << 32) | lo;
+    mcb_traj_desc t = mcb_traj_desc();
+    t.maxscat = maxscat_;
+    t.maxloop = (maxloop_ != 0 ? maxloop_ : loopFactor_ * maxscat_);              // problem.cpp:256
+    t.sdom = -1;
+    if (prop_) { t.has_prop = 1; t.w = prop_->w; t.p = prop_->p; }
+    const Subdomain::Pointers& sp = dom()->sdomPtrs();
+    if (pos_) {
+        t.has_pos = 1;
+        for (int k = 0; k < 3; ++k) t.pos[k] = (*pos_)(k);
+        const Subdomain* s = dom()->locate(*pos_);                               // problem.cpp:241-242
+        MC_ASSERT_MSG(s, "Position not inside domain");
+        for (size_t i = 0; i < sp.size(); ++i) if (sp[i] == s) t.sdom = (int32_t)i;
+        if (dir_) { t.has_dir = 1; for (int k = 0; k < 3; ++k) t.dir[k] = (*dir_)(k); }
+    }
+    const long nmax = std::max(t.maxloop, 1l);
+    std::vector<double> pts((size_t)(3 * (2 * nmax + 1)));
+    std::vector<int32_t> ssd((size_t)nmax), sin_((size_t)nmax), sink((size_t)nmax), sout((size_t)nmax), soutk((size_t)nmax);
+    mcb_traj_out o = mcb_traj_out();
+    o.max_points = 2 * nmax + 1; o.points = pts.data(); o.max_steps = nmax;
+    o.step_sdom = ssd.data(); o.step_in = sin_.data(); o.step_in_kind = sink.data(); o.step_out = sout.data(); o.step_out_kind = soutk.data();
+    withDevice(mat(), dom(), [&](mcb_ctx* ctx) { check(ctx, mcb_traj(ctx, &t, seed, &o), "mcb_traj"); });
+
+    // the per-trip lines of problem.cpp:260-275
+    auto typeOf = [&](int s, int k) { return k >= 0 ? sp.at((size_t)s)->bdryPtrs().at((size_t)k)->type() : std::string("Null"); };
+    for (long i = 0; i < o.nsteps; ++i) {
+        std::cout << std::setw(2) << ssd[(size_t)i] << ": " << std::setw(2) << sin_[(size_t)i] << " " << std::setw(5) << typeOf(ssd[(size_t)i], sin_[(size_t)i]) << " -> ";
+        if (o.escaped == 1 && i == o.nsteps - 1) break;        // killed inside advect: the reference breaks before the right-hand side
+        std::cout << std::setw(2) << sout[(size_t)i] << " " << std::setw(5) << typeOf(ssd[(size_t)i], sout[(size_t)i]) << std::endl;
+    }
+    if (o.escaped) { if (prog) prog->incrEsc(); std::cout << "Escaped" << std::endl; }
+    ArrayXXd traj(3, o.npoints);
+    for (long j = 0; j < o.npoints; ++j) for (int k = 0; k < 3; ++k) traj(k, j) = pts[(size_t)(3 * j + k)];
+    return traj;
+}
+
 //---------------------------------------- FieldProblem
 FieldProblem::FieldProblem() : nemit_(0), maxscat_(0), maxloop_(0), power_(0.) {}
 
@@ -197,23 +283,10 @@ mcb_problem_desc FieldProblem::desc() const {
 ArrayXXd FieldProblem::solveSeeded(unsigned long long seed, long n_begin, long n_end, Progress* prog) const {
     ArrayXXd out = initSolution();
     mcb_stats st = mcb_stats();
-    {
-        // one GPU stream per device: calls from several host threads are serialised
-        std::lock_guard<std::mutex> lock(g_mu);
-        std::unique_ptr<DeviceContext>& dc = g_ctx[t_device];
-        if (!dc) {
-            dc.reset(new DeviceContext);
-            int rc = mcb_create(t_device, &dc->ctx);
-            if (rc != MCB_OK) { std::string msg = mcb_last_error(0); dc.reset(); g_ctx.erase(t_device); throw std::runtime_error("mcb_create: " + msg); }
-        }
-        if (dc->mat != mat()) { mcb_material_desc md = mat()->desc(); check(dc->ctx, mcb_upload_material(dc->ctx, &md), "mcb_upload_material"); dc->mat = mat(); }
-        if (dc->dom != dom()) {
-            FlatDomain fd = flattenDomain(dom()); mcb_domain_desc dd = fd.desc();
-            check(dc->ctx, mcb_upload_domain(dc->ctx, &dd), "mcb_upload_domain"); dc->dom = dom(); dc->cols = fd.cols;
-        }
+    withDevice(mat(), dom(), [&](mcb_ctx* ctx) {
         mcb_problem_desc pd = desc();
-        check(dc->ctx, mcb_solve(dc->ctx, &pd, seed, n_begin, n_end, out.data(), &st), "mcb_solve");
-    }
+        check(ctx, mcb_solve(ctx, &pd, seed, n_begin, n_end, out.data(), &st), "mcb_solve");
+    });
     t_stats = st;
     if (prog) prog->advance((long)st.emitted, (long)st.esc);
     return out;

@@ -5,6 +5,7 @@
 #define MCB_HOST_PROBLEM_H
 #include <ctime>
 #include <iosfwd>
+#include <optional>
 #include <string>
 #include <vector>
 #include "../../include/mcb.h"
@@ -52,6 +53,30 @@ public:
     virtual Progress initProgress() const = 0;
     virtual ArrayXXd solve(Rng& gen, Progress* prog) const = 0;
     friend std::ostream& operator<<(std::ostream& os, const Problem& prob);
+};
+
+// Single-particle trajectory (problem.h:86-119, problem.cpp:163-299): the geometry self-check behind the
+// `traj` and `check` CLI modes.  solve() prints one `sdom: bdry type -> bdry type` line per loop trip and returns
+// the 3 x N polyline TrkPhonon records; the trace itself runs on the device (mcb_traj).
+class TrajProblem : public Problem {
+public:
+    struct Prop { long w, p; Prop(long w_ = 0, long p_ = 0) : w(w_), p(p_) {} };     // Phonon::Prop (phonon.h:21-33)
+private:
+    static const long loopFactor_ = 100;
+    long maxscat_, maxloop_;
+    std::optional<Prop> prop_;
+    std::optional<Vector3d> pos_, dir_;
+    std::string info() const;
+public:
+    TrajProblem();
+    TrajProblem(const Material* mat, const Domain* dom, const Prop& prop, const Vector3d& pos, const Vector3d& dir,
+                long maxscat = 100, long maxloop = 0);
+    TrajProblem(const Material* mat, const Domain* dom, const Prop& prop, const Vector3d& pos, long maxscat = 100, long maxloop = 0);
+    TrajProblem(const Material* mat, const Domain* dom, const Vector3d& pos, const Vector3d& dir, long maxscat = 100, long maxloop = 0);
+    TrajProblem(const Material* mat, const Domain* dom, const Vector3d& pos, long maxscat = 100, long maxloop = 0);
+    TrajProblem(const Material* mat, const Domain* dom, long maxscat = 100, long maxloop = 0);
+    Progress initProgress() const;
+    ArrayXXd solve(Rng& gen, Progress* prog) const;
 };
 
 // Flattened Domain (what mcb_upload_domain consumes); storage owned here.

@@ -1133,6 +1133,71 @@ int orc_trace(const orc_problem* P, uint64_t seed, int64_t n_begin, int64_t n_en
     return MCB_OK;
 }
 
+int orc_domain_locate(const orc_domain* d, const double pos[3]) {
+    for (size_t s = 0; s < d->sdoms.size(); ++s) if (d->isInside((int)s, V3(pos[0], pos[1], pos[2]))) return (int)s;
+    return -1;
+}
+
+/* TrajProblem::solve problem.cpp:226-299 with TrkPhonon's recording (phonon.cpp:129-170) */
+int orc_traj(const orc_material* M, const orc_domain* D, const mcb_traj_desc* t, uint64_t seed, mcb_traj_out* o) {
+    if (!M || !D || !t || !o) { set_err("null argument"); return MCB_EINVAL; }
+    Words g(ORC_RNG_PHILOX, seed);
+    g.begin(0, 0);
+    auto push = [&](const V3& p) {
+        if (o->npoints < o->max_points) { o->points[3 * o->npoints] = p.x; o->points[3 * o->npoints + 1] = p.y; o->points[3 * o->npoints + 2] = p.z; }
+        o->npoints++;
+    };
+    o->npoints = 0; o->nsteps = 0; o->escaped = 0;
+    int sdom = -1, bdry = -1;
+    Phonon phn;
+    long w = t->w, p = t->p;
+    if (!t->has_prop) M->scatDist.draw(g, w, p);                                   /* :232 */
+    if (t->has_pos) {                                                              /* :233-243 */
+        V3 pos(t->pos[0], t->pos[1], t->pos[2]);
+        V3 dir = t->has_dir ? V3(t->dir[0], t->dir[1], t->dir[2]) : drawIso(g);
+        phn = Phonon(true, w, p, pos, dir);
+        sdom = t->sdom; bdry = -1;
+        if (sdom < 0 || sdom >= (int)D->sdoms.size()) { set_err("Position not inside domain"); return MCB_EINVAL; }
+    } else {                                                                       /* :244-253 */
+        const OEmitter& e = D->emitters.at((size_t)uniformInt(g, (long)D->emitters.size()));
+        phn = D->emit(e, w, p, g);
+        sdom = D->emitSdom(e);
+        bdry = e.kind == MCB_EMIT_BDRY ? e.index : -1;
+    }
+    push(phn.pos);                                                                 /* TrkPhonon ctor */
+    M->drawScatNext(phn, g);                                                       /* :254 */
+    auto local = [&](int s, int b) {                                               /* find(sdom->bdryPtrs(), bdry) */
+        if (b < 0) return -1;
+        const std::vector<int>& pl = D->sdoms[s].planes;
+        for (size_t k = 0; k < pl.size(); ++k) if (pl[k] == b) return (int)k;
+        return -1;
+    };
+    for (long i = 0; i < t->maxloop; i++) {                                        /* :258 */
+        g.begin(0, (uint32_t)(i + 1));
+        const long k = o->nsteps++;
+        if (k < o->max_steps) {
+            o->step_sdom[k] = sdom; o->step_in[k] = local(sdom, bdry); o->step_in_kind[k] = bdry >= 0 ? D->planes[bdry].kind : -1;
+            o->step_out[k] = -1; o->step_out_kind[k] = -1;
+        }
+        double vel = M->velAt(phn);
+        bdry = D->advect(sdom, phn, vel);                                          /* :265 */
+        push(phn.pos);                                                             /* Phonon::move -> TrkPhonon::pos */
+        if (!phn.alive) { o->escaped = 1; break; }                                 /* :267-271 */
+        if (k < o->max_steps) { o->step_out[k] = local(sdom, bdry); o->step_out_kind[k] = bdry >= 0 ? D->planes[bdry].kind : -1; }
+        if (bdry >= 0) {                                                           /* :277-290 */
+            const bool peri = D->planes[bdry].kind == MCB_BDRY_PERI;
+            bdry = D->scatter(bdry, phn, g);
+            if (peri) push(phn.pos);                                               /* PeriBoundary::scatter sets pos */
+            if (bdry < 0) { o->escaped = 2; break; }
+            sdom = D->planes[bdry].sdom;
+        } else {
+            M->scatter(phn, g);                                                    /* :291-294 */
+        }
+        if (!phn.alive || phn.nscat >= t->maxscat) break;                          /* :295 */
+    }
+    return MCB_OK;
+}
+
 int orc_cell_index(const orc_domain* d, int64_t n, const double* pos, const int32_t* sdom, int64_t* index) {
     for (int64_t i = 0; i < n; ++i) {
         long idx[3]; V3 p(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);

@@ -78,6 +78,11 @@ int    orc_finalize(const orc_problem*, double* field);
 int    orc_trace(const orc_problem*, uint64_t seed, int64_t n_begin, int64_t n_end,
                  int64_t nsteps, mcb_trace_out* out);
 
+/* TrajProblem::solve (problem.cpp:226-299), Philox word source (particle id 0): same records as mcb_traj */
+int    orc_traj(const orc_material*, const orc_domain*, const mcb_traj_desc*, uint64_t seed, mcb_traj_out* out);
+/* Domain::locate (domain.cpp:59-67): index of the first subdomain containing pos, -1 if none */
+int    orc_domain_locate(const orc_domain*, const double pos[3]);
+
 int    orc_cell_index(const orc_domain*, int64_t n, const double* pos, const int32_t* sdom,
                       int64_t* index);
 int    orc_accumulate(const orc_domain*, int32_t rows, int64_t n, const int32_t* sdom,

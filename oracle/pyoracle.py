@@ -60,6 +60,8 @@ def lib():
         L.orc_finalize.argtypes = [vp, dp]
         L.orc_trace.argtypes = [vp, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.POINTER(abi.TraceOut)]
         L.orc_cell_index.argtypes = [vp, C.c_int64, dp, ip, lp]
+        L.orc_traj.argtypes = [vp, vp, C.POINTER(abi.TrajDesc), C.c_uint64, C.POINTER(abi.TrajOut)]
+        L.orc_domain_locate.argtypes = [vp, dp]
         L.orc_accumulate.argtypes = [vp, C.c_int32, C.c_int64, ip, dp, dp, dp, dp]
         L.orc_philox_words.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
         L.orc_mt_draws.argtypes = [C.c_uint32, C.c_int, C.c_int64, C.c_int64, dp]
@@ -202,6 +204,29 @@ class Problem:
     def __del__(self):
         if getattr(self, "h", None):
             lib().orc_problem_free(self.h); self.h = None
+
+
+def traj(mat, dom, seed, maxscat, maxloop=0, prop=None, pos=None, dir=None):
+    """TrajProblem(mat, dom, [prop], [pos], [dir], maxscat, maxloop).solve() -> dict of records."""
+    t = make_traj_desc(dom, maxscat, maxloop, prop, pos, dir, lambda q: lib().orc_domain_locate(dom.h, _dp(q)))
+    bufs, out = abi.traj_buffers(t.maxloop)
+    if lib().orc_traj(mat.h, dom.h, C.byref(t), seed, C.byref(out)) != 0:
+        raise RuntimeError(_err())
+    return abi.traj_result(bufs, out)
+
+
+def make_traj_desc(dom, maxscat, maxloop, prop, pos, dir, locate):
+    t = abi.TrajDesc()
+    t.maxscat, t.maxloop = maxscat, (maxloop if maxloop else 100 * maxscat)
+    t.sdom = -1
+    if prop is not None:
+        t.has_prop, t.w, t.p = 1, prop[0], prop[1]
+    if pos is not None:
+        q = np.ascontiguousarray(pos, np.float64)
+        t.has_pos = 1; t.pos[:] = list(q); t.sdom = locate(q)
+        if dir is not None:
+            t.has_dir = 1; t.dir[:] = list(dir)
+    return t
 
 
 def philox_words(seed, particle, event, block):
