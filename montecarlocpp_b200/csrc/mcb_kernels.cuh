@@ -72,7 +72,7 @@ __device__ __forceinline__ uint32_t draw_prop(Rng& g, const Tables& T, const dou
 // Material::drawScatNext (material.cpp:215-224); lambda = vel*tau
 __device__ __forceinline__ double draw_scat_next(Rng& g, double lambda) {
     double d = 0.0;
-    while (d < 2.2250738585072014e-308) d = lambda * -log(1.0 - g.u01());
+    while (d < 2.2250738585072014e-308) d = lambda * neg_log1m_u32(g.next());     // -log(1 - uniform_01)
     return d;
 }
 
@@ -229,19 +229,19 @@ __device__ __forceinline__ uint32_t collide(const StepParams& P, const Tables& T
             const DPlaneHot h = T.hot[hit];
             const double c2 = 2.0 * dot3(h.nx, h.ny, h.nz, ph.dx, ph.dy, ph.dz);
             ph.dx -= c2 * h.nx; ph.dy -= c2 * h.ny; ph.dz -= c2 * h.nz;
-            normalize3(ph.dx, ph.dy, ph.dz);
+            renorm_unit(ph.dx, ph.dy, ph.dz);
         } else if (kind == MCB_BDRY_DIFF) {                                    // boundary.cpp:308-312
             Rng g; g.begin(P.seed, ph.pid, ph.step);
             double ax, ay, az; draw_aniso(g, false, ax, ay, az);
             matvec(cb.m, ax, ay, az, ph.dx, ph.dy, ph.dz);
-            normalize3(ph.dx, ph.dy, ph.dz);
+            renorm_unit(ph.dx, ph.dy, ph.dz);
             ph.nscat++;
         } else if (kind == MCB_BDRY_PERI) {                                    // boundary.cpp:516-522
             double nx, ny, nz; matvec(cb.m, sg.ex, sg.ey, sg.ez, nx, ny, nz);
             ph.px = nx + cb.t[0]; ph.py = ny + cb.t[1]; ph.pz = nz + cb.t[2];
             matvec(cb.m, ph.dx, ph.dy, ph.dz, nx, ny, nz);
             ph.dx = nx; ph.dy = ny; ph.dz = nz;
-            normalize3(ph.dx, ph.dy, ph.dz);
+            renorm_unit(ph.dx, ph.dy, ph.dz);
             sg.next_plane = T.pairs[cb.pair_begin];
             ph.sdom = (uint32_t)T.cold[sg.next_plane].sdom;
         } else if (kind == MCB_BDRY_INTER) {                                   // boundary.cpp:349-359
@@ -275,8 +275,8 @@ __device__ __forceinline__ uint32_t collide(const StepParams& P, const Tables& T
             const uint32_t wp = (double)a[3] * (1.0 / 4294967296.0) < T.pprob[k] ? k : w * (uint32_t)T.np + (uint32_t)T.palias[k];
             const double c = (double)b[0] * (1.0 / 2147483648.0) - 1.0;       // drawIso random.cpp:16-27
             const double sth = sqrt(1.0 - c * c);
-            double sp, cp; sincospi((double)b[1] * (1.0 / 2147483648.0) - 1.0, &sp, &cp);
-            const double dist = T.lambda[wp] * -log(1.0 - (double)b[2] * (1.0 / 4294967296.0));
+            double sp, cp; sincospi_unit((double)b[1] * (1.0 / 2147483648.0) - 1.0, &sp, &cp);
+            const double dist = T.lambda[wp] * neg_log1m_u32(b[2]);
             fast = fast && !(dist < 2.2250738585072014e-308);
             if (fast) { ph.wp = wp; ph.dx = sth * cp; ph.dy = sth * sp; ph.dz = c; ph.sn = dist; }
         }
@@ -286,7 +286,7 @@ __device__ __forceinline__ uint32_t collide(const StepParams& P, const Tables& T
             draw_iso(g, ph.dx, ph.dy, ph.dz);
             ph.sn = draw_scat_next(g, T.lambda[ph.wp]);
         }
-        normalize3(ph.dx, ph.dy, ph.dz);
+        renorm_unit(ph.dx, ph.dy, ph.dz);
         ph.nscat++;
     }
     if ((long long)ph.nscat >= P.maxscat || (long long)ph.step >= P.maxloop) ph.active = 0;   // :434, :401
