@@ -216,7 +216,7 @@ void fill_params(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, StepPa
     P->mat_blob = c->mat_blob.p; P->mv = c->mv; P->geo_blob = c->geo_blob.p; P->gv = c->gv;
     P->emitters = c->emitters.p; P->emit_cdf = c->emit_cdf.p; P->nemitter = c->nemitter;
     P->f_wprob = c->f_wprob.p; P->f_pprob = c->f_pprob.p; P->f_walias = c->f_walias.p; P->f_palias = c->f_palias.p;
-    P->kind = prob->kind; P->rows = prob->rows; P->cum_step = prob->step > 0 ? prob->step : 1;
+    P->kind = prob->kind; P->rows = prob->rows; P->cols = (int32_t)c->cols; P->cum_step = prob->step > 0 ? prob->step : 1;
     P->maxscat = prob->maxscat; P->maxloop = prob->maxloop; P->seed = seed;
     P->ctr = c->ctr.p; P->field_len = (long long)prob->rows * c->cols;
     P->so_mat = 16; P->so_geo = 16 + c->mv.bytes; P->so_hist = 16 + c->mv.bytes + c->gv.bytes;

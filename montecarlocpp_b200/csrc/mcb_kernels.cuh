@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(MCB_BLOCK_MAX, 1) k_step(const StepParams P) {
                 else if (NCOMP == 4) { amt[0] = sg_ * (sg.d * T.inv_vel[ph.wp]); amt[1 % NCOMP] = sg_ * (sg.ex - sg.bx); amt[2 % NCOMP] = sg_ * (sg.ey - sg.by); amt[3 % NCOMP] = sg_ * (sg.ez - sg.bz); }
                 else { amt[0] = sg_ * (sg.ex - sg.bx); amt[1 % NCOMP] = sg_ * (sg.ey - sg.by); amt[2 % NCOMP] = sg_ * (sg.ez - sg.bz); }
                 const int rbase = cum ? NCOMP * (int)(((long long)sg.nscat_before + P.cum_step - 1) / P.cum_step) : 0;
-                tally_segments<NCOMP, TM, ND, true>(T.sdom[ph.sdom], T.hist, P.rows, rbase, sg.ok, sg.bx, sg.by, sg.bz, sg.ex, sg.ey, sg.ez, amt, lane);
+                tally_segments<NCOMP, TM, ND, true>(T.sdom[ph.sdom], T.hist, P.rows, P.cols, rbase, sg.ok, sg.bx, sg.by, sg.bz, sg.ex, sg.ey, sg.ez, amt, lane);
             }
             if (sg.ok) my_esc += collide(P, T, ph, sg);
             if (__all_sync(0xFFFFFFFFu, !ph.active && (!EMIT || exhausted || !valid || !P.refill))) break;
@@ -446,14 +446,17 @@ __global__ void __launch_bounds__(MCB_BLOCK_MAX, 1) k_step(const StepParams P) {
         if (s_red[3]) atomicAdd(&P.ctr->live, s_red[3]);
         if (s_red[4]) atomicAdd(&P.ctr->stores, s_red[4]);
     }
-    // --- flush the shared-memory histogram(s): sum the warp copies, one fp64 RED per non-zero entry
-    if (TM != MCB_TM_GLOBAL && P.do_tally)
-        for (long long i = threadIdx.x; i < P.field_len; i += blockDim.x) {
+    // --- flush the shared-memory histogram(s): sum the copies, transpose row-major -> the field's column-major layout,
+    //     one fp64 RED per non-zero entry
+    if (TM != MCB_TM_GLOBAL && P.do_tally) {
+        const unsigned ncopy = TM == MCB_TM_WARP ? nwarps * (unsigned)P.hist_copies : 1u;
+        for (long long i = threadIdx.x; i < P.field_len; i += blockDim.x) {        // i = r*cols + c in the histograms
             double v = 0.0;
-            if (TM == MCB_TM_WARP) for (unsigned w = 0; w < nwarps * (unsigned)P.hist_copies; ++w) v += s_hist[(long long)w * P.field_len + i];
-            else v = s_hist[i];
-            if (v != 0.0) atomicAdd(P.field + i, v);
+            for (unsigned w = 0; w < ncopy; ++w) v += s_hist[(long long)w * P.field_len + i];
+            const long long r = i / P.cols, c = i - r * P.cols;
+            if (v != 0.0) atomicAdd(P.field + c * P.rows + r, v);
         }
+    }
 }
 
 // ------------------------------------------------------------------------------- k_emit
@@ -621,7 +624,7 @@ __global__ void k_accumulate(const unsigned char* geo_blob, GeometryView gv, int
     const double* a = amount + (long long)rows * i;
     // generic row count: deposit one component at a time (same weights, same order per component)
     for (int r = 0; r < rows; ++r)
-        tally_segments<1, MCB_TM_GLOBAL, true, false>(sd, field, rows, r, true, bpos[3 * i], bpos[3 * i + 1], bpos[3 * i + 2],
+        tally_segments<1, MCB_TM_GLOBAL, true, false>(sd, field, rows, 0, r, true, bpos[3 * i], bpos[3 * i + 1], bpos[3 * i + 2],
                                                epos[3 * i], epos[3 * i + 1], epos[3 * i + 2], a + r, threadIdx.x & 31u);
 }
 

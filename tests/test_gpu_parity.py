@@ -289,8 +289,8 @@ def test_cli_check_mode_traces_every_boundary(matfiles, tmp_path):
     import os, shutil, subprocess
     from montecarlocpp_b200 import capi
     exe = os.path.join(os.path.dirname(capi.LIB_PATH), "montecarlo")
-    for f in matfiles["grey"]:
-        shutil.copy(f, tmp_path)
+    from montecarlocpp_b200 import materials
+    materials.write_grey(str(tmp_path), inv_tau=6.0)      # mean free path 1 km: every ray reaches a wall (seeds are random)
     r = subprocess.run([exe, str(tmp_path), "grey", "300", "tube", "1e-6", "5e-8", "2e-8", "8", "4", "check", "1", "0", "0", "0", "1", "0", "0", "0", "1"],
                        capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stderr
@@ -298,7 +298,8 @@ def test_cli_check_mode_traces_every_boundary(matfiles, tmp_path):
     assert out.count("TrajProblem ") == 18 and out.count("Trajectory ") >= 18 and "Combined Trajectory" in out
     assert "Escaped" not in out
     # sdom 0's top face (5) is the Inter hand-off to sdom 1; the partner face is 2 there, and so on round the L
-    for token in (" 0: -1  Null ->  5 Inter", " 1: -1  Null ->  1 Inter", " 2:  4 Inter -> ", " Diff", " Spec"):
+    for token in (" 0: -1  Null ->  5 Inter", " 0: -1  Null ->  3 PeriP", " 0: -1  Null ->  2  Spec", " 1: -1  Null ->  1 Inter",
+                  " 1: -1  Null ->  2 Inter", " 2: -1  Null ->  4 Inter", " 2: -1  Null ->  1  Spec", " 1:  2 Inter -> ", " Diff"):
         assert token in out, token
     r2 = subprocess.run([exe, str(tmp_path), "grey", "300", "film", "1e-6", "1e-7", "10", "traj", "5e-7", "5e-8", "5e-7", "0", "1", "0", "3", "0"],
                         capture_output=True, text=True, timeout=120)
