@@ -269,6 +269,15 @@ def run_ours(args):
         dec_ms = tot["step_ms"] - tot["steady_ms"]
         dec_steps = tot["steps"] - tot["steady_steps"]
         slots = args.slots if args.slots else 148 * 768 * 32
+        # DRAM traffic of that kernel from the committed ncu --set full capture (profiles/ncu_traffic.json), per launch
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["kernels"]
+            key = {"C2-slab100nm-si": "k_step_steady_S1_C2", "C1-film100nm-si": "k_step_film_S1_C1"}.get(args.workload)
+            if key and args.mode == "streaming" and not args.slots:
+                traffic = tj[key]["dram_bytes_per_launch"]
+        except Exception:
+            pass
         line = {
             "metric": "phonon_steps_per_s", "value": all_steps / elapsed, "unit": "phonon-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps,
@@ -282,7 +291,9 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(d2h), "calls": "mcb_upload_material + mcb_upload_domain + mcb_solve (host buffers)"},
             "gpu_launches": int(all_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": f"k_step, steady-phase launches (S={S})",
+                         "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                         "algorithmic_bytes_per_launch": tot["steady_stores"] * B_ALG / max(1, tot["steady_launches"]),
+                         "kernel": f"k_step, steady-phase launches (S={S})",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
                          "bytes_per_phonon_step": tot["steady_stores"] * B_ALG / max(1, tot["steady_steps"]),
                          "kernel_ms_per_launch": tot["steady_ms"] / max(1, tot["steady_launches"]),
