@@ -132,9 +132,10 @@ typedef struct mcb_sdom_desc {
     double  emit_rot[9];       /* EmitSubdomain::rot_ = rotMatrix(gradT.normalized()) */
     int32_t plane_begin;       /* bdryPtrs() -> range in mcb_domain_desc.planes       */
     int32_t plane_count;
-    int32_t nbase;             /* Prism/Pyramid: number of base columns (else 0)      */
+    int32_t nbase;             /* Prism/Pyramid: N = columns of mat_ (else 0)         */
     int32_t pad_;
-    double  base[3 * MCB_MAX_BASE]; /* Prism/Pyramid mat columns (subdomain.h)        */
+    double  base[3 * MCB_MAX_BASE]; /* Prism/Pyramid mat_ columns: col 0 = axis/apex  */
+                               /* vector, cols 1..N-1 = base fan (subdomain.h:378,501)*/
 } mcb_sdom_desc;
 
 /* One entry of Domain::emitPtrs() (domain.cpp:88-102), in that order. */
@@ -149,6 +150,9 @@ typedef struct mcb_domain_desc {
     int32_t nplane;  const mcb_plane_desc*   planes;
     int32_t npair;   const int32_t*          pairs;     /* plane ids                  */
     int32_t nemitter;const mcb_emitter_desc* emitters;  /* Domain::emitPtrs() order   */
+    /* Field(1, dom, CellVolF()).data().row(0) (problem.cpp:302-306, 441-442): Subdomain::cellVol of every field column,
+     * in Field::init order.  May be NULL when every gridded subdomain is a parallelepiped (vol / shape.prod()). */
+    int64_t ncols;   const double*           cell_vol;
 } mcb_domain_desc;
 
 /*

@@ -58,7 +58,8 @@ class DomainDesc(C.Structure):
     _fields_ = [("nsdom", C.c_int32), ("sdoms", C.POINTER(SdomDesc)),
                 ("nplane", C.c_int32), ("planes", C.POINTER(PlaneDesc)),
                 ("npair", C.c_int32), ("pairs", c_int32_p),
-                ("nemitter", C.c_int32), ("emitters", C.POINTER(EmitterDesc))]
+                ("nemitter", C.c_int32), ("emitters", C.POINTER(EmitterDesc)),
+                ("ncols", C.c_int64), ("cell_vol", c_double_p)]
 
 
 class ProblemDesc(C.Structure):

@@ -529,8 +529,13 @@ int mcb_upload_domain(mcb_ctx* c, const mcb_domain_desc* d) {
         if (sp == 0) D.col_offset = -1;                                                                    // field.cpp:34
         else {
             D.col_offset = (int32_t)cols; cols += sp;
-            if (S.cell != MCB_CELL_PARALLELEPIPED && sp != 1) { c->err = "gridded non-box cells are not built yet (SURVEY N3)"; return MCB_EINVAL; }
-            for (long long k = 0; k < sp; ++k) cell_vol.push_back(S.vol / (double)sp);                     // subdomain.cpp:269-273
+            if (d->cell_vol) {                                       // Subdomain::cellVol evaluated by the caller (CellVolF)
+                if (cols > d->ncols) { c->err = "cell_vol has fewer entries than the field has columns"; return MCB_EINVAL; }
+                for (long long k = 0; k < sp; ++k) cell_vol.push_back(d->cell_vol[cols - sp + k]);
+            } else {
+                if (S.cell != MCB_CELL_PARALLELEPIPED && sp != 1) { c->err = "gridded non-box cells need mcb_domain_desc.cell_vol (Subdomain::cellVol per column)"; return MCB_EINVAL; }
+                for (long long k = 0; k < sp; ++k) cell_vol.push_back(S.vol / (double)sp);                 // subdomain.cpp:269-273, 396-399, 428-431
+            }
         }
         if (cols > 0x7FFFFFFFll) { c->err = "too many cells"; return MCB_ELIMIT; }
     }
@@ -541,19 +546,46 @@ int mcb_upload_domain(mcb_ctx* c, const mcb_domain_desc* d) {
         if (e.kind == MCB_EMIT_SDOM) {
             if (e.index < 0 || e.index >= d->nsdom) { c->err = "emitter sdom out of range"; return MCB_EINVAL; }
             const mcb_sdom_desc& S = d->sdoms[e.index];
-            if (S.cell != MCB_CELL_PARALLELEPIPED) { c->err = "volumetric emission from non-box cells is not built yet (SURVEY N3)"; return MCB_EINVAL; }
-            E.sdom = e.index;
+            if (S.cell < MCB_CELL_PARALLELEPIPED || S.cell > MCB_CELL_PYRAMID) { c->err = "unknown cell kind"; return MCB_EINVAL; }
+            E.sdom = e.index; E.shape = S.cell;
             for (int k = 0; k < 3; ++k) { E.o[k] = S.origin[k]; E.g[k] = S.grad_t[k]; }
             for (int k = 0; k < 9; ++k) { E.a[k] = S.mat[k]; E.rot[k] = S.emit_rot[k]; }
+            if (S.cell == MCB_CELL_PRISM || S.cell == MCB_CELL_PYRAMID) {
+                // volDist_ over PrismImpl::volume / PyramidImpl::volume (subdomain.cpp:385-394, 417-426): vol(i) uses columns
+                // i and i+1 (sic: i = 0 pairs the axis with itself and is zero), while drawPos uses columns ind+1, ind+2
+                const int N = S.nbase;
+                if (N < 4 || N > MCB_MAX_BASE) { c->err = "prism/pyramid needs 4..9 mat columns"; return MCB_EINVAL; }
+                for (int k = 0; k < 3 * N; ++k) E.a[k] = S.base[k];
+                double vol[MCB_MAX_BASE];
+                const double div = S.cell == MCB_CELL_PRISM ? 2.0 : 6.0;
+                for (int i = 0; i < N - 2; ++i) {
+                    const double* a = &S.base[3 * i]; const double* b = &S.base[3 * (i + 1)]; const double* z = &S.base[0];
+                    const double cx = a[1] * b[2] - a[2] * b[1], cy = a[2] * b[0] - a[0] * b[2], cz = a[0] * b[1] - a[1] * b[0];
+                    vol[i] = (cx * z[0] + cy * z[1] + cz * z[2]) / div;
+                }
+                E.nsub = N - 2;
+                build_alias(vol, (size_t)E.nsub, E.sprob, E.salias);
+            }
         } else if (e.kind == MCB_EMIT_BDRY) {
             if (e.index < 0 || e.index >= d->nplane) { c->err = "emitter plane out of range"; return MCB_EINVAL; }
             const mcb_plane_desc& p = d->planes[e.index];
-            if (p.shape != MCB_SHAPE_PARALLELOGRAM && p.shape != MCB_SHAPE_TRIANGLE) { c->err = "polygon emitters are not built yet (SURVEY N3)"; return MCB_EINVAL; }
+            if (p.shape < MCB_SHAPE_PARALLELOGRAM || p.shape > MCB_SHAPE_POLYGON) { c->err = "emitting boundary without a shape"; return MCB_EINVAL; }
+            if (p.nvert < 2 || p.nvert > MCB_MAX_VERTS || (p.shape != MCB_SHAPE_POLYGON && p.nvert != 2)) { c->err = "bad shape vertex count"; return MCB_EINVAL; }
             E.sdom = p.sdom; E.shape = p.shape;
             for (int k = 0; k < 3; ++k) E.o[k] = p.origin[k];
-            for (int k = 0; k < 6; ++k) E.a[k] = p.verts[k];
+            for (int k = 0; k < 3 * p.nvert; ++k) E.a[k] = p.verts[k];
             for (int k = 0; k < 9; ++k) E.rot[k] = p.rot[k];
             E.g[0] = p.T;
+            if (p.shape == MCB_SHAPE_POLYGON) {                      // areaDist_ over the fan triangles (boundary.cpp:195-214)
+                double area[MCB_MAX_VERTS];
+                for (int n = 0; n < p.nvert - 1; ++n) {
+                    const double* a = &p.verts[3 * n]; const double* b = &p.verts[3 * (n + 1)];
+                    const double cx = a[1] * b[2] - a[2] * b[1], cy = a[2] * b[0] - a[0] * b[2], cz = a[0] * b[1] - a[1] * b[0];
+                    area[n] = std::sqrt(cx * cx + cy * cy + cz * cz) / 2.0;
+                }
+                E.nsub = p.nvert - 1;
+                build_alias(area, (size_t)E.nsub, E.sprob, E.salias);
+            }
         } else { c->err = "unknown emitter kind"; return MCB_EINVAL; }
     }
     GeometryView v{}; v.nsdom = d->nsdom; v.nplane = d->nplane; v.npair = d->npair;

@@ -76,24 +76,51 @@ __device__ __forceinline__ double draw_scat_next(Rng& g, double lambda) {
     return d;
 }
 
+// TriangularPrismImpl::drawPos (subdomain.cpp:309-320) / TetrahedronImpl::drawPos (:351-377): fold the unit cube
+// onto the prism / tetrahedron spanned by the three columns at a[0], a[3], a[6]
+__device__ __forceinline__ void fold_simplex(bool tet, double& c0, double& c1, double& c2) {
+    if (c0 + c1 > 1.0) { c0 = 1.0 - c0; c1 = 1.0 - c1; }
+    if (!tet) return;
+    if (c1 + c2 > 1.0) { const double t = c2; c2 = 1.0 - c0 - c1; c1 = 1.0 - t; }
+    else if (c0 + c1 + c2 > 1.0) { const double t = c2; c2 = c0 + c1 + c2 - 1.0; c0 = 1.0 - c1 - t; }
+}
+// boost discrete_distribution draw on a small alias table (volDist_ / areaDist_)
+__device__ __forceinline__ int draw_small(Rng& g, int n, const double* prob, const int32_t* alias) {
+    const uint32_t r = g.uint_below((uint32_t)n);
+    const double t = g.u01();
+    return t < prob[r] ? (int)r : alias[r];
+}
+
 // Emitter::emit (boundary.cpp:378-385): position, direction and sign from one emitter
 __device__ __forceinline__ void emit_from(const DEmitter& E, Rng& g, Particle& ph) {
     double px, py, pz, dx, dy, dz; uint32_t sign;
     if (E.kind == MCB_EMIT_SDOM) {
-        // ParallelepipedImpl::drawPos subdomain.cpp:275-281 ; drawDir :255-258 ; emitSign :260-263
+        // *Impl::drawPos subdomain.cpp:275-281, 309-320, 351-377, 401-409, 433-441 ; drawDir :255-258 ; emitSign :260-263
+        const double* m = E.a;
+        double loc[9];
+        if (E.shape == MCB_CELL_PRISM || E.shape == MCB_CELL_PYRAMID) {
+            const int ind = draw_small(g, E.nsub, E.sprob, E.salias);      // sub-wedge, then local = (col ind+1, col ind+2, col 0)
+            for (int k = 0; k < 3; ++k) { loc[k] = E.a[3 * (ind + 1) + k]; loc[3 + k] = E.a[3 * (ind + 2) + k]; loc[6 + k] = E.a[k]; }
+            m = loc;
+        }
         double c0 = g.u01(), c1 = g.u01(), c2 = g.u01();
-        double mx, my, mz; matvec(E.a, c0, c1, c2, mx, my, mz);
+        if (E.shape == MCB_CELL_TRIPRISM || E.shape == MCB_CELL_PRISM) fold_simplex(false, c0, c1, c2);
+        else if (E.shape == MCB_CELL_TETRAHEDRON || E.shape == MCB_CELL_PYRAMID) fold_simplex(true, c0, c1, c2);
+        double mx, my, mz; matvec(m, c0, c1, c2, mx, my, mz);
         px = E.o[0] + mx; py = E.o[1] + my; pz = E.o[2] + mz;
         double ax, ay, az; draw_aniso(g, true, ax, ay, az);
         matvec(E.rot, ax, ay, az, dx, dy, dz);
         sign = dot3(dx, dy, dz, E.g[0], E.g[1], E.g[2]) < 0.0 ? 1u : 0u;
     } else {
-        // EmitBoundary::drawPos / drawDir / emitSign boundary.cpp:418-431 ; shapes :147-152,:182-187
+        // EmitBoundary::drawPos / drawDir / emitSign boundary.cpp:418-431 ; shapes :147-152, :182-187, :243-251
+        int n = 0;
+        if (E.shape == MCB_SHAPE_POLYGON) n = draw_small(g, E.nsub, E.sprob, E.salias);     // fan triangle (verts n, n+1)
         double r1 = g.u01(), r2 = g.u01();
-        if (E.shape == MCB_SHAPE_TRIANGLE && !(r1 + r2 < 1.0)) { r1 = 1.0 - r1; r2 = 1.0 - r2; }
-        px = E.o[0] + (r1 * E.a[0] + r2 * E.a[3]);
-        py = E.o[1] + (r1 * E.a[1] + r2 * E.a[4]);
-        pz = E.o[2] + (r1 * E.a[2] + r2 * E.a[5]);
+        if (E.shape != MCB_SHAPE_PARALLELOGRAM && !(r1 + r2 < 1.0)) { r1 = 1.0 - r1; r2 = 1.0 - r2; }
+        const double* vi = E.a + 3 * n; const double* vj = E.a + 3 * (n + 1);
+        px = E.o[0] + (r1 * vi[0] + r2 * vj[0]);
+        py = E.o[1] + (r1 * vi[1] + r2 * vj[1]);
+        pz = E.o[2] + (r1 * vi[2] + r2 * vj[2]);
         double ax, ay, az; draw_aniso(g, false, ax, ay, az);
         matvec(E.rot, ax, ay, az, dx, dy, dz);
         sign = E.g[0] >= 0.0 ? 1u : 0u;

@@ -384,6 +384,8 @@ struct OSubdomain {                             /* subdomain.h:35-126 */
     long div[3] = {0, 0, 0}, shape[3] = {1, 1, 1}, max[3] = {0, 0, 0};
     int accum = -1; double eps = 0.;
     V3 gradT; M3 emitRot;
+    std::vector<V3> base;                       /* Prism / Pyramid: mat_ columns (subdomain.h:378,501) */
+    Discrete volDist;                           /* Prism / Pyramid: volDist_ */
     std::vector<int> planes;                    /* bdryPtrs_ (plane ids, declaration order) */
     std::vector<int> emitPlanes;                /* emitPtrs_ of this sdom */
     double emitWeight() const { return 2. * vol * norm(gradT); }                        /* subdomain.cpp:250-253 */
@@ -400,7 +402,7 @@ struct orc_domain {
     long cols = 0;
     /* flattened copies handed out through orc_domain_desc */
     std::vector<mcb_sdom_desc> fs; std::vector<mcb_plane_desc> fp; std::vector<int32_t> fpairs;
-    std::vector<mcb_emitter_desc> fe;
+    std::vector<mcb_emitter_desc> fe; std::vector<double> fcellvol;
 
     /* subdomain.cpp:108-116 */
     bool isInside(int s, const V3& pos) const {
@@ -472,16 +474,63 @@ struct orc_domain {
         return -1;
     }
     /* ParallelepipedImpl::cellVol subdomain.cpp:269-273 (other cells: N3, not built yet) */
-    double cellVol(int s) const { const OSubdomain& sd = sdoms[s]; return sd.vol / (double)sd.shapeProd(); }
+    /* Subdomain::cellVol(index): ParallelepipedImpl :269-273, TriangularPrismImpl :283-307, TetrahedronImpl :322-349,
+     * PrismImpl :396-399, PyramidImpl :428-431.  The partial-cell formulas (and their normalisation, which counts a full
+     * cell as vol/prod(shape) although the simplex fills only 1/2 resp. 1/6 of the spanning box) are kept literally. */
+    double cellVol(int s, const long idx[3]) const {
+        const OSubdomain& sd = sdoms[s];
+        const double prod = (double)sd.shapeProd();
+        if (sd.cell == MCB_CELL_PARALLELEPIPED) return sd.vol / prod;
+        if (sd.cell == MCB_CELL_PRISM || sd.cell == MCB_CELL_PYRAMID) return sd.vol;
+        const int nd = sd.cell == MCB_CELL_TRIPRISM ? 2 : 3;
+        double shp[3] = {(double)sd.shape[0], (double)sd.shape[1], (double)sd.shape[2]};
+        double q = 0.; for (int d = 0; d < nd; ++d) q += (double)idx[d] / shp[d];
+        const double f0 = 1. - q;
+        if (f0 <= 0.) return 0.;
+        double one = 0.; for (int d = 0; d < nd; ++d) one += 1. / shp[d];
+        const double f1 = f0 - one;
+        if (f1 >= 0.) return sd.vol / prod;
+        if (nd == 2) {
+            double frac = std::pow(f0, 2);
+            for (int i = 0; i < 2; i++) {                                   /* corners (1,0), (0,1): one step along one axis */
+                double f = f0 - 1. / shp[i];
+                if (f > 0.) frac += -1 * std::pow(f, 2);
+            }
+            return sd.vol * frac / (2. * shp[2]);
+        }
+        static const int pts[6][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, 1, 1}, {1, 0, 1}, {1, 1, 0}};
+        double frac = std::pow(f0, 3);
+        for (int i = 0; i < 6; i++) {
+            int sum = pts[i][0] + pts[i][1] + pts[i][2];
+            int sign = (sum % 2) ? -1 : 1;
+            double f = f0 - ((double)pts[i][0] / shp[0] + (double)pts[i][1] / shp[1] + (double)pts[i][2] / shp[2]);
+            if (f > 0.) frac += sign * std::pow(f, 3);
+        }
+        return sd.vol * frac / 6.;
+    }
 
     /* Emitter::emit boundary.cpp:378-385 */
     Phonon emit(const OEmitter& e, long w, long p, Words& g) const {
         V3 pos, dir; bool sign;
         if (e.kind == MCB_EMIT_SDOM) {
             const OSubdomain& sd = sdoms[e.index];
-            /* ParallelepipedImpl::drawPos subdomain.cpp:275-281 */
+            M3 m = sd.mat;
+            if (sd.cell == MCB_CELL_PRISM || sd.cell == MCB_CELL_PYRAMID) {     /* PrismImpl/PyramidImpl::drawPos :401-409, :433-441 */
+                long ind = sd.volDist(g);
+                const V3 &a = sd.base.at((size_t)ind + 1), &b = sd.base.at((size_t)ind + 2), &z = sd.base[0];
+                for (int k = 0; k < 3; ++k) { m(k, 0) = a[k]; m(k, 1) = b[k]; m(k, 2) = z[k]; }
+            }
+            /* ParallelepipedImpl::drawPos :275-281 ; TriangularPrismImpl :309-320 ; TetrahedronImpl :351-377 */
             double c0 = uniform01(g), c1 = uniform01(g), c2 = uniform01(g);
-            pos = sd.o + sd.mat * V3(c0, c1, c2);
+            const bool tet = sd.cell == MCB_CELL_TETRAHEDRON || sd.cell == MCB_CELL_PYRAMID;
+            if (sd.cell != MCB_CELL_PARALLELEPIPED) {
+                if (c0 + c1 > 1.) { c0 = 1. - c0; c1 = 1. - c1; }
+                if (tet) {
+                    if (c1 + c2 > 1.) { double tmp = c2; c2 = 1. - c0 - c1; c1 = 1. - tmp; }
+                    else if (c0 + c1 + c2 > 1.) { double tmp = c2; c2 = c0 + c1 + c2 - 1.; c0 = 1. - c1 - tmp; }
+                }
+            }
+            pos = sd.o + m * V3(c0, c1, c2);
             dir = sd.emitRot * drawAniso(g, true);                 /* subdomain.cpp:255-258 */
             sign = dot(dir, sd.gradT) < 0.;                        /* subdomain.cpp:260-263 */
         } else {
@@ -580,6 +629,84 @@ int addParallelepiped(orc_domain& D, const V3& o, const M3& mat, const long div[
     return s;
 }
 
+OBoundary makeBoundaryShape(int kind, const V3& o, int shape, const std::vector<V3>& verts, double T) {
+    OBoundary B;
+    B.kind = kind; B.shape = shape; B.verts = verts;
+    B.normal = normalized(cross(verts[0], verts[1]));   /* Parallelogram/Triangle/Polygon::normal boundary.cpp:137,172,231 */
+    B.offset = -dot(B.normal, o);
+    B.o = o; B.T = T;
+    B.rot = rotMatrix(B.normal); B.refl = reflMatrix(B.normal);
+    return B;
+}
+int finishCell(orc_domain& D, OSubdomain& sd, std::vector<OBoundary>& b) {
+    int s = (int)D.sdoms.size();
+    for (OBoundary& B : b) {
+        B.sdom = s;
+        int id = (int)D.planes.size();
+        bool emitting = (B.kind == MCB_BDRY_ISOT || B.kind == MCB_BDRY_PERI);
+        if (emitting && B.emitWeight() != 0.) { B.emitRegistered = true; sd.emitPlanes.push_back(id); }
+        D.planes.push_back(B);
+        sd.planes.push_back(id);
+    }
+    D.sdoms.push_back(sd);
+    return s;
+}
+const int PAR = MCB_SHAPE_PARALLELOGRAM, TRI = MCB_SHAPE_TRIANGLE, POLY = MCB_SHAPE_POLYGON;
+
+/* TriangularPrism<Bac,Lef,Bot,Dia,Top> subdomain.h:206-233 */
+int addTriangularPrism(orc_domain& D, const V3& o, const M3& mat, const long div[3], const V3& gradT, const int kinds[5], const double T[5]) {
+    OSubdomain sd; sd.cell = MCB_CELL_TRIPRISM;
+    initSubdomain(sd, determinant(mat) / 2., o, mat, div, gradT);
+    V3 c0 = mat.col(0), c1 = mat.col(1), c2 = mat.col(2);
+    std::vector<OBoundary> b = {
+        makeBoundaryShape(kinds[0], o,      PAR, {c1, c2}, T[0]),
+        makeBoundaryShape(kinds[1], o,      PAR, {c2, c0}, T[1]),
+        makeBoundaryShape(kinds[2], o,      TRI, {c0, c1}, T[2]),
+        makeBoundaryShape(kinds[3], o + c0, PAR, {c2, c1 - c0}, T[3]),
+        makeBoundaryShape(kinds[4], o + c2, TRI, {c1, c0}, T[4])};
+    return finishCell(D, sd, b);
+}
+/* Tetrahedron<Bac,Lef,Bot,Dia> subdomain.h:289-314 */
+int addTetrahedron(orc_domain& D, const V3& o, const M3& mat, const long div[3], const V3& gradT, const int kinds[4], const double T[4]) {
+    OSubdomain sd; sd.cell = MCB_CELL_TETRAHEDRON;
+    initSubdomain(sd, determinant(mat) / 6., o, mat, div, gradT);
+    V3 c0 = mat.col(0), c1 = mat.col(1), c2 = mat.col(2);
+    std::vector<OBoundary> b = {
+        makeBoundaryShape(kinds[0], o,      TRI, {c1, c2}, T[0]),
+        makeBoundaryShape(kinds[1], o,      TRI, {c2, c0}, T[1]),
+        makeBoundaryShape(kinds[2], o,      TRI, {c0, c1}, T[2]),
+        makeBoundaryShape(kinds[3], o + c0, TRI, {c2 - c0, c1 - c0}, T[3])};
+    return finishCell(D, sd, b);
+}
+/* Prism<Bot,Top,Sid> subdomain.h:363-470 and Pyramid<Bot,Sid> :486-596.  cols = mat_ (col 0 = axis / apex vector, cols
+ * 1..N-1 = base fan).  PrismImpl/PyramidImpl::volume (subdomain.cpp:385-394, 417-426) pairs columns i, i+1 for i < N-2. */
+int addPrismLike(orc_domain& D, bool pyramid, const V3& o, const std::vector<V3>& cols, long div, const V3& gradT,
+                 const std::vector<int>& kinds, const std::vector<double>& T) {
+    const long N = (long)cols.size();
+    OSubdomain sd; sd.cell = pyramid ? MCB_CELL_PYRAMID : MCB_CELL_PRISM;
+    std::vector<double> vol((size_t)(N - 2));
+    double total = 0.;
+    for (long i = 0; i < N - 2; ++i) { vol[(size_t)i] = dot(cross(cols[(size_t)i], cols[(size_t)i + 1]), cols[0]) / (pyramid ? 6. : 2.); total += vol[(size_t)i]; }
+    M3 base;                                                         /* matBase = (col 1, col N-1, col 0) */
+    for (int k = 0; k < 3; ++k) { base(k, 0) = cols[1][k]; base(k, 1) = cols[(size_t)N - 1][k]; base(k, 2) = cols[0][k]; }
+    long dv[3] = {div < 0 ? -1l : 0l, div < 0 ? -1l : 0l, div < 0 ? -1l : 0l};
+    initSubdomain(sd, total, o, base, dv, gradT);
+    sd.base = cols;
+    sd.volDist = Discrete(vol.data(), vol.data() + (N - 2));
+    std::vector<V3> bot(cols.begin() + 1, cols.end()), top(bot.rbegin(), bot.rend());
+    std::vector<OBoundary> b;
+    size_t t = 0;
+    b.push_back(makeBoundaryShape(kinds[t], o, POLY, bot, T[t])); ++t;
+    if (!pyramid) { b.push_back(makeBoundaryShape(kinds[t], o + cols[0], POLY, top, T[t])); ++t; }
+    for (long ind = 0; ind < N; ++ind, ++t) {                        /* InitSidesF :428-452 / :553-578 */
+        V3 p; if (ind != 0) p = p + cols[(size_t)ind];
+        V3 i = cols[0]; if (pyramid && ind != 0) i = i - cols[(size_t)ind];
+        V3 j = -p; if (ind != N - 1) j = j + cols[(size_t)ind + 1];
+        b.push_back(makeBoundaryShape(kinds[t], o + p, pyramid ? TRI : PAR, {i, j}, T[t]));
+    }
+    return finishCell(D, sd, b);
+}
+
 /* makePair(InterBoundary&, InterBoundary&) boundary.cpp:361-369 */
 void pairInter(orc_domain& D, int a, int b) { D.planes[a].pairs.push_back(b); D.planes[b].pairs.push_back(a); }
 /* makePair(PeriBoundary&, PeriBoundary&, transl, rot) boundary.cpp:524-550 */
@@ -636,9 +763,13 @@ void finishDomain(orc_domain& D) {
         s.grad_t[0] = S.gradT.x; s.grad_t[1] = S.gradT.y; s.grad_t[2] = S.gradT.z;
         std::memcpy(s.emit_rot, S.emitRot.m, sizeof s.emit_rot);
         s.plane_begin = S.planes.empty() ? 0 : S.planes.front(); s.plane_count = (int32_t)S.planes.size();
+        s.nbase = (int32_t)S.base.size();
+        for (size_t v = 0; v < S.base.size() && v < MCB_MAX_BASE; ++v) { s.base[3 * v] = S.base[v].x; s.base[3 * v + 1] = S.base[v].y; s.base[3 * v + 2] = S.base[v].z; }
         D.fs.push_back(s);
     }
     for (const OEmitter& e : D.emitters) D.fe.push_back({e.kind, e.index, D.emitWeight(e)});
+    D.fcellvol.assign((size_t)D.cols, 0.);
+    orc_domain_cell_vol(&D, D.fcellvol.data());
 }
 
 const int SPEC = MCB_BDRY_SPEC, DIFF = MCB_BDRY_DIFF, INTER = MCB_BDRY_INTER, ISOT = MCB_BDRY_ISOT, PERI = MCB_BDRY_PERI;
@@ -1029,11 +1160,43 @@ orc_domain* orc_domain_create(const char* kind, const double* dim, int ndim, con
         pairPeri(*D, pl(*D, 0, 0), pl(*D, 0, 3), transl);
         pairPeri(*D, pl(*D, 1, 0), pl(*D, 1, 3), transl);
         pairPeri(*D, pl(*D, 2, 0), pl(*D, 2, 3), transl);
+    } else if (k == "hex") {                          /* domain.h:142-143, domain.cpp:238-256 (+ init(), which the reference forgets) */
+        if (!need(4, 0)) return nullptr;
+        std::vector<V3> cols = {V3(dim[0], 0., 0.), V3(0., dim[1], -dim[3]), V3(0., 2. * dim[1], 0.), V3(0., 2. * dim[1], dim[2]),
+                                V3(0., dim[1], dim[2] + dim[3]), V3(0., 0., dim[2])};
+        addPrismLike(*D, false, V3(), cols, 0, V3(-dT / dim[0], 0., 0.), {PERI, PERI, SPEC, SPEC, SPEC, SPEC, SPEC, SPEC}, std::vector<double>(8, 0.));
+        pairPeri(*D, pl(*D, 0, 0), pl(*D, 0, 1), V3(dim[0], 0., 0.));
+    } else if (k == "pyr") {                          /* domain.h:165, domain.cpp:299-314 */
+        if (!need(3, 0)) return nullptr;
+        std::vector<V3> cols = {V3(dim[0], 0.5 * dim[1], 0.5 * dim[2]), V3(0., dim[1], 0.), V3(0., dim[1], dim[2]), V3(0., 0., dim[2])};
+        addPrismLike(*D, true, V3(), cols, 0, V3(-dT / dim[0], 0., 0.), {SPEC, SPEC, SPEC, SPEC, SPEC}, std::vector<double>(5, 0.));
     } else {
-        set_err("Invalid domain " + k + " (oracle builds bulk, film, jct, tee, tube and orc_domain_box)");
+        set_err("Invalid domain " + k + " (oracle builds bulk, film, jct, tee, tube, hex, pyr, orc_domain_box and orc_domain_cell)");
         return nullptr;
     }
     for (const OSubdomain& s : D->sdoms) if (!(s.vol >= DMIN)) { set_err("Volume too small, check vector order"); return nullptr; }
+    finishDomain(*D);
+    return D.release();
+}
+/* One non-box cell (MCB_CELL_TRIPRISM / TETRAHEDRON: cols = 3 mat columns, div[3]; PRISM / PYRAMID: cols = N mat_ columns,
+ * div[0] only) with the given boundary kinds and wall temperatures in declaration order; no pairing (Spec/Diff/Isot). */
+orc_domain* orc_domain_cell(int cell, const double origin[3], const double* cols, int ncols, const int64_t div[3],
+                            const double grad_t[3], const int32_t* kinds, const double* T) {
+    std::unique_ptr<orc_domain> D(new orc_domain);
+    V3 o(origin[0], origin[1], origin[2]), g(grad_t[0], grad_t[1], grad_t[2]);
+    std::vector<V3> c; for (int i = 0; i < ncols; ++i) c.push_back(V3(cols[3 * i], cols[3 * i + 1], cols[3 * i + 2]));
+    long dv[3] = {(long)div[0], (long)div[1], (long)div[2]};
+    if (cell == MCB_CELL_TRIPRISM || cell == MCB_CELL_TETRAHEDRON) {
+        if (ncols != 3) { set_err("tri-prism / tetrahedron need 3 columns"); return nullptr; }
+        M3 m; for (int i = 0; i < 3; ++i) for (int k = 0; k < 3; ++k) m(k, i) = c[(size_t)i][k];
+        int kk[5]; for (int i = 0; i < (cell == MCB_CELL_TRIPRISM ? 5 : 4); ++i) kk[i] = kinds[i];
+        if (cell == MCB_CELL_TRIPRISM) addTriangularPrism(*D, o, m, dv, g, kk, T); else addTetrahedron(*D, o, m, dv, g, kk, T);
+    } else if (cell == MCB_CELL_PRISM || cell == MCB_CELL_PYRAMID) {
+        if (ncols < 4 || ncols > MCB_MAX_BASE) { set_err("prism / pyramid need 4..9 columns"); return nullptr; }
+        const int nb = ncols + (cell == MCB_CELL_PRISM ? 2 : 1);
+        addPrismLike(*D, cell == MCB_CELL_PYRAMID, o, c, dv[0], g, std::vector<int>(kinds, kinds + nb), std::vector<double>(T, T + nb));
+    } else { set_err("orc_domain_cell: unknown cell kind"); return nullptr; }
+    if (!(D->sdoms[0].vol >= DMIN)) { set_err("Volume too small, check vector order"); return nullptr; }
     finishDomain(*D);
     return D.release();
 }
@@ -1045,14 +1208,18 @@ int orc_domain_desc(const orc_domain* d, mcb_domain_desc* o) {
     o->nplane = (int32_t)d->fp.size(); o->planes = d->fp.data();
     o->npair = (int32_t)d->fpairs.size(); o->pairs = d->fpairs.data();
     o->nemitter = (int32_t)d->fe.size(); o->emitters = d->fe.data();
+    o->ncols = d->cols; o->cell_vol = d->fcellvol.data();
     return MCB_OK;
 }
 /* Field(1, dom, CellVolF()) field.cpp:53-80: columns in (k, j, i) nesting, i fastest */
 int orc_domain_cell_vol(const orc_domain* d, double* vol) {
     long n = 0;
     for (size_t s = 0; s < d->sdoms.size(); ++s) {
-        long sp = d->sdoms[s].shapeProd();
-        for (long i = 0; i < sp; ++i) vol[n++] = d->cellVol((int)s);
+        const long* sh = d->sdoms[s].shape;
+        for (long k = 0; k < sh[2]; ++k) for (long j = 0; j < sh[1]; ++j) for (long i = 0; i < sh[0]; ++i) {
+            long idx[3] = {i, j, k};
+            vol[n++] = d->cellVol((int)s, idx);
+        }
     }
     return MCB_OK;
 }

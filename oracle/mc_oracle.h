@@ -41,8 +41,8 @@ double orc_material_cond(const orc_material*);                         /* Materi
 int    orc_material_alias(const orc_material*, int which, double* wprob, int32_t* walias,
                           double* pprob, int32_t* palias);
 
-/* Shipped domains (domain.cpp): kind in {"bulk","film","jct","tee","tube"}; dim/div are the
- * constructor vectors (NOT the CLI shorthand).  */
+/* Shipped domains (domain.cpp): kind in {"bulk","film","jct","tee","tube","hex","pyr"}; dim/div are the
+ * constructor vectors (NOT the CLI shorthand).  hex/pyr take no divisions (ndiv = 0). */
 orc_domain* orc_domain_create(const char* kind, const double* dim, int ndim,
                               const int64_t* div, int ndiv, double dT);
 /* One Parallelepiped<...> with arbitrary boundary kinds (MCB_BDRY_*), wall temperatures
@@ -50,6 +50,9 @@ orc_domain* orc_domain_create(const char* kind, const double* dim, int ndim,
  * 2<->5 by pure translation (as BulkDomain::init does, domain.cpp:137-141). */
 orc_domain* orc_domain_box(const double origin[3], const double mat[9], const int64_t div[3],
                            const double grad_t[3], const int32_t kinds[6], const double T[6]);
+/* One non-box cell (tri-prism, tetrahedron, prism, pyramid: subdomain.h:200-630) with Spec/Diff/Isot faces. */
+orc_domain* orc_domain_cell(int cell, const double origin[3], const double* cols, int ncols, const int64_t div[3],
+                            const double grad_t[3], const int32_t* kinds, const double* T);
 void   orc_domain_free(orc_domain*);
 int    orc_domain_desc(const orc_domain*, mcb_domain_desc* out);
 int64_t orc_domain_cols(const orc_domain*);

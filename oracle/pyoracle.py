@@ -46,6 +46,8 @@ def lib():
         L.orc_domain_create.argtypes = [C.c_char_p, dp, C.c_int, lp, C.c_int, C.c_double]
         L.orc_domain_box.restype = vp
         L.orc_domain_box.argtypes = [dp, dp, lp, dp, ip, dp]
+        L.orc_domain_cell.restype = vp
+        L.orc_domain_cell.argtypes = [C.c_int, dp, dp, C.c_int, lp, dp, ip, dp]
         L.orc_domain_free.argtypes = [vp]
         L.orc_domain_desc.argtypes = [vp, C.POINTER(abi.DomainDesc)]
         L.orc_domain_cols.restype = C.c_int64
@@ -135,6 +137,17 @@ class Domain:
         t = np.ascontiguousarray(T, np.float64)
         return cls(lib().orc_domain_box(_dp(origin), _dp(matc), div.ctypes.data_as(abi.c_int64_p), _dp(g),
                                         k.ctypes.data_as(abi.c_int32_p), _dp(t)))
+
+    @classmethod
+    def cell(cls, cell, origin, cols, div, grad_t, kinds, T=None):
+        """One non-box cell: cols = list of 3-vectors (mat columns)."""
+        origin = np.ascontiguousarray(origin, np.float64)
+        c = np.ascontiguousarray(np.asarray(cols, np.float64).reshape(-1))
+        div = np.ascontiguousarray(div, np.int64); g = np.ascontiguousarray(grad_t, np.float64)
+        k = np.ascontiguousarray(kinds, np.int32)
+        t = np.ascontiguousarray(T if T is not None else [0.0] * len(k), np.float64)
+        return cls(lib().orc_domain_cell(cell, _dp(origin), _dp(c), len(c) // 3, div.ctypes.data_as(abi.c_int64_p), _dp(g),
+                                         k.ctypes.data_as(abi.c_int32_p), _dp(t)))
 
     def cell_vol(self):
         v = np.zeros(self.cols)

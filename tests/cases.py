@@ -46,6 +46,35 @@ def tube(L=1e-6, a=5e-8, t=2e-8, div=(0, 8, 8, 4)):
     return orc.Domain.create("tube", [L, a, a, t], list(div), 1e6 * L)
 
 
+def hexd(L=1e-6, a=5e-8, b=8e-8, c=3e-8):
+    """HexDomain (domain.h:142): one hexagonal Prism, periodic along x, six specular sides."""
+    return orc.Domain.create("hex", [L, a, b, c], [], 1e6 * L)
+
+
+def pyr(a=1e-7):
+    """PyrDomain (domain.h:165): one square Pyramid, all faces specular."""
+    return orc.Domain.create("pyr", [a, a, a], [], 1e6 * a)
+
+
+def triprism(div=(4, 4, 2)):
+    """One gridded TriangularPrism (subdomain.h:206) with mixed diffuse / specular faces and a volumetric source."""
+    return orc.Domain.cell(abi.CELL_TRIPRISM, [1e-8, 0, -2e-8], [[1e-7, 0, 0], [2e-8, 1e-7, 0], [0, 1e-8, 2e-7]], list(div),
+                           [-1e6, 5e5, 0], [D, S, D, S, D])
+
+
+def tet(div=(3, 3, 3)):
+    """One gridded Tetrahedron (subdomain.h:289) with an isothermal emitting face (Triangle shape)."""
+    return orc.Domain.cell(abi.CELL_TETRAHEDRON, [0, 0, 0], [[1e-7, 0, 0], [1e-8, 1e-7, 0], [0, 2e-8, 1e-7]], list(div),
+                           [0, 0, 0], [ISO, S, D, D], [1.0, 0, 0, 0])
+
+
+def prism5(div=0):
+    """A 5-column Prism (pentagonal base) with isothermal Polygon faces top and bottom (Polygon emitters)."""
+    cols = [[1e-7, 0, 0], [0, 5e-8, -2e-8], [0, 9e-8, 1e-8], [0, 7e-8, 6e-8], [0, 0, 5e-8]]
+    return orc.Domain.cell(abi.CELL_PRISM, [0, 0, 0], cols, [div, 0, 0], [-1e6, 0, 0], [ISO, ISO, D, S, D, S, D], [0.5, -0.5, 0, 0, 0, 0, 0])
+
+
+NONBOX = {"hex": hexd, "pyr": pyr, "triprism": triprism, "tet": tet, "prism5": prism5}
 DOMAINS = {"slab": slab, "wire": wire, "skew": skew, "bulk": bulk, "film": film, "jct": jct, "tee": tee, "tube": tube}
 
 
