@@ -80,6 +80,31 @@ public:
     std::vector<Vector3d> verts() const { return {i_, j_}; }
 };
 
+// Polygon<N>: planar fan of N-1 edge vectors from a common corner, N-2 triangles (boundary.h:112-131, boundary.cpp:189-258)
+template <int N>
+class Polygon : public Boundary::Shape {
+    static_assert(N > 3, "Polygon must have more than 3 sides");
+    std::vector<Vector3d> verts_;
+    std::vector<double> areas_;
+public:
+    Polygon() : verts_((size_t)(N - 1)), areas_((size_t)(N - 2), 0.) {}
+    explicit Polygon(const std::vector<Vector3d>& v) : verts_(v), areas_((size_t)(N - 2)) {
+        MC_ASSERT_MSG((int)verts_.size() == N - 1, "Incorrect number of vertices");
+        for (int n = 0; n < N - 2; ++n) {
+            const Vector3d c = verts_[(size_t)n].cross(verts_[(size_t)n + 1]);
+            areas_[(size_t)n] = c.norm() / 2.;
+            MC_ASSERT_MSG(areas_[(size_t)n] > Dbl::min(), "Area too small");
+            const Vector3d a = c.normalized(), b = normal();
+            for (int k = 0; k < 3; ++k) MC_ASSERT_MSG(std::abs(a(k) - b(k)) <= 1e-9, "Normals are inconsistent");
+        }
+    }
+    std::string type() const { return std::to_string(N); }
+    int kind() const { return MCB_SHAPE_POLYGON; }
+    Vector3d normal() const { return verts_[0].cross(verts_[1]).normalized(); }
+    double area() const { double s = 0.; for (double a : areas_) s += a; return s; }
+    std::vector<Vector3d> verts() const { return verts_; }
+};
+
 //---------------------------------------- non-emitting boundaries
 class SpecBoundary : public Boundary {
 public:

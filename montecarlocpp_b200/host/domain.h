@@ -1,7 +1,7 @@
 // domain.h — host mirror of Domain and the box-celled domains the reference ships (domain.h:38-296,
 // domain.cpp:28-570): Bulk, Film, Jct, Tee, Tube.  SlabDomain and WireDomain are NOT in the reference;
 // they are the two box variants BASELINE.json's configs need (isothermal walls; diffuse wire) and use
-// only reference building blocks.  Hex/Pyr/Octet need non-box cells and are not built.
+// only reference building blocks.  HexDomain / PyrDomain (non-box cells) are built; the 42-subdomain OctetDomain is not.
 #ifndef MCB_HOST_DOMAIN_H
 #define MCB_HOST_DOMAIN_H
 #include <iosfwd>
@@ -89,6 +89,31 @@ private:
     std::string info() const;
 public:
     WireDomain(const Vector3d& dim, const Vector3l& div, double dT);
+    Matrix3Xd checkpoints() const;
+};
+
+class HexDomain : public Domain {
+public:
+    typedef PeriBoundary<Polygon<6> > Peri6;
+    typedef Prism<Peri6, Peri6, std::tuple<Spec, Spec, Spec, Spec, Spec, Spec> > Sdom;
+private:
+    VectorXd dim_; double dT_;
+    Sdom sdom_;
+    std::string info() const;
+public:
+    HexDomain(const VectorXd& dim, double dT);                      // 4 dims
+    Matrix3Xd checkpoints() const;
+};
+
+class PyrDomain : public Domain {
+public:
+    typedef Pyramid<Spec, std::tuple<Spec, Spec, Spec, Spec> > Sdom;
+private:
+    Vector3d dim_; double dT_;
+    Sdom sdom_;
+    std::string info() const;
+public:
+    PyrDomain(const Vector3d& dim, double dT);
     Matrix3Xd checkpoints() const;
 };
 

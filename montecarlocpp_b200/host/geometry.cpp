@@ -130,6 +130,53 @@ void EmitSubdomain::describe(mcb_sdom_desc& d) const {
     for (int k = 0; k < 9; ++k) d.emit_rot[k] = rot_.m[k];
 }
 
+//---------------------------------------- simplex / prism helpers
+// Volume of grid cell `index` of a triangular prism: the part of the cell's base rectangle under the diagonal, by
+// inclusion-exclusion on the normalised distance f to the diagonal.  (The normalisation treats a full cell as
+// vol / prod(shape); kept as in the reference, subdomain.cpp:283-307.)
+double TriangularPrismImpl::cellVol(const Vector3l& index, const Vector3l& shape, double vol) {
+    const double s0 = (double)shape(0), s1 = (double)shape(1);
+    const double f0 = 1. - ((double)index(0) / s0 + (double)index(1) / s1);
+    if (f0 <= 0.) return 0.;
+    const double f1 = f0 - (1. / s0 + 1. / s1);
+    if (f1 >= 0.) return vol / shape.prod();
+    double frac = std::pow(f0, 2);
+    const double step[2] = {1. / s0, 1. / s1};
+    for (int i = 0; i < 2; i++) {
+        const double f = f0 - step[i];
+        if (f > 0.) frac += -1 * std::pow(f, 2);
+    }
+    return vol * frac / (2. * shape(2));
+}
+// Same for a tetrahedron (subdomain.cpp:322-349): corners one step (sign -) and two steps (sign +) away
+double TetrahedronImpl::cellVol(const Vector3l& index, const Vector3l& shape, double vol) {
+    const double s[3] = {(double)shape(0), (double)shape(1), (double)shape(2)};
+    const double f0 = 1. - ((double)index(0) / s[0] + (double)index(1) / s[1] + (double)index(2) / s[2]);
+    if (f0 <= 0.) return 0.;
+    const double f1 = f0 - (1. / s[0] + 1. / s[1] + 1. / s[2]);
+    if (f1 >= 0.) return vol / shape.prod();
+    static const int corner[6][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, 1, 1}, {1, 0, 1}, {1, 1, 0}};
+    double frac = std::pow(f0, 3);
+    for (int i = 0; i < 6; i++) {
+        const int n = corner[i][0] + corner[i][1] + corner[i][2];
+        const int sign = (n % 2) ? -1 : 1;
+        const double f = f0 - ((double)corner[i][0] / s[0] + (double)corner[i][1] / s[1] + (double)corner[i][2] / s[2]);
+        if (f > 0.) frac += sign * std::pow(f, 3);
+    }
+    return vol * frac / 6.;
+}
+Matrix3d PrismImpl::matBase(const std::vector<Vector3d>& mat) {
+    MC_ASSERT_MSG(mat.size() >= 4, "Incorrect number of matrix columns");
+    return Matrix3d::Columns(mat[1], mat[mat.size() - 1], mat[0]);
+}
+// Sub-wedge volumes as the reference computes them (subdomain.cpp:385-394, 417-426): columns i and i+1 for i < N-2.
+std::vector<double> PrismImpl::volume(const std::vector<Vector3d>& mat, double div) {
+    const size_t N = mat.size();
+    std::vector<double> vol(N - 2);
+    for (size_t i = 0; i + 2 < N; ++i) vol[i] = mat[i].cross(mat[i + 1]).dot(mat[0]) / div;
+    return vol;
+}
+
 //---------------------------------------- Domain
 bool Domain::isInit() const {
     if (sdomPtrs_.empty()) return false;
@@ -276,3 +323,30 @@ Matrix3Xd TubeDomain::checkpoints() const {
                    Vector3d(0.5 * dim_[0], dim_[1] + 0.5 * dim_[3], dim_[2] + 0.5 * dim_[3]),
                    Vector3d(0.5 * dim_[0], 0.5 * dim_[1], dim_[2] + 0.5 * dim_[3])});
 }
+
+// hexagonal prism, periodic along x (domain.h:142-143, domain.cpp:238-256).  The reference's (dim, dT) constructor
+// never calls init(), which leaves the domain unusable; here it does.
+static std::vector<Vector3d> hexColumns(const VectorXd& d) {
+    return {Vector3d(d[0], 0., 0.), Vector3d(0., d[1], -d[3]), Vector3d(0., 2. * d[1], 0.), Vector3d(0., 2. * d[1], d[2]),
+            Vector3d(0., d[1], d[2] + d[3]), Vector3d(0., 0., d[2])};
+}
+HexDomain::HexDomain(const VectorXd& dim, double dT)
+    : dim_(checked(dim, 4, "HexDomain needs 4 dimensions")), dT_(dT),
+      sdom_(Vector3d::Zero(), hexColumns(dim), 0, Vector3d(-dT / dim[0], 0., 0.)) {
+    makePair(sdom_.bottom(), sdom_.top(), Vector3d(dim_[0], 0., 0.));
+    addSdom(&sdom_);
+}
+std::string HexDomain::info() const { return describe("HexDomain", static_cast<const Domain*>(this), dim_, VectorXl(), dT_); }
+Matrix3Xd HexDomain::checkpoints() const {
+    return points({Vector3d(0.5 * dim_[0], 0.5 * dim_[1], 0.5 * dim_[2]), Vector3d(0.5 * dim_[0], 1.5 * dim_[1], 0.5 * dim_[2])});
+}
+
+// square pyramid with its apex above the centre of the y-z base, all faces specular (domain.h:165, domain.cpp:299-314)
+PyrDomain::PyrDomain(const Vector3d& dim, double dT)
+    : dim_(dim), dT_(dT),
+      sdom_(Vector3d::Zero(), {Vector3d(dim(0), 0.5 * dim(1), 0.5 * dim(2)), Vector3d(0., dim(1), 0.), Vector3d(0., dim(1), dim(2)), Vector3d(0., 0., dim(2))},
+            0, Vector3d(-dT / dim(0), 0., 0.)) {
+    addSdom(&sdom_);
+}
+std::string PyrDomain::info() const { return describe("PyrDomain", static_cast<const Domain*>(this), vec(dim_), VectorXl(), dT_); }
+Matrix3Xd PyrDomain::checkpoints() const { return points({0.5 * dim_}); }

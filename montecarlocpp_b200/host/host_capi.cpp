@@ -42,6 +42,8 @@ mcbh_domain* mcbh_domain_create(const char* kind, const double* dim, int ndim, c
         } else if (k == "jct") { need(4, 4); h->dom.reset(new JctDomain(d, v, dT)); }
         else if (k == "tee") { need(5, 5); h->dom.reset(new TeeDomain(d, v, dT)); }
         else if (k == "tube") { need(4, 4); h->dom.reset(new TubeDomain(d, v, dT)); }
+        else if (k == "hex") { need(4, 0); h->dom.reset(new HexDomain(d, dT)); }
+        else if (k == "pyr") { need(3, 0); h->dom.reset(new PyrDomain(Vector3d(d[0], d[1], d[2]), dT)); }
         else MC_ASSERT_MSG(false, "Invalid domain");
         h->flat = flattenDomain(h->dom.get());
         return h.release();
@@ -90,6 +92,12 @@ int mcbh_problem_solve_seeded(const mcbh_problem* p, int device, uint64_t seed, 
         if (stats) *stats = FieldProblem::lastStats();
         return MCB_OK;
     , MCB_EINVAL)
+}
+
+// TriangularPrismImpl::cellVol (cell = MCB_CELL_TRIPRISM) / TetrahedronImpl::cellVol (MCB_CELL_TETRAHEDRON)
+double mcbh_simplex_cell_vol(int cell, const int64_t index[3], const int64_t shape[3], double vol) {
+    const Vector3l i(index[0], index[1], index[2]), s(shape[0], shape[1], shape[2]);
+    return cell == MCB_CELL_TRIPRISM ? TriangularPrismImpl::cellVol(i, s, vol) : TetrahedronImpl::cellVol(i, s, vol);
 }
 
 // TrajProblem(mat, dom, [prop], [pos], [dir], maxscat, maxloop).solve(mt19937(mt_seed)): polyline out (3 x npoints,

@@ -4,14 +4,14 @@
 //   <dir> <material> [T] <domain> <dims...> <divs...> <problem> <nemit> [size] <maxscat> <maxloop> <nsim>
 //
 //   grey|silicon [T] | custom [T] disp relax
-//   bulk dim div0 | film dim0 dim1 div1 | jct dim0 dim3 | tee dim0 dim4 div0 | tube dim0 dim1 dim3 div1 div3
+//   bulk dim div0 | film dim0 dim1 div1 | hex dim0 dim1 | pyr dim0 dim1 | jct dim0 dim3 | tee dim0 dim4 div0 | tube dim0 dim1 dim3 div1 div3
 //   slab dim0 dim1 div0 dT | wire dim0 dim1 div1        (not in the reference; see domain.h)
 //   temp|flux|multi nemit maxscat maxloop nsim | cumtemp|cumflux nemit size maxscat maxloop nsim
 //   check r00 r01 r02 r10 r11 r12 r20 r21 r22 | traj px py pz dx dy dz maxscat maxloop
 //
 // Differences from the reference driver: the solve runs on the GPU and is called once per repetition from
-// the main thread (the reference opens an OpenMP region and sums per-thread partials); the hex/pyr/octet
-// domains (non-box cells) are not built.
+// the main thread (the reference opens an OpenMP region and sums per-thread partials); the 42-subdomain octet
+// domain is not built.
 #include <unistd.h>
 #include <iomanip>
 #include <iostream>
@@ -144,6 +144,12 @@ int main(int argc, const char* argv[]) {
         } else if (domStr == "wire") {
             double d0, d1; long v1; argss >> d0 >> d1 >> v1;
             dom.reset(new WireDomain(Vector3d(d0, d1, d1), Vector3l(0, v1, v1), 1e6 * d0));
+        } else if (domStr == "hex") {
+            double d0, d1; argss >> d0 >> d1;
+            dom.reset(new HexDomain(VectorXd{d0, d1, d1, d1}, 1e6 * d0));
+        } else if (domStr == "pyr") {
+            double d0, d1; argss >> d0 >> d1;
+            dom.reset(new PyrDomain(Vector3d(d0, d1, d1), 1e6 * d0));
         } else if (domStr == "jct") {
             double d0, d3; argss >> d0 >> d3;
             dom.reset(new JctDomain(VectorXd{d0, d0, d0, d3}, VectorXl{0, 0, 0, 0}, 2e6 * d0));

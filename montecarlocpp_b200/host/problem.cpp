@@ -79,6 +79,7 @@ mcb_domain_desc FlatDomain::desc() const {
     d.nplane = (int32_t)planes.size(); d.planes = planes.data();
     d.npair = (int32_t)pairs.size(); d.pairs = pairs.data();
     d.nemitter = (int32_t)emitters.size(); d.emitters = emitters.data();
+    d.ncols = (int64_t)cell_vol.size(); d.cell_vol = cell_vol.empty() ? nullptr : cell_vol.data();
     return d;
 }
 
@@ -100,6 +101,9 @@ FlatDomain flattenDomain(const Domain* dom) {
         }
         f.sdoms.push_back(d);
         f.cols += sp[s]->shape().prod();
+        const Vector3l shp = sp[s]->shape();                               // Field(rows, dom, fun) nesting: k, j, i (field.cpp:62-78)
+        for (long k = 0; k < shp(2); ++k) for (long j = 0; j < shp(1); ++j) for (long i = 0; i < shp(0); ++i)
+            f.cell_vol.push_back(sp[s]->cellVol(Vector3l(i, j, k)));
     }
     for (size_t s = 0; s < sp.size(); ++s) {
         const Boundary::Pointers& bp = sp[s]->bdryPtrs();

@@ -85,6 +85,7 @@ struct FlatDomain {
     std::vector<mcb_plane_desc> planes;
     std::vector<int32_t> pairs;
     std::vector<mcb_emitter_desc> emitters;
+    std::vector<double> cell_vol;       // Field(1, dom, CellVolF()): Subdomain::cellVol per column
     long cols;
     mcb_domain_desc desc() const;
 };

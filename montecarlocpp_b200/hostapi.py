@@ -41,6 +41,8 @@ def lib():
         L.mcbh_problem_desc.argtypes = [vp, C.POINTER(abi.ProblemDesc)]
         L.mcbh_problem_solve.argtypes = [vp, C.c_int, C.c_uint32, dp, C.POINTER(abi.Stats)]
         L.mcbh_problem_solve_seeded.argtypes = [vp, C.c_int, C.c_uint64, C.c_int64, C.c_int64, dp, C.POINTER(abi.Stats)]
+        L.mcbh_simplex_cell_vol.restype = C.c_double
+        L.mcbh_simplex_cell_vol.argtypes = [C.c_int, lp, lp, C.c_double]
         _lib = L
     return _lib
 
@@ -125,3 +127,9 @@ class FieldProblem:
     def __del__(self):
         if getattr(self, "h", None):
             lib().mcbh_problem_free(self.h); self.h = None
+
+
+def simplex_cell_vol(cell, index, shape, vol):
+    """TriangularPrismImpl::cellVol / TetrahedronImpl::cellVol of the host mirror."""
+    i = np.ascontiguousarray(index, np.int64); s = np.ascontiguousarray(shape, np.int64)
+    return lib().mcbh_simplex_cell_vol(cell, i.ctypes.data_as(abi.c_int64_p), s.ctypes.data_as(abi.c_int64_p), float(vol))

@@ -328,3 +328,15 @@ def test_nonbox_cells_match_oracle(gpu_ctx, omats, dname):
     fin = np.isfinite(ref)
     scale = np.abs(ref[fin]).max()
     assert np.abs(got[fin] - ref[fin]).max() <= 1e-9 * scale
+
+
+def test_host_mirror_hex_and_pyr_domains_solve(matfiles, omats):
+    """HexDomain / PyrDomain through the C++ mirror (Prism / Pyramid cells, Polygon<6> periodic faces)."""
+    from montecarlocpp_b200 import hostapi
+    hm = hostapi.Material(*matfiles["grey"])
+    for k, dim, odom in (("hex", [1e-6, 5e-8, 8e-8, 3e-8], cases.hexd()), ("pyr", [1e-7, 1e-7, 1e-7], cases.pyr())):
+        hp = hostapi.FieldProblem(hm, hostapi.Domain(k, dim, [], 1e6 * dim[0]), "multi", 20000, 30)
+        got, gst = hp.solve_seeded(SEED)
+        ref, rst = orc.Problem(omats["grey"], odom, "multi", 20000, 30).solve(rng=orc.RNG_PHILOX, seed=SEED)
+        assert (gst["emitted"], gst["steps"], gst["esc"]) == (rst["emitted"], rst["steps"], 0)
+        assert np.abs(got - ref).max() <= 1e-9 * np.abs(ref).max()

@@ -242,6 +242,41 @@ def test_host_mirror_tables_are_bit_identical_to_the_oracle(matfiles, omats):
     assert all(_bytes(hw.desc.planes[i]) == _bytes(ow.desc.planes[i]) for i in range(6)) and _bytes(hw.desc.sdoms[0]) == _bytes(ow.desc.sdoms[0])
 
 
+def test_host_mirror_nonbox_cells_match_the_oracle():
+    """HexDomain / PyrDomain flatten bit-identically; the simplex cell-volume formulas agree cell by cell."""
+    from montecarlocpp_b200 import hostapi
+    for k, dim in (("hex", [1e-6, 5e-8, 8e-8, 3e-8]), ("pyr", [1e-7, 1e-7, 1e-7])):
+        hd, od = hostapi.Domain(k, dim, [], 1.0), orc.Domain.create(k, dim, [], 1.0)
+        assert (hd.desc.nsdom, hd.desc.nplane, hd.desc.npair, hd.desc.nemitter, hd.cols) == \
+               (od.desc.nsdom, od.desc.nplane, od.desc.npair, od.desc.nemitter, od.cols)
+        assert all(_bytes(hd.desc.sdoms[i]) == _bytes(od.desc.sdoms[i]) for i in range(hd.desc.nsdom))
+        assert all(_bytes(hd.desc.planes[i]) == _bytes(od.desc.planes[i]) for i in range(hd.desc.nplane))
+        assert all(_bytes(hd.desc.emitters[i]) == _bytes(od.desc.emitters[i]) for i in range(hd.desc.nemitter))
+        assert [hd.desc.cell_vol[i] for i in range(hd.desc.ncols)] == [od.desc.cell_vol[i] for i in range(od.desc.ncols)]
+    for name, cell in (("triprism", abi.CELL_TRIPRISM), ("tet", abi.CELL_TETRAHEDRON)):
+        dom = cases.NONBOX[name]()
+        S = dom.desc.sdoms[0]
+        shape = list(S.shape[:]); vols = dom.cell_vol(); n = 0
+        for kk in range(shape[2]):
+            for j in range(shape[1]):
+                for i in range(shape[0]):
+                    assert hostapi.simplex_cell_vol(cell, [i, j, kk], shape, S.vol) == vols[n]; n += 1
+        assert (vols == 0).any() and (vols > 0).any()             # cells outside the simplex have zero volume
+    # a single-cell triangular prism: the literal formula returns vol / 2 (sic, subdomain.cpp:306)
+    assert hostapi.simplex_cell_vol(abi.CELL_TRIPRISM, [0, 0, 0], [1, 1, 1], 3.0) == 1.5
+
+
+def test_nonbox_oracle_geometry_is_closed(omats):
+    """No phonon escapes a tri-prism / tetrahedron / prism / pyramid cell: the plane sets are consistent (esc == 0)."""
+    for name in sorted(cases.NONBOX):
+        dom = cases.NONBOX[name]()
+        sol, st = orc.Problem(omats["grey"], dom, "multi", 20000, 20).solve(seed=4)
+        assert st["esc"] == 0 and st["steps"] > 20000, name
+        d = dom.desc
+        for b in range(d.nplane):
+            assert abs(np.linalg.norm(d.planes[b].normal[:]) - 1) < 1e-14
+
+
 def test_host_mirror_error_behaviour(matfiles):
     from montecarlocpp_b200 import hostapi
     with pytest.raises(RuntimeError, match="Error opening dispersion file"):
