@@ -32,6 +32,9 @@ WORKLOADS = {
     "C2-slab100nm-si": ("slab", [100e-9, 100e-9, 100e-9], [100, 0, 0], 1.0, "multi", 1000, "silicon"),
     "C2-slab100nm-grey": ("slab", [100e-9, 100e-9, 100e-9], [100, 0, 0], 1.0, "multi", 1000, "grey"),
     "C1-film100nm-si": ("film", [1e-6, 100e-9, 1e-6], [0, 20, 0], 1.0, "multi", 100, "silicon"),
+    "C3-wire32x32-si": ("wire", [1e-6, 100e-9, 100e-9], [0, 32, 32], 1.0, "multi", 100, "silicon"),
+    "C4-tube-si": ("tube", [1e-6, 5e-8, 5e-8, 2e-8], [0, 8, 8, 4], 1.0, "multi", 100, "silicon"),
+    "C5-bulk128-si": ("bulk", [1e-6, 1e-6, 1e-6], [128, 128, 128], 1.0, "multi", 100, "silicon"),
 }
 
 
@@ -108,6 +111,9 @@ def cpu_reference_rate(workload, nemit_total, sample, seed, threads=0):
         from montecarlocpp_b200 import abi
         dom = orc.Domain.box([0, 0, 0], dim, div, [0, 0, 0], [abi.BDRY_ISOT, abi.BDRY_SPEC, abi.BDRY_SPEC] * 2,
                              [dT / 2, 0, 0, -dT / 2, 0, 0])
+    elif kind == "wire":
+        from montecarlocpp_b200 import abi
+        dom = orc.Domain.box([0, 0, 0], dim, div, [-dT / dim[0], 0, 0], [abi.BDRY_PERI, abi.BDRY_DIFF, abi.BDRY_DIFF] * 2)
     else:
         dom = orc.Domain.create(kind, dim, div, dT)
     prob = orc.Problem(mat, dom, pkind, nemit_total, maxscat)

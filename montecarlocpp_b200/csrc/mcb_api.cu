@@ -94,7 +94,7 @@ struct mcb_ctx {
     DevBuf<double> f_wprob, f_pprob; DevBuf<int32_t> f_walias, f_palias;
     // geometry
     bool has_dom = false; GeometryView gv{}; DevBuf<unsigned char> geo_blob;
-    std::vector<DSdom> h_sdom; int nemitter = 0; bool any_nd = false;
+    std::vector<DSdom> h_sdom; int nemitter = 0; int any_nd = 0;      // 0 / 1 / 2: see k_step's NDM
     DevBuf<DEmitter> emitters; DevBuf<double> cell_vol; long long cols = 0;
     // problem / run state
     DevBuf<long long> emit_cdf;
@@ -140,21 +140,22 @@ int check_problem(mcb_ctx* c, const mcb_problem_desc* p) {
     return MCB_OK;
 }
 
-template <int NCOMP, int TM, bool ND, bool EMIT>
+template <int NCOMP, int TM, int NDM, bool EMIT>
 cudaError_t launch_step_inst(const StepParams& P, int grid, int block, size_t smem, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(k_step<NCOMP, TM, ND, EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_step<NCOMP, TM, NDM, EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k_step<NCOMP, TM, ND, EMIT><<<grid, block, smem, s>>>(P);
+    k_step<NCOMP, TM, NDM, EMIT><<<grid, block, smem, s>>>(P);
     return cudaGetLastError();
 }
 template <int NCOMP, int TM>
-cudaError_t launch_step_nd(const StepParams& P, bool nd, int grid, int block, size_t smem, cudaStream_t s) {
+cudaError_t launch_step_nd(const StepParams& P, int ndm, int grid, int block, size_t smem, cudaStream_t s) {
     const bool emit = P.free_list == nullptr;          // no free list -> emission happens inside k_step
-    if (nd) return emit ? launch_step_inst<NCOMP, TM, true, true>(P, grid, block, smem, s) : launch_step_inst<NCOMP, TM, true, false>(P, grid, block, smem, s);
-    return emit ? launch_step_inst<NCOMP, TM, false, true>(P, grid, block, smem, s) : launch_step_inst<NCOMP, TM, false, false>(P, grid, block, smem, s);
+    if (ndm == 2) return emit ? launch_step_inst<NCOMP, TM, 2, true>(P, grid, block, smem, s) : launch_step_inst<NCOMP, TM, 2, false>(P, grid, block, smem, s);
+    if (ndm == 1) return emit ? launch_step_inst<NCOMP, TM, 1, true>(P, grid, block, smem, s) : launch_step_inst<NCOMP, TM, 1, false>(P, grid, block, smem, s);
+    return emit ? launch_step_inst<NCOMP, TM, 0, true>(P, grid, block, smem, s) : launch_step_inst<NCOMP, TM, 0, false>(P, grid, block, smem, s);
 }
 template <int NCOMP>
-cudaError_t launch_step_tm(const StepParams& P, int tm, bool nd, int grid, int block, size_t smem, cudaStream_t s) {
+cudaError_t launch_step_tm(const StepParams& P, int tm, int nd, int grid, int block, size_t smem, cudaStream_t s) {
     switch (tm) {
     case MCB_TM_WARP: return launch_step_nd<NCOMP, MCB_TM_WARP>(P, nd, grid, block, smem, s);
     case MCB_TM_BLOCK: return launch_step_nd<NCOMP, MCB_TM_BLOCK>(P, nd, grid, block, smem, s);
@@ -162,7 +163,7 @@ cudaError_t launch_step_tm(const StepParams& P, int tm, bool nd, int grid, int b
     }
 }
 // payload rows per deposit: Temp/CumTemp 1 (dt), Flux/CumFlux 3 (dpos), Multi 4 (dt, dpos)
-cudaError_t launch_step(const StepParams& P, int tm, bool nd, int grid, int block, size_t smem, cudaStream_t s) {
+cudaError_t launch_step(const StepParams& P, int tm, int nd, int grid, int block, size_t smem, cudaStream_t s) {
     switch (P.kind) {
     case MCB_PROB_TEMP: case MCB_PROB_CUMTEMP: return launch_step_tm<1>(P, tm, nd, grid, block, smem, s);
     case MCB_PROB_FLUX: case MCB_PROB_CUMFLUX: return launch_step_tm<3>(P, tm, nd, grid, block, smem, s);
@@ -184,8 +185,9 @@ struct RunPlan { long long slots; int S, block, grid; int tm, copies; size_t sme
 
 int plan_run(mcb_ctx* c, const mcb_problem_desc* prob, long long nparticles, RunPlan* r) {
     const mcb_options& o = c->opt;
-    r->block = o.block > 0 ? o.block : MCB_BLOCK_MAX;
-    if (r->block % 32 != 0 || r->block > MCB_BLOCK_MAX) { c->err = "block must be a multiple of 32, <= " + std::to_string(MCB_BLOCK_MAX); return MCB_EINVAL; }
+    const int block_max = c->any_nd == 2 ? MCB_BLOCK_MAX_ND : MCB_BLOCK_MAX;  // the cooperative N-D kernels are built for fewer, fatter threads
+    r->block = o.block > 0 ? std::min(o.block, block_max) : block_max;
+    if (r->block % 32 != 0 || o.block > MCB_BLOCK_MAX) { c->err = "block must be a multiple of 32, <= " + std::to_string(MCB_BLOCK_MAX); return MCB_EINVAL; }
     const int per_sm = o.ctas_per_sm > 0 ? o.ctas_per_sm : 1;
     r->S = o.steps_per_launch > 0 ? o.steps_per_launch : 16;
     long long slots = o.slots > 0 ? o.slots : (long long)c->sm_count * r->block * 32;   // ~2.4 M resident phonons
@@ -503,7 +505,7 @@ int mcb_upload_domain(mcb_ctx* c, const mcb_domain_desc* d) {
         for (int k = 0; k < 3; ++k) q.t[k] = p.peri_transl[k];
     }
     for (int i = 0; i < d->npair; ++i) if (d->pairs[i] < 0 || d->pairs[i] >= d->nplane) { c->err = "pair id out of range"; return MCB_EINVAL; }
-    std::vector<DSdom> sd(d->nsdom); std::vector<double> cell_vol; bool any_nd = false;
+    std::vector<DSdom> sd(d->nsdom); std::vector<double> cell_vol; int any_nd = 0;
     long long cols = 0;
     for (int s = 0; s < d->nsdom; ++s) {
         const mcb_sdom_desc& S = d->sdoms[s]; DSdom& D = sd[s]; std::memset(&D, 0, sizeof D);
@@ -523,7 +525,7 @@ int mcb_upload_domain(mcb_ctx* c, const mcb_domain_desc* d) {
             for (int k = 0; k < 3; ++k) if (pl.normal[k] != (k == b ? 1.0 : 0.0)) D.aabb = 0;
         }
         for (int b = 0; b < 3; ++b) { D.offl[b] = d->planes[S.plane_begin + b].offset; D.offh[b] = D.is_box ? d->planes[S.plane_begin + b + 3].offset : 0.0; }
-        if (S.accum >= 3) any_nd = true;
+        if (S.accum >= 3) any_nd = std::max(any_nd, (S.shape[0] >= 64 || S.shape[1] >= 64 || S.shape[2] >= 64) ? 2 : 1);
         const long long sp = S.shape[0] * S.shape[1] * S.shape[2];
         if (S.accum < -2 || S.accum > 4 || sp < 0) { c->err = "bad accum flag / shape"; return MCB_EINVAL; }
         if (sp == 0) D.col_offset = -1;                                                                    // field.cpp:34

@@ -322,13 +322,18 @@ __device__ __forceinline__ uint32_t collide(const StepParams& P, const Tables& T
 
 // ------------------------------------------------------------------------------- k_step
 // NCOMP: payload rows per deposit (1: Temp/CumTemp dt ; 3: Flux/CumFlux dpos ; 4: Multi dt,dpos)
-// TM   : MCB_TM_WARP / MCB_TM_BLOCK / MCB_TM_GLOBAL ; ND: some subdomain has a 2-D/3-D tally grid
+// TM   : MCB_TM_WARP / MCB_TM_BLOCK / MCB_TM_GLOBAL
+// NDM  : 0 only 1-D / single-cell tally grids; 1 some subdomain has a 2-D/3-D grid; 2 same, and the grid is fine enough
+//        (>= 64 cells along an axis) for the warp-cooperative N-D walk to pay for its registers
 // Dynamic shared memory: [mbarrier 16 B][material blob][geometry blob][histogram(s)]
 #ifndef MCB_BLOCK_MAX
 #define MCB_BLOCK_MAX 768
 #endif
-template <int NCOMP, int TM, bool ND, bool EMIT>
-__global__ void __launch_bounds__(MCB_BLOCK_MAX, 1) k_step(const StepParams P) {
+#ifndef MCB_BLOCK_MAX_ND
+#define MCB_BLOCK_MAX_ND 512      // the N-D walk keeps two crossing iterators live: give it 128 registers
+#endif
+template <int NCOMP, int TM, int NDM, bool EMIT>
+__global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : MCB_BLOCK_MAX, 1) k_step(const StepParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
     unsigned char* s_mat = smem + P.so_mat;
@@ -421,7 +426,7 @@ __global__ void __launch_bounds__(MCB_BLOCK_MAX, 1) k_step(const StepParams P) {
                 else if (NCOMP == 4) { amt[0] = sg_ * (sg.d * T.inv_vel[ph.wp]); amt[1 % NCOMP] = sg_ * (sg.ex - sg.bx); amt[2 % NCOMP] = sg_ * (sg.ey - sg.by); amt[3 % NCOMP] = sg_ * (sg.ez - sg.bz); }
                 else { amt[0] = sg_ * (sg.ex - sg.bx); amt[1 % NCOMP] = sg_ * (sg.ey - sg.by); amt[2 % NCOMP] = sg_ * (sg.ez - sg.bz); }
                 const int rbase = cum ? NCOMP * (int)(((long long)sg.nscat_before + P.cum_step - 1) / P.cum_step) : 0;
-                tally_segments<NCOMP, TM, ND, true>(T.sdom[ph.sdom], T.hist, P.rows, P.cols, rbase, sg.ok, sg.bx, sg.by, sg.bz, sg.ex, sg.ey, sg.ez, amt, lane);
+                tally_segments<NCOMP, TM, (NDM > 0), true, (NDM == 2)>(T.sdom[ph.sdom], T.hist, P.rows, P.cols, rbase, sg.ok, sg.bx, sg.by, sg.bz, sg.ex, sg.ey, sg.ez, amt, lane);
             }
             if (sg.ok) my_esc += collide(P, T, ph, sg);
             if (__all_sync(0xFFFFFFFFu, !ph.active && (!EMIT || exhausted || !valid || !P.refill))) break;

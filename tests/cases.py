@@ -30,6 +30,11 @@ def bulk(L=1e-6, div=(10, 0, 0)):
     return orc.Domain.create("bulk", [L, L, L], list(div), 1e6 * L)
 
 
+def bulk64(L=1e-6):
+    """Fine 3-D grid (>= 64 cells along x): takes the warp-cooperative N-D walk of the CUDA kernel."""
+    return orc.Domain.create("bulk", [L, L, L], [64, 6, 5], 1e6 * L)
+
+
 def film(L=1e-6, t=100e-9, ncell=20):
     return orc.Domain.create("film", [L, t, L], [0, ncell, 0], 1e6 * L)
 
@@ -75,7 +80,7 @@ def prism5(div=0):
 
 
 NONBOX = {"hex": hexd, "pyr": pyr, "triprism": triprism, "tet": tet, "prism5": prism5}
-DOMAINS = {"slab": slab, "wire": wire, "skew": skew, "bulk": bulk, "film": film, "jct": jct, "tee": tee, "tube": tube}
+DOMAINS = {"bulk64": bulk64, "slab": slab, "wire": wire, "skew": skew, "bulk": bulk, "film": film, "jct": jct, "tee": tee, "tube": tube}
 
 
 def upload(ctx, mat, dom):

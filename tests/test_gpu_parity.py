@@ -56,7 +56,7 @@ def test_cell_index_bit_exact(gpu_ctx, omats, dname):
     assert np.array_equal(gpu_ctx.cell_index(pos, sd), dom.cell_index(pos, sd))
 
 
-@pytest.mark.parametrize("dname,rows", [("film", 4), ("slab", 1), ("wire", 4), ("skew", 3), ("tube", 4), ("bulk", 3)])
+@pytest.mark.parametrize("dname,rows", [("film", 4), ("slab", 1), ("wire", 4), ("skew", 3), ("tube", 4), ("bulk", 3), ("bulk64", 4)])
 def test_accumulate_matches_oracle(gpu_ctx, omats, dname, rows):
     """Field::accumulate (field.cpp:92-220): 1-D shares and the N-D crossing walk."""
     dom = cases.DOMAINS[dname]()
@@ -110,7 +110,8 @@ def test_trace_state_parity(gpu_ctx, omats, mname, dname, pkind, nsteps):
 SOLVE_CASES = [("grey", "slab", "multi", 0), ("grey", "slab", "temp", 0), ("silicon", "film", "multi", 0),
                ("grey", "bulk", "flux", 0), ("silicon", "jct", "multi", 0), ("grey", "tee", "multi", 0),
                ("silicon", "tube", "multi", 0), ("grey", "wire", "multi", 0), ("silicon_small", "skew", "flux", 0),
-               ("grey", "film", "cumtemp", 4), ("silicon", "slab", "cumflux", 3)]
+               ("grey", "film", "cumtemp", 4), ("silicon", "slab", "cumflux", 3), ("grey", "bulk64", "multi", 0),
+               ("silicon", "bulk64", "flux", 0)]
 
 
 @pytest.mark.parametrize("mname,dname,pkind,size", SOLVE_CASES)
@@ -125,7 +126,7 @@ def test_solve_matches_oracle_philox(gpu_ctx, omats, mname, dname, pkind, size):
     assert gst["emitted"] == rst["emitted"] == prob.nemit
     assert gst["steps"] == rst["steps"]
     assert gst["esc"] == rst["esc"]
-    if dname in ("slab", "wire", "skew", "bulk", "film"):
+    if dname in ("slab", "wire", "skew", "bulk", "film", "bulk64"):
         assert gst["esc"] == 0                     # KA5: no escapes on single-box domains
     scale = np.abs(ref).max(axis=1, keepdims=True)
     assert (np.abs(got - ref) <= 1e-9 * scale).all()
