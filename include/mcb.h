@@ -192,10 +192,12 @@ typedef struct mcb_stats {
 
 /* Tunables of the device schedule (not part of the physics). 0 = library default. */
 typedef struct mcb_options {
-    int64_t slots;             /* resident particle slots (SoA length)                */
+    int64_t slots;             /* resident particle slots (SoA length); default 32 tiles */
+                               /* per thread of the persistent grid                      */
     int32_t steps_per_launch;  /* S: loop-body trips per state load/store             */
     int32_t block;             /* threads per CTA                                     */
-    int32_t ctas_per_sm;       /* persistent grid = ctas_per_sm * SM count            */
+    int32_t ctas_per_sm;       /* persistent grid = ctas_per_sm * SM count (default 1:   */
+                               /* the tables + histograms fill one CTA's shared memory)  */
     int32_t tally_mode;        /* 0 auto, 1 warp-private smem histograms, 2 global    */
                                /* field (fp64 RED in L2), 3 one smem histogram per CTA */
     int32_t decay_mode;        /* 0: once nothing is left to emit use S >= 16, compact,  */

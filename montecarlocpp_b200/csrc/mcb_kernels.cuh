@@ -1,15 +1,19 @@
 // mcb_kernels.cuh — the CUDA kernels (sm_100a) of the phonon Monte Carlo hot path.
 //
-//   k_step      K1+K2 fused: refill freed slots by emitting the next particle (problem.cpp:386-399),
-//               then S trips of the loop body (problem.cpp:401-435): advect -> tally -> boundary or
-//               intrinsic scattering.  State streams HBM -> registers -> HBM once per launch.
-//               Material tables are staged into shared memory with a TMA bulk copy
-//               (cp.async.bulk + mbarrier); tallies go to a per-CTA shared-memory histogram
-//               (flushed once per CTA) or, for big fields, straight to L2 with fp64 RED.
-//   k_compact   K3: stream-compacts the active slots of the tail (no reference analogue; replaces the
-//               `break`s at problem.cpp:411,425,434).
+//   k_emit      K1 (dense): the next particles are emitted into the free slots listed by k_step (problem.cpp:386-399),
+//               one thread per particle, full warps; k_emit_commit advances the particle counter; k_free_init seeds the list.
+//   k_step      K2: S trips of the loop body (problem.cpp:401-435) per resident slot: advect -> tally -> boundary or
+//               intrinsic scattering.  State streams HBM -> registers -> HBM once per launch.  Material + geometry tables
+//               are staged into shared memory with a TMA bulk copy (cp.async.bulk + mbarrier); tallies go to warp-private
+//               shared-memory histograms (flushed once per CTA), one histogram per CTA, or straight to L2 with fp64 RED.
+//               Template modes: payload rows, tally destination, N-D walk (none / serial / warp-cooperative), and EMIT
+//               (emission inside the kernel: used by mcb_trace and as an option).
+//   k_compact   K3: stream-compacts the active slots of the decay phase (no reference analogue; replaces the `break`s at
+//               problem.cpp:411,425,434).
 //   k_finalize  K4: postProc, / cellVol, * power_ (problem.cpp:439-444).
-//   k_cell_index / k_accumulate / k_gather_trace: diagnostics behind mcb_cell_index / mcb_accumulate / mcb_trace.
+//   k_traj      TrajProblem::solve (problem.cpp:226-299) for one particle.
+//   k_cell_index / k_accumulate / k_gather_trace / k_philox: diagnostics behind mcb_cell_index / mcb_accumulate /
+//               mcb_trace / mcb_philox_words.
 #pragma once
 #include "mcb_device.cuh"
 #include "../../include/mcb.h"
