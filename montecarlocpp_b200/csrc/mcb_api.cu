@@ -89,6 +89,9 @@ struct mcb_ctx {
     mcb_options opt{};
     // material
     bool has_mat = false; long nw = 0, np = 0; double energy_sum = 0, flux_sum = 0;
+    double inv_vel_fx = 0;       // slowness 1/vel that all but 0.1 % of the drawn modes stay below: sets the fixed-point
+                                 // range of the dt payload (slower flights take the exact fp64 path)
+    double flight_max = 0;       // largest possible flight inside one subdomain (sum of its edge-vector lengths)
     MaterialView mv{}; DevBuf<unsigned char> mat_blob;
     AliasTables flux_alias, scat_alias;
     DevBuf<double> f_wprob, f_pprob; DevBuf<int32_t> f_walias, f_palias;
@@ -227,6 +230,27 @@ void fill_params(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, StepPa
     P->so_hot = P->so_geo + c->gv.off_hot; P->so_cold = P->so_geo + c->gv.off_cold; P->so_sdom = P->so_geo + c->gv.off_sdom; P->so_pairs = P->so_geo + c->gv.off_pairs;
 }
 
+// Fixed-point scale of the shared-memory tally (mcb_device.cuh: deposit).  Payload component k of a flight is accepted
+// up to fx_max = 2^E >= 2 * flight_max (* the 99.9 % slowness for the dt row; anything larger takes the exact fp64
+// path).  A histogram is flushed at least every `trips` loop trips (k_step flushes between tiles and the schedule keeps
+// steps_per_launch <= trips), so an entry receives at most `bound` deposits between flushes, and q = v * 2^(QB-1-E) with
+// 2^QB * bound <= 2^62 can never overflow 64 bits (QB <= 50 keeps q inside the DFMA rounding trick's range):
+// 32 lanes x 128 trips -> QB = 49.  Only the warp histograms are fixed point.
+#define MCB_FX_FLUSH_TRIPS 128
+void set_fixed_point(mcb_ctx* c, const mcb_problem_desc* prob, StepParams* P) {
+    const double bound = 2.0 * 32.0 * (double)MCB_FX_FLUSH_TRIPS;                          // <= 2 deposits per cell per flight (cooperative N-D pieces)
+    int bits = 0; std::frexp(bound, &bits);                                                // bound <= 2^bits
+    const int QB = std::min(50, 62 - bits);
+    for (int k = 0; k < 4; ++k) {
+        const bool is_dt = (prob->kind == MCB_PROB_TEMP || prob->kind == MCB_PROB_CUMTEMP || prob->kind == MCB_PROB_MULTI) && k == 0;
+        const double amax = c->flight_max * (is_dt ? c->inv_vel_fx : 1.0);
+        int e = 0; std::frexp(amax > 0.0 ? amax : 1.0, &e);                                // amax < 2^e
+        const int E = e + 1;
+        P->fx_max[k] = std::ldexp(1.0, E); P->fx_scale[k] = std::ldexp(1.0, QB - 1 - E); P->fx_inv[k] = std::ldexp(1.0, E + 1 - QB);
+    }
+    P->fx_flush_trips = MCB_FX_FLUSH_TRIPS;
+}
+
 int upload_cdf(mcb_ctx* c, const mcb_problem_desc* prob) {
     std::vector<long long> cdf(c->nemitter);
     long long acc = 0;
@@ -256,6 +280,7 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
     StepParams P; fill_params(c, prob, seed, &P);
     P.field = raw_field_dev; P.tally_smem = plan.tm; P.hist_copies = plan.copies; P.do_tally = 1; P.refill = 1;
     P.steps_per_launch = plan.S; P.n_end = (unsigned long long)n_end;
+    set_fixed_point(c, prob, &P);
 
     Counters init{}; init.next = (unsigned long long)n_begin;
     CUDA_TRY(c, cudaMemcpyAsync(c->ctr.p, &init, sizeof init, cudaMemcpyHostToDevice, c->stream));
@@ -286,6 +311,8 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
     unsigned long long steady_steps = 0, steady_stores = 0, prev_steps = 0, prev_stores = 0;
     if (total > 0) for (long long it = 0;; ++it) {
         const int slot = (int)(it & 1);
+        // fixed-point histograms are flushed between tiles: keep a tile's loop trips within the flush interval
+        if (MCB_TALLY_FX && plan.tm == MCB_TM_WARP) S_cur = std::min(S_cur, MCB_FX_FLUSH_TRIPS);
         P.st = soa_of(c, cur, c->slots_alloc); P.nslots = nslots; P.steps_per_launch = S_cur;
         if (dense && !host_all_emitted) {
             // K1: fill the free slots listed by the previous k_step (all of them before the first), with full warps
@@ -462,6 +489,16 @@ int mcb_upload_material(mcb_ctx* c, const mcb_material_desc* m) {
             pprob[dst] = c->scat_alias.pprob[dst]; palias[dst] = (uint8_t)c->scat_alias.palias[dst];
         }
     }
+    {   // 99.9 % quantile of 1/vel over the modes as they are drawn (emission ~ fluxPdf, scattering ~ scatPdf)
+        std::vector<std::pair<double, double>> sw((size_t)n);
+        double fs = 0.0, ss = 0.0;
+        for (long i = 0; i < n; ++i) { fs += m->flux_pdf[i]; ss += m->scat_pdf[i]; }
+        for (long i = 0; i < n; ++i)
+            sw[(size_t)i] = {1.0 / m->vel[i], (fs > 0.0 ? m->flux_pdf[i] / fs : 0.0) + (ss > 0.0 ? m->scat_pdf[i] / ss : 0.0)};
+        std::sort(sw.begin(), sw.end(), [](const std::pair<double, double>& a, const std::pair<double, double>& b) { return a.first > b.first; });
+        double tail = 0.0; c->inv_vel_fx = sw.back().first;
+        for (const auto& e : sw) { tail += e.second; if (tail > 2e-3) { c->inv_vel_fx = e.first; break; } }
+    }
     CUDA_TRY(c, c->mat_blob.alloc(v.bytes));
     CUDA_TRY(c, cudaMemcpy(c->mat_blob.p, blob.data(), v.bytes, cudaMemcpyHostToDevice));
     CUDA_TRY(c, c->f_wprob.alloc(nw)); CUDA_TRY(c, c->f_walias.alloc(nw));
@@ -505,7 +542,7 @@ int mcb_upload_domain(mcb_ctx* c, const mcb_domain_desc* d) {
         for (int k = 0; k < 3; ++k) q.t[k] = p.peri_transl[k];
     }
     for (int i = 0; i < d->npair; ++i) if (d->pairs[i] < 0 || d->pairs[i] >= d->nplane) { c->err = "pair id out of range"; return MCB_EINVAL; }
-    std::vector<DSdom> sd(d->nsdom); std::vector<double> cell_vol; int any_nd = 0;
+    std::vector<DSdom> sd(d->nsdom); std::vector<double> cell_vol; int any_nd = 0; double flight_max = 0.0;
     long long cols = 0;
     for (int s = 0; s < d->nsdom; ++s) {
         const mcb_sdom_desc& S = d->sdoms[s]; DSdom& D = sd[s]; std::memset(&D, 0, sizeof D);
@@ -525,6 +562,13 @@ int mcb_upload_domain(mcb_ctx* c, const mcb_domain_desc* d) {
             for (int k = 0; k < 3; ++k) if (pl.normal[k] != (k == b ? 1.0 : 0.0)) D.aabb = 0;
         }
         for (int b = 0; b < 3; ++b) { D.offl[b] = d->planes[S.plane_begin + b].offset; D.offh[b] = D.is_box ? d->planes[S.plane_begin + b + 3].offset : 0.0; }
+        {   // a flight stays inside its (convex) subdomain: its length is bounded by the sum of the edge-vector lengths
+            double diam = 0.0;
+            const int ncol = S.nbase > 0 ? std::min<int>(S.nbase, MCB_MAX_BASE) : 3;
+            const double* cols3 = S.nbase > 0 ? S.base : S.mat;
+            for (int k = 0; k < ncol; ++k) diam += std::sqrt(cols3[3 * k] * cols3[3 * k] + cols3[3 * k + 1] * cols3[3 * k + 1] + cols3[3 * k + 2] * cols3[3 * k + 2]);
+            flight_max = std::max(flight_max, diam + 4.0 * std::fabs(S.eps));
+        }
         if (S.accum >= 3) any_nd = std::max(any_nd, (S.shape[0] >= 64 || S.shape[1] >= 64 || S.shape[2] >= 64) ? 2 : 1);
         const long long sp = S.shape[0] * S.shape[1] * S.shape[2];
         if (S.accum < -2 || S.accum > 4 || sp < 0) { c->err = "bad accum flag / shape"; return MCB_EINVAL; }
@@ -608,7 +652,7 @@ int mcb_upload_domain(mcb_ctx* c, const mcb_domain_desc* d) {
     CUDA_TRY(c, cudaMemcpy(c->emitters.p, em.data(), em.size() * sizeof(DEmitter), cudaMemcpyHostToDevice));
     CUDA_TRY(c, c->cell_vol.alloc(cell_vol.size()));
     if (!cell_vol.empty()) CUDA_TRY(c, cudaMemcpy(c->cell_vol.p, cell_vol.data(), cell_vol.size() * 8, cudaMemcpyHostToDevice));
-    c->gv = v; c->h_sdom = sd; c->nemitter = d->nemitter; c->cols = cols; c->any_nd = any_nd; c->has_dom = true;
+    c->gv = v; c->h_sdom = sd; c->nemitter = d->nemitter; c->cols = cols; c->any_nd = any_nd; c->flight_max = flight_max; c->has_dom = true;
     return MCB_OK;
 }
 

@@ -324,6 +324,26 @@ __device__ __forceinline__ uint32_t collide(const StepParams& P, const Tables& T
     return esc;
 }
 
+// Flush `ncopy` fixed-point histogram copies (two 32-bit planes each, mcb_device.cuh: deposit) into the global fp64
+// field: the copies are summed as 64-bit integers (exact, order-free), converted once, transposed from the histograms'
+// row-major layout to the field's column-major one, and re-armed with zeros.  `tid`/`nthr` = the cooperating threads
+// (a warp for its private copies in the middle of a launch, the CTA at the end).
+template <int NCOMP>
+__device__ __forceinline__ void flush_fixed_point(uint32_t* words, unsigned ncopy, const StepParams& P, unsigned tid, unsigned nthr) {
+    for (long long i = tid; i < P.field_len; i += nthr) {                         // i = r*cols + c in the histograms
+        long long acc = 0;
+        for (unsigned w = 0; w < ncopy; ++w) {
+            uint32_t* h = words + 2ll * w * P.field_len;
+            acc += (long long)(((unsigned long long)h[P.field_len + i] << 32) | (unsigned long long)h[i]);
+            h[i] = 0u; h[P.field_len + i] = 0u;
+        }
+        if (acc != 0) {
+            const long long r = i / P.cols, c = i - r * P.cols;
+            atomicAdd(P.field + c * P.rows + r, (double)acc * P.fx_inv[(int)(r % NCOMP)]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------- k_step
 // NCOMP: payload rows per deposit (1: Temp/CumTemp dt ; 3: Flux/CumFlux dpos ; 4: Multi dt,dpos)
 // TM   : MCB_TM_WARP / MCB_TM_BLOCK / MCB_TM_GLOBAL
@@ -375,9 +395,14 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : MCB_BLOCK_MAX, 1
     T.hist = TM == MCB_TM_WARP ? s_hist + ((long long)warp * P.hist_copies + (lane & (unsigned)(P.hist_copies - 1))) * P.field_len
                                : (TM == MCB_TM_BLOCK ? s_hist : P.field);
     const bool cum = P.kind == MCB_PROB_CUMTEMP || P.kind == MCB_PROB_CUMFLUX;
+    constexpr bool FX = MCB_TALLY_FX && TM == MCB_TM_WARP;        // fixed-point warp histograms (mcb_device.cuh: deposit)
+    const uint32_t hi_off = 4u * (uint32_t)P.field_len;            // low-word plane, then high-word plane
 
     unsigned long long my_steps = 0, my_esc = 0, my_emitted = 0, my_live = 0, my_stores = 0;
     bool exhausted = false;
+    // fixed-point histograms are flushed by the CTA between tiles at least every fx_flush_trips loop trips (the host keeps
+    // steps_per_launch below that), which bounds the number of deposits an entry can receive (set_fixed_point, mcb_api.cu)
+    int since_flush = 0;
     // dense emission (EMIT == false): free slots are only LISTED here; k_emit fills them between launches with full
     // warps (in-kernel emission of a few dead lanes per warp runs the long emission path at ~5 % lane efficiency)
     const bool list_free = !EMIT && P.free_list != nullptr && P.ctr->next < P.n_end;
@@ -401,6 +426,16 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : MCB_BLOCK_MAX, 1
             }
         }
         bool dirty = false;
+        if (FX && P.do_tally) {
+            // between tiles (CTA-uniform): flush before an entry could have received more than fx_flush_trips rounds of deposits
+            if (since_flush + P.steps_per_launch > P.fx_flush_trips) {
+                __syncthreads();
+                flush_fixed_point<NCOMP>(reinterpret_cast<uint32_t*>(s_hist), TM == MCB_TM_WARP ? nwarps * (unsigned)P.hist_copies : 1u, P, threadIdx.x, blockDim.x);
+                __syncthreads();
+                since_flush = 0;
+            }
+            since_flush += P.steps_per_launch;
+        }
         for (int s = 0; s < P.steps_per_launch; ++s) {
             // refill: a freed slot takes the next particle id (warp-aggregated ticket)
             const bool want = EMIT && valid && !ph.active && !exhausted && (P.refill || s == 0);
@@ -429,8 +464,17 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : MCB_BLOCK_MAX, 1
                 if (NCOMP == 1) amt[0] = sg_ * (sg.d * T.inv_vel[ph.wp]);
                 else if (NCOMP == 4) { amt[0] = sg_ * (sg.d * T.inv_vel[ph.wp]); amt[1 % NCOMP] = sg_ * (sg.ex - sg.bx); amt[2 % NCOMP] = sg_ * (sg.ey - sg.by); amt[3 % NCOMP] = sg_ * (sg.ez - sg.bz); }
                 else { amt[0] = sg_ * (sg.ex - sg.bx); amt[1 % NCOMP] = sg_ * (sg.ey - sg.by); amt[2 % NCOMP] = sg_ * (sg.ez - sg.bz); }
+                FxArgs fx{hi_off, false, &P};
+                if (FX) {
+                    // fixed-point histograms: scale by the launch's power of two (exact); a payload beyond the chosen range
+                    // (rare: a long flight of a very slow mode) is deposited exactly through the global fp64 path instead
+                    bool fits = true;
+#pragma unroll
+                    for (int k = 0; k < NCOMP; ++k) { fits = fits && fabs(amt[k]) <= P.fx_max[k]; amt[k] *= P.fx_scale[k]; }
+                    fx.slow = !fits;
+                }
                 const int rbase = cum ? NCOMP * (int)(((long long)sg.nscat_before + P.cum_step - 1) / P.cum_step) : 0;
-                tally_segments<NCOMP, TM, (NDM > 0), true, (NDM == 2)>(T.sdom[ph.sdom], T.hist, P.rows, P.cols, rbase, sg.ok, sg.bx, sg.by, sg.bz, sg.ex, sg.ey, sg.ez, amt, lane);
+                tally_segments<NCOMP, TM, (NDM > 0), true, (NDM == 2)>(T.sdom[ph.sdom], T.hist, P.rows, P.cols, rbase, sg.ok, sg.bx, sg.by, sg.bz, sg.ex, sg.ey, sg.ez, amt, lane, fx);
             }
             if (sg.ok) my_esc += collide(P, T, ph, sg);
             if (__all_sync(0xFFFFFFFFu, !ph.active && (!EMIT || exhausted || !valid || !P.refill))) break;
@@ -486,7 +530,8 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : MCB_BLOCK_MAX, 1
     //     one fp64 RED per non-zero entry
     if (TM != MCB_TM_GLOBAL && P.do_tally) {
         const unsigned ncopy = TM == MCB_TM_WARP ? nwarps * (unsigned)P.hist_copies : 1u;
-        for (long long i = threadIdx.x; i < P.field_len; i += blockDim.x) {        // i = r*cols + c in the histograms
+        if (FX) flush_fixed_point<NCOMP>(reinterpret_cast<uint32_t*>(s_hist), ncopy, P, threadIdx.x, blockDim.x);
+        else for (long long i = threadIdx.x; i < P.field_len; i += blockDim.x) {   // i = r*cols + c in the histograms
             double v = 0.0;
             for (unsigned w = 0; w < ncopy; ++w) v += s_hist[(long long)w * P.field_len + i];
             const long long r = i / P.cols, c = i - r * P.cols;

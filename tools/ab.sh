@@ -12,9 +12,14 @@ import torch
 d = tempfile.mkdtemp()
 mat = hostapi.Material(*materials.write_silicon(d, nw=1000))
 ctx = capi.Context(0); ctx.upload_material(mat.desc)
-for wl in ("slab", "film"):
+import os
+for wl in os.environ.get("AB_WL", "slab film wire").split():
     if wl == "slab":
         dom = hostapi.Domain("slab", [100e-9] * 3, [100, 0, 0], 1.0); prob = hostapi.FieldProblem(mat, dom, "multi", 10_000_000, 1000)
+    elif wl == "wire":
+        dom = hostapi.Domain("wire", [1e-6, 1e-7, 1e-7], [0, 32, 32], 1.0); prob = hostapi.FieldProblem(mat, dom, "multi", 4_000_000, 100)
+    elif wl == "bulk":
+        dom = hostapi.Domain("bulk", [1e-6] * 3, [128, 128, 128], 1.0); prob = hostapi.FieldProblem(mat, dom, "multi", 4_000_000, 100)
     else:
         dom = hostapi.Domain("film", [1e-6, 1e-7, 1e-6], [0, 20, 0], 1.0); prob = hostapi.FieldProblem(mat, dom, "multi", 4_000_000, 100)
     ctx.upload_domain(dom.desc)
