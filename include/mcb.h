@@ -205,7 +205,8 @@ typedef struct mcb_options {
                                /* 1: keep steps_per_launch throughout (compaction only)  */
     int32_t emit_mode;         /* 0: dense emission kernel between step launches;        */
                                /* 1: emit inside the step kernel (slot refilled at once) */
-    int32_t reserved_;
+    int32_t compact_pct;       /* decay phase: compact the survivors when fewer than this */
+                               /* percentage of the visited slots is live (0 = default)  */
 } mcb_options;
 
 typedef struct mcb_ctx mcb_ctx;

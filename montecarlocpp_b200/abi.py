@@ -84,7 +84,7 @@ class Stats(C.Structure):
 class Options(C.Structure):
     _fields_ = [("slots", C.c_int64), ("steps_per_launch", C.c_int32), ("block", C.c_int32),
                 ("ctas_per_sm", C.c_int32), ("tally_mode", C.c_int32), ("decay_mode", C.c_int32),
-                ("emit_mode", C.c_int32), ("reserved_", C.c_int32)]
+                ("emit_mode", C.c_int32), ("compact_pct", C.c_int32)]
 
 
 class TraceOut(C.Structure):

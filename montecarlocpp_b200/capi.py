@@ -11,7 +11,7 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmcb.so")
+LIB_PATH = os.environ.get("MCB_LIBMCB") or os.path.join(_HERE, "libmcb.so")     # MCB_LIBMCB: A/B a differently built library
 
 SYMBOLS = [
     "mcb_create", "mcb_destroy", "mcb_last_error", "mcb_abi_version", "mcb_set_options", "mcb_get_options",

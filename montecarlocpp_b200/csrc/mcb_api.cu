@@ -175,6 +175,7 @@ cudaError_t launch_step(const StepParams& P, int tm, int nd, int grid, int block
 }
 
 int ensure_slots(mcb_ctx* c, long long slots) {
+    slots = (slots + 31) / 32 * 32;          // whole warps
     if (slots <= c->slots_alloc) return MCB_OK;
     for (int w = 0; w < 2; ++w) {
         CUDA_TRY(c, c->state[w].alloc((size_t)slots * 7));
@@ -188,7 +189,7 @@ struct RunPlan { long long slots; int S, block, grid; int tm, copies; size_t sme
 
 int plan_run(mcb_ctx* c, const mcb_problem_desc* prob, long long nparticles, RunPlan* r) {
     const mcb_options& o = c->opt;
-    const int block_max = c->any_nd == 2 ? MCB_BLOCK_MAX_ND : MCB_BLOCK_MAX;  // the cooperative N-D kernels are built for fewer, fatter threads
+    const int block_max = c->any_nd == 2 ? MCB_BLOCK_MAX_ND : (c->any_nd == 1 ? MCB_BLOCK_MAX_ND1 : MCB_BLOCK_MAX);  // the N-D kernels are built for fewer, fatter threads
     r->block = o.block > 0 ? std::min(o.block, block_max) : block_max;
     if (r->block % 32 != 0 || o.block > MCB_BLOCK_MAX) { c->err = "block must be a multiple of 32, <= " + std::to_string(MCB_BLOCK_MAX); return MCB_EINVAL; }
     const int per_sm = o.ctas_per_sm > 0 ? o.ctas_per_sm : 1;
@@ -237,6 +238,9 @@ void fill_params(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, StepPa
 // 2^QB * bound <= 2^62 can never overflow 64 bits (QB <= 50 keeps q inside the DFMA rounding trick's range):
 // 32 lanes x 128 trips -> QB = 49.  Only the warp histograms are fixed point.
 #define MCB_FX_FLUSH_TRIPS 128
+#ifndef MCB_COMPACT_PCT
+#define MCB_COMPACT_PCT 90
+#endif
 void set_fixed_point(mcb_ctx* c, const mcb_problem_desc* prob, StepParams* P) {
     const double bound = 2.0 * 32.0 * (double)MCB_FX_FLUSH_TRIPS;                          // <= 2 deposits per cell per flight (cooperative N-D pieces)
     int bits = 0; std::frexp(bound, &bits);                                                // bound <= 2^bits
@@ -299,6 +303,7 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
     // dense emission (default): k_step only lists free slots, k_emit fills them between launches; emit_mode = 1
     // selects emission inside k_step instead
     const bool dense = c->opt.emit_mode != 1;
+    const long long compact_pct = c->opt.compact_pct > 0 ? c->opt.compact_pct : MCB_COMPACT_PCT;
     bool host_all_emitted = false;
     if (dense) {
         CUDA_TRY(c, c->free_list.alloc((size_t)c->slots_alloc));
@@ -347,7 +352,7 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
             cudaEventElapsedTime(&ms, c->evA[slot], c->evB[slot]); step_ms_total += ms;
             break;
         }
-        if (all_emitted && (long long)live * 2 < nslots && nslots > tail_slots) {
+        if (all_emitted && (long long)live * 100 < nslots * compact_pct && nslots > tail_slots) {
             // tail: compact the survivors so later launches stream only live state.  `live` is one launch old,
             // i.e. an upper bound (nothing is emitted any more); unused destination slots stay inactive.
             const int other = cur ^ 1;
@@ -440,7 +445,7 @@ void mcb_destroy(mcb_ctx* c) {
 
 int mcb_set_options(mcb_ctx* c, const mcb_options* o) {
     if (!c || !o) return MCB_EINVAL;
-    if (o->slots < 0 || o->steps_per_launch < 0 || o->block < 0 || o->ctas_per_sm < 0 || o->tally_mode < 0 || o->tally_mode > 3 || o->decay_mode < 0 || o->decay_mode > 1 || o->emit_mode < 0 || o->emit_mode > 1) {
+    if (o->slots < 0 || o->steps_per_launch < 0 || o->block < 0 || o->ctas_per_sm < 0 || o->tally_mode < 0 || o->tally_mode > 3 || o->decay_mode < 0 || o->decay_mode > 1 || o->emit_mode < 0 || o->emit_mode > 1 || o->compact_pct < 0 || o->compact_pct > 100) {
         c->err = "negative / unknown option"; return MCB_EINVAL;
     }
     c->opt = *o;

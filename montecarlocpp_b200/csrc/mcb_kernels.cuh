@@ -55,10 +55,30 @@ __device__ __forceinline__ void st_stream(unsigned long long* p, unsigned long l
 }
 
 // ------------------------------------------------------------------------------ particle
+// The integer state stays PACKED in registers exactly as it lies in HBM (meta = mlo | nscat << 32, pidstep = ps): three
+// registers instead of nine, no pack / unpack at the load and the store; fields are extracted where they are used.
 struct Particle {
     double px, py, pz, dx, dy, dz, sn;
-    uint32_t wp, sign, active, killed, sdom, nscat, step;
-    unsigned long long pid;
+    uint32_t mlo;                 // wp:20 | sign:1 | active:1 | killed:1 | sdom:9   (low word of meta)
+    uint32_t nscat;               // high word of meta
+    unsigned long long ps;        // pid:40 | step:24
+    __device__ __forceinline__ uint32_t wp() const { return mlo & 0xFFFFFu; }
+    __device__ __forceinline__ bool sign() const { return (mlo >> 20) & 1u; }
+    __device__ __forceinline__ bool active() const { return (mlo >> 21) & 1u; }
+    __device__ __forceinline__ bool killed() const { return (mlo >> 22) & 1u; }
+    __device__ __forceinline__ uint32_t sdom() const { return mlo >> 23; }
+    __device__ __forceinline__ uint32_t step() const { return (uint32_t)ps & 0xFFFFFFu; }
+    __device__ __forceinline__ unsigned long long pid() const { return ps >> 24; }
+    __device__ __forceinline__ uint32_t pid_lo() const { return (uint32_t)(ps >> 24); }
+    __device__ __forceinline__ uint32_t pid_hi() const { return (uint32_t)(ps >> 56); }
+    __device__ __forceinline__ void set_wp(uint32_t v) { mlo = (mlo & ~0xFFFFFu) | v; }
+    __device__ __forceinline__ void set_sdom(uint32_t v) { mlo = (mlo & 0x7FFFFFu) | (v << 23); }
+    __device__ __forceinline__ void stop() { mlo &= ~(1u << 21); }                       // alive but finished (or never started)
+    __device__ __forceinline__ void kill() { mlo = (mlo | (1u << 22)) & ~(1u << 21); }  // Phonon::kill phonon.cpp:47-50
+    __device__ __forceinline__ void init(uint32_t wp_, bool sign_, bool active_, uint32_t sdom_, unsigned long long pid_) {
+        mlo = wp_ | ((uint32_t)sign_ << 20) | ((uint32_t)active_ << 21) | (sdom_ << 23); nscat = 0; ps = pid_ << 24;
+    }
+    __device__ __forceinline__ unsigned long long meta() const { return (unsigned long long)mlo | ((unsigned long long)nscat << 32); }
 };
 
 // Material::Dist::drawProp (material.cpp:71-75) on the two-level Walker tables; entry (w,p) at w*np+p
@@ -131,7 +151,7 @@ __device__ __forceinline__ void emit_from(const DEmitter& E, Rng& g, Particle& p
     }
     normalize3(dx, dy, dz);                                  // Phonon ctor phonon.cpp:33-37
     ph.px = px; ph.py = py; ph.pz = pz; ph.dx = dx; ph.dy = dy; ph.dz = dz;
-    ph.sign = sign; ph.killed = 0; ph.sdom = (uint32_t)E.sdom; ph.nscat = 0; ph.step = 0;
+    ph.init(0u, sign != 0u, false, (uint32_t)E.sdom, 0ull);           // the caller sets wp, active and the particle id
 }
 
 // problem.cpp:386-399 for particle `pid`: pick emitter, drawFluxProp, Emitter::emit, drawScatNext
@@ -143,7 +163,7 @@ __device__ __noinline__ void emit_particle(const StepParams& P, const Tables& T,
     Rng g; g.begin(P.seed, pid, 0u);
     const uint32_t wp = draw_prop(g, T, P.f_wprob, P.f_walias, P.f_pprob, P.f_palias);
     emit_from(E, g, ph);
-    ph.wp = wp; ph.active = P.maxloop > 0 ? 1u : 0u; ph.pid = pid;
+    ph.init(wp, ph.sign(), P.maxloop > 0, ph.sdom(), pid);
     ph.sn = draw_scat_next(g, T.lambda[wp]);
 }
 
@@ -181,7 +201,7 @@ struct Segment {                  // what one advect produced
 
 // First half of a loop trip (problem.cpp:403-412): Subdomain::advect + Phonon::move.  Returns escapes (0/1).
 __device__ __forceinline__ uint32_t advect_move(const Tables& T, Particle& ph, Segment& sg) {
-    const DSdom& sd = T.sdom[ph.sdom];
+    const DSdom& sd = T.sdom[ph.sdom()];
     // Subdomain::advect subdomain.cpp:161-192
     double d = ph.sn; int hit = -1;
     if (sd.aabb) {
@@ -240,9 +260,9 @@ __device__ __forceinline__ uint32_t advect_move(const Tables& T, Particle& ph, S
     sg.ex = sg.bx + ph.dx * d; sg.ey = sg.by + ph.dy * d; sg.ez = sg.bz + ph.dz * d;
     ph.px = sg.ex; ph.py = sg.ey; ph.pz = sg.ez;
     sg.d = d; sg.hit = hit; sg.nscat_before = ph.nscat;
-    ph.step++;
+    ph.ps++;                                                                   // step is the low field of ps
     if (d < -sd.eps || !is_inside(T, sd, sg.ex, sg.ey, sg.ez)) {              // subdomain.cpp:182-189
-        ph.killed = 1; ph.active = 0; sg.ok = false; return 1u;               // problem.cpp:408-412
+        ph.kill(); sg.ok = false; return 1u;                                  // problem.cpp:408-412
     }
     sg.ok = true;
     return 0u;
@@ -262,7 +282,7 @@ __device__ __forceinline__ uint32_t collide(const StepParams& P, const Tables& T
             ph.dx -= c2 * h.nx; ph.dy -= c2 * h.ny; ph.dz -= c2 * h.nz;
             renorm_unit(ph.dx, ph.dy, ph.dz);
         } else if (kind == MCB_BDRY_DIFF) {                                    // boundary.cpp:308-312
-            Rng g; g.begin(P.seed, ph.pid, ph.step);
+            Rng g; g.begin(P.seed, ph.pid(), ph.step());
             double ax, ay, az; draw_aniso(g, false, ax, ay, az);
             matvec(cb.m, ax, ay, az, ph.dx, ph.dy, ph.dz);
             renorm_unit(ph.dx, ph.dy, ph.dz);
@@ -274,7 +294,7 @@ __device__ __forceinline__ uint32_t collide(const StepParams& P, const Tables& T
             ph.dx = nx; ph.dy = ny; ph.dz = nz;
             renorm_unit(ph.dx, ph.dy, ph.dz);
             sg.next_plane = T.pairs[cb.pair_begin];
-            ph.sdom = (uint32_t)T.cold[sg.next_plane].sdom;
+            ph.set_sdom((uint32_t)T.cold[sg.next_plane].sdom);
         } else if (kind == MCB_BDRY_INTER) {                                   // boundary.cpp:349-359
             int target = -1;
             if (cb.pair_count == 1) target = T.pairs[cb.pair_begin];
@@ -282,11 +302,11 @@ __device__ __forceinline__ uint32_t collide(const StepParams& P, const Tables& T
                 const int cand = T.pairs[cb.pair_begin + q];
                 if (is_inside(T, T.sdom[T.cold[cand].sdom], sg.ex, sg.ey, sg.ez)) target = cand;
             }
-            if (target < 0) { ph.killed = 1; ph.active = 0; esc = 1; }         // problem.cpp:422-426
-            else ph.sdom = (uint32_t)T.cold[target].sdom;
+            if (target < 0) { ph.kill(); esc = 1; }                            // problem.cpp:422-426
+            else ph.set_sdom((uint32_t)T.cold[target].sdom);
             sg.next_plane = target;
         } else {                                                               // Isot boundary.cpp:455-460
-            ph.killed = 1; ph.active = 0;
+            ph.kill();
         }
     } else {                                                                   // Material::scatter material.cpp:226-231
         // Fast path: the event's seven words (w int, w real, p int, p real, iso mu, iso phi, free path) come from two
@@ -295,8 +315,8 @@ __device__ __forceinline__ uint32_t collide(const StepParams& P, const Tables& T
         bool fast = T.nw > 1 && T.np > 1;
         if (fast) {
             uint32_t a[4], b[4];
-            philox4x32_10((uint32_t)ph.pid, (uint32_t)(ph.pid >> 32), ph.step, 0u, (uint32_t)P.seed, (uint32_t)(P.seed >> 32), a);
-            philox4x32_10((uint32_t)ph.pid, (uint32_t)(ph.pid >> 32), ph.step, 1u, (uint32_t)P.seed, (uint32_t)(P.seed >> 32), b);
+            philox4x32_10(ph.pid_lo(), ph.pid_hi(), ph.step(), 0u, (uint32_t)P.seed, (uint32_t)(P.seed >> 32), a);
+            philox4x32_10(ph.pid_lo(), ph.pid_hi(), ph.step(), 1u, (uint32_t)P.seed, (uint32_t)(P.seed >> 32), b);
             uint32_t r = (uint32_t)(((double)a[0] + 0.5) * T.inv_bucket_w);
             uint32_t q = (uint32_t)(((double)a[2] + 0.5) * T.inv_bucket_p);
             fast = r < (uint32_t)T.nw && q < (uint32_t)T.np;
@@ -309,18 +329,18 @@ __device__ __forceinline__ uint32_t collide(const StepParams& P, const Tables& T
             double sp, cp; sincospi_unit((double)b[1] * (1.0 / 2147483648.0) - 1.0, &sp, &cp);
             const double dist = T.lambda[wp] * neg_log1m_u32(b[2]);
             fast = fast && !(dist < 2.2250738585072014e-308);
-            if (fast) { ph.wp = wp; ph.dx = sth * cp; ph.dy = sth * sp; ph.dz = c; ph.sn = dist; }
+            if (fast) { ph.set_wp(wp); ph.dx = sth * cp; ph.dy = sth * sp; ph.dz = c; ph.sn = dist; }
         }
         if (!fast) {
-            Rng g; g.begin(P.seed, ph.pid, ph.step);
-            ph.wp = draw_prop(g, T, T.wprob, T.walias, T.pprob, T.palias);
+            Rng g; g.begin(P.seed, ph.pid(), ph.step());
+            ph.set_wp(draw_prop(g, T, T.wprob, T.walias, T.pprob, T.palias));
             draw_iso(g, ph.dx, ph.dy, ph.dz);
-            ph.sn = draw_scat_next(g, T.lambda[ph.wp]);
+            ph.sn = draw_scat_next(g, T.lambda[ph.wp()]);
         }
         renorm_unit(ph.dx, ph.dy, ph.dz);
         ph.nscat++;
     }
-    if ((long long)ph.nscat >= P.maxscat || (long long)ph.step >= P.maxloop) ph.active = 0;   // :434, :401
+    if ((long long)ph.nscat >= P.maxscat || (long long)ph.step() >= P.maxloop) ph.stop();     // :434, :401
     return esc;
 }
 
@@ -351,13 +371,16 @@ __device__ __forceinline__ void flush_fixed_point(uint32_t* words, unsigned ncop
 //        (>= 64 cells along an axis) for the warp-cooperative N-D walk to pay for its registers
 // Dynamic shared memory: [mbarrier 16 B][material blob][geometry blob][histogram(s)]
 #ifndef MCB_BLOCK_MAX
-#define MCB_BLOCK_MAX 768
+#define MCB_BLOCK_MAX 896         // 1-D / single-cell tallies: 72 registers x 28 warps (measured best of 768 / 896 / 1024)
+#endif
+#ifndef MCB_BLOCK_MAX_ND1
+#define MCB_BLOCK_MAX_ND1 768     // serial N-D walk: 80 registers
 #endif
 #ifndef MCB_BLOCK_MAX_ND
-#define MCB_BLOCK_MAX_ND 512      // the N-D walk keeps two crossing iterators live: give it 128 registers
+#define MCB_BLOCK_MAX_ND 512      // the cooperative N-D walk keeps two crossing iterators live: give it 128 registers
 #endif
 template <int NCOMP, int TM, int NDM, bool EMIT>
-__global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : MCB_BLOCK_MAX, 1) k_step(const StepParams P) {
+__global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : (NDM == 1 ? MCB_BLOCK_MAX_ND1 : MCB_BLOCK_MAX), 1) k_step(const StepParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
     unsigned char* s_mat = smem + P.so_mat;
@@ -398,7 +421,7 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : MCB_BLOCK_MAX, 1
     constexpr bool FX = MCB_TALLY_FX && TM == MCB_TM_WARP;        // fixed-point warp histograms (mcb_device.cuh: deposit)
     const uint32_t hi_off = 4u * (uint32_t)P.field_len;            // low-word plane, then high-word plane
 
-    unsigned long long my_steps = 0, my_esc = 0, my_emitted = 0, my_live = 0, my_stores = 0;
+    unsigned my_steps = 0, my_esc = 0, my_emitted = 0, my_live = 0, my_stores = 0;     // per thread and launch: < 2^32
     bool exhausted = false;
     // fixed-point histograms are flushed by the CTA between tiles at least every fx_flush_trips loop trips (the host keeps
     // steps_per_launch below that), which bounds the number of deposits an entry can receive (set_fixed_point, mcb_api.cu)
@@ -410,19 +433,16 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : MCB_BLOCK_MAX, 1
     for (long long base = (long long)blockIdx.x * blockDim.x; base < P.nslots; base += (long long)gridDim.x * blockDim.x) {
         const long long i = base + threadIdx.x;
         const bool valid = i < P.nslots;
-        Particle ph; ph.active = 0; ph.killed = 0; ph.sdom = 0; ph.wp = 0; ph.sign = 0; ph.nscat = 0; ph.step = 0; ph.pid = 0;
+        Particle ph; ph.mlo = 0; ph.nscat = 0; ph.ps = 0;
         ph.px = ph.py = ph.pz = ph.dx = ph.dy = ph.dz = ph.sn = 0.0;
         if (valid) {
             const unsigned long long meta = ld_stream(P.st.meta + i);
-            ph.active = MCB_META_ACTIVE(meta);
-            if (ph.active) {
-                const unsigned long long ps = ld_stream(P.st.pidstep + i);
+            if (MCB_META_ACTIVE(meta)) {
+                ph.mlo = (uint32_t)meta & ~(1u << 22); ph.nscat = (uint32_t)(meta >> 32);
+                ph.ps = ld_stream(P.st.pidstep + i);
                 ph.px = ld_stream(P.st.px + i); ph.py = ld_stream(P.st.py + i); ph.pz = ld_stream(P.st.pz + i);
                 ph.dx = ld_stream(P.st.dx + i); ph.dy = ld_stream(P.st.dy + i); ph.dz = ld_stream(P.st.dz + i);
                 ph.sn = ld_stream(P.st.sn + i);
-                ph.wp = MCB_META_WP(meta); ph.sign = MCB_META_SIGN(meta); ph.killed = 0;
-                ph.sdom = MCB_META_SDOM(meta); ph.nscat = MCB_META_NSCAT(meta);
-                ph.pid = MCB_PID(ps); ph.step = MCB_STEP(ps);
             }
         }
         bool dirty = false;
@@ -438,7 +458,7 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : MCB_BLOCK_MAX, 1
         }
         for (int s = 0; s < P.steps_per_launch; ++s) {
             // refill: a freed slot takes the next particle id (warp-aggregated ticket)
-            const bool want = EMIT && valid && !ph.active && !exhausted && (P.refill || s == 0);
+            const bool want = EMIT && valid && !ph.active() && !exhausted && (P.refill || s == 0);
             const unsigned m = EMIT ? __ballot_sync(0xFFFFFFFFu, want) : 0u;
             if (EMIT && m) {
                 unsigned long long ticket = 0;
@@ -452,17 +472,17 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : MCB_BLOCK_MAX, 1
                 }
             }
             // one loop trip (problem.cpp:401-435) in three phases; the tally phase is warp-synchronous
-            const bool run = ph.active != 0;
+            const bool run = ph.active();
             Segment sg; sg.ok = false; sg.hit = -1; sg.d = 0.0; sg.nscat_before = 0;
             sg.bx = sg.by = sg.bz = sg.ex = sg.ey = sg.ez = 0.0;
             if (run) { my_esc += advect_move(T, ph, sg); my_steps++; dirty = true; }
             if (P.do_tally) {
                 __syncwarp();
                 // accumAmt (problem.cpp:473-476,506-509,539-544,581-589,629-637) times sign (:414)
-                const double sg_ = ph.sign ? 1.0 : -1.0;
+                const double sg_ = ph.sign() ? 1.0 : -1.0;
                 double amt[NCOMP];
-                if (NCOMP == 1) amt[0] = sg_ * (sg.d * T.inv_vel[ph.wp]);
-                else if (NCOMP == 4) { amt[0] = sg_ * (sg.d * T.inv_vel[ph.wp]); amt[1 % NCOMP] = sg_ * (sg.ex - sg.bx); amt[2 % NCOMP] = sg_ * (sg.ey - sg.by); amt[3 % NCOMP] = sg_ * (sg.ez - sg.bz); }
+                if (NCOMP == 1) amt[0] = sg_ * (sg.d * T.inv_vel[ph.wp()]);
+                else if (NCOMP == 4) { amt[0] = sg_ * (sg.d * T.inv_vel[ph.wp()]); amt[1 % NCOMP] = sg_ * (sg.ex - sg.bx); amt[2 % NCOMP] = sg_ * (sg.ey - sg.by); amt[3 % NCOMP] = sg_ * (sg.ez - sg.bz); }
                 else { amt[0] = sg_ * (sg.ex - sg.bx); amt[1 % NCOMP] = sg_ * (sg.ey - sg.by); amt[2 % NCOMP] = sg_ * (sg.ez - sg.bz); }
                 FxArgs fx{hi_off, false, &P};
                 if (FX) {
@@ -474,22 +494,22 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : MCB_BLOCK_MAX, 1
                     fx.slow = !fits;
                 }
                 const int rbase = cum ? NCOMP * (int)(((long long)sg.nscat_before + P.cum_step - 1) / P.cum_step) : 0;
-                tally_segments<NCOMP, TM, (NDM > 0), true, (NDM == 2)>(T.sdom[ph.sdom], T.hist, P.rows, P.cols, rbase, sg.ok, sg.bx, sg.by, sg.bz, sg.ex, sg.ey, sg.ez, amt, lane, fx);
+                tally_segments<NCOMP, TM, (NDM > 0), true, (NDM == 2)>(T.sdom[ph.sdom()], T.hist, P.rows, P.cols, rbase, sg.ok, sg.bx, sg.by, sg.bz, sg.ex, sg.ey, sg.ez, amt, lane, fx);
             }
             if (sg.ok) my_esc += collide(P, T, ph, sg);
-            if (__all_sync(0xFFFFFFFFu, !ph.active && (!EMIT || exhausted || !valid || !P.refill))) break;
+            if (__all_sync(0xFFFFFFFFu, !ph.active() && (!EMIT || exhausted || !valid || !P.refill))) break;
         }
         if (valid && dirty) {
             my_stores++;
             st_stream(P.st.px + i, ph.px); st_stream(P.st.py + i, ph.py); st_stream(P.st.pz + i, ph.pz);
             st_stream(P.st.dx + i, ph.dx); st_stream(P.st.dy + i, ph.dy); st_stream(P.st.dz + i, ph.dz);
             st_stream(P.st.sn + i, ph.sn);
-            st_stream(P.st.meta + i, pack_meta(ph.wp, ph.sign, ph.active, ph.killed, ph.sdom, ph.nscat));
-            st_stream(P.st.pidstep + i, (ph.pid << 24) | (unsigned long long)ph.step);
+            st_stream(P.st.meta + i, ph.meta());
+            st_stream(P.st.pidstep + i, ph.ps);
         }
-        if (ph.active) my_live++;
+        if (ph.active()) my_live++;
         if (!EMIT && list_free) {
-            const bool fr = valid && !ph.active;
+            const bool fr = valid && !ph.active();
             const unsigned fm = __ballot_sync(0xFFFFFFFFu, fr);
             if (fm) {
                 unsigned long long pos = 0;
@@ -505,18 +525,15 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : MCB_BLOCK_MAX, 1
     __shared__ unsigned long long s_red[5];
     if (threadIdx.x < 5) s_red[threadIdx.x] = 0;
     __syncthreads();
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        my_steps += __shfl_down_sync(0xFFFFFFFFu, my_steps, o); my_esc += __shfl_down_sync(0xFFFFFFFFu, my_esc, o);
-        my_emitted += __shfl_down_sync(0xFFFFFFFFu, my_emitted, o); my_live += __shfl_down_sync(0xFFFFFFFFu, my_live, o);
-        my_stores += __shfl_down_sync(0xFFFFFFFFu, my_stores, o);
-    }
+    my_steps = __reduce_add_sync(0xFFFFFFFFu, my_steps); my_esc = __reduce_add_sync(0xFFFFFFFFu, my_esc);       // REDUX
+    my_emitted = __reduce_add_sync(0xFFFFFFFFu, my_emitted); my_live = __reduce_add_sync(0xFFFFFFFFu, my_live);
+    my_stores = __reduce_add_sync(0xFFFFFFFFu, my_stores);
     if (lane == 0) {
-        if (my_steps) atomicAdd(&s_red[0], my_steps);
-        if (my_esc) atomicAdd(&s_red[1], my_esc);
-        if (my_emitted) atomicAdd(&s_red[2], my_emitted);
-        if (my_live) atomicAdd(&s_red[3], my_live);
-        if (my_stores) atomicAdd(&s_red[4], my_stores);
+        if (my_steps) atomicAdd(&s_red[0], (unsigned long long)my_steps);
+        if (my_esc) atomicAdd(&s_red[1], (unsigned long long)my_esc);
+        if (my_emitted) atomicAdd(&s_red[2], (unsigned long long)my_emitted);
+        if (my_live) atomicAdd(&s_red[3], (unsigned long long)my_live);
+        if (my_stores) atomicAdd(&s_red[4], (unsigned long long)my_stores);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -555,8 +572,8 @@ __global__ void __launch_bounds__(256) k_emit(const StepParams P) {
         emit_particle(P, T, next + j, ph);
         P.st.px[i] = ph.px; P.st.py[i] = ph.py; P.st.pz[i] = ph.pz;
         P.st.dx[i] = ph.dx; P.st.dy[i] = ph.dy; P.st.dz[i] = ph.dz; P.st.sn[i] = ph.sn;
-        P.st.meta[i] = pack_meta(ph.wp, ph.sign, ph.active, ph.killed, ph.sdom, ph.nscat);
-        P.st.pidstep[i] = (ph.pid << 24) | (unsigned long long)ph.step;
+        P.st.meta[i] = ph.meta();
+        P.st.pidstep[i] = ph.ps;
     }
 }
 // after k_emit: advance the particle counter, empty the free list (one thread)
@@ -600,31 +617,31 @@ __global__ void k_traj(const StepParams P, const mcb_traj_desc t, const TrajDev 
         if (npts < o.max_points) { o.points[3 * npts] = x; o.points[3 * npts + 1] = y; o.points[3 * npts + 2] = z; }
         npts++;
     };
-    Particle ph; ph.pid = 0; ph.active = 1; ph.killed = 0; ph.nscat = 0; ph.step = 0; ph.sign = 1;
+    Particle ph; ph.init(0u, true, true, 0u, 0ull);
     Rng g; g.begin(P.seed, 0ull, 0u);
-    ph.wp = t.has_prop ? (uint32_t)(t.w * T.np + t.p) : draw_prop(g, T, T.wprob, T.walias, T.pprob, T.palias);   // :232
+    ph.set_wp(t.has_prop ? (uint32_t)(t.w * T.np + t.p) : draw_prop(g, T, T.wprob, T.walias, T.pprob, T.palias));   // :232
     int cur = -1;
     if (t.has_pos) {                                                                                          // :233-243
         ph.px = t.pos[0]; ph.py = t.pos[1]; ph.pz = t.pos[2];
         if (t.has_dir) { ph.dx = t.dir[0]; ph.dy = t.dir[1]; ph.dz = t.dir[2]; }
         else draw_iso(g, ph.dx, ph.dy, ph.dz);
         normalize3(ph.dx, ph.dy, ph.dz);
-        ph.sdom = (uint32_t)t.sdom;
+        ph.set_sdom((uint32_t)t.sdom);
     } else {                                                                                                  // :244-253
         const DEmitter& E = P.emitters[g.uint_below((uint32_t)P.nemitter)];
-        const uint32_t wp = ph.wp;
+        const uint32_t wp = ph.wp();
         emit_from(E, g, ph);
-        ph.wp = wp; ph.active = 1; ph.pid = 0;
+        ph.init(wp, true, true, ph.sdom(), 0ull);         // TrajProblem traces with sign +1 (problem.cpp:244-253)
         cur = E.kind == MCB_EMIT_BDRY ? E.index : -1;
     }
     push(ph.px, ph.py, ph.pz);
-    ph.sn = draw_scat_next(g, T.lambda[ph.wp]);                                                               // :254
+    ph.sn = draw_scat_next(g, T.lambda[ph.wp()]);                                                             // :254
     for (long long i = 0; i < P.maxloop; ++i) {                                                               // :258
-        const DSdom& sd = T.sdom[ph.sdom];
+        const DSdom& sd = T.sdom[ph.sdom()];
         const long long k = nsteps++;
         const int in_local = (cur >= sd.plane_begin && cur < sd.plane_begin + sd.plane_count) ? cur - sd.plane_begin : -1;
         if (k < o.max_steps) {
-            o.step_sdom[k] = (int32_t)ph.sdom; o.step_in[k] = in_local; o.step_in_kind[k] = cur >= 0 ? T.cold[cur].kind : -1;
+            o.step_sdom[k] = (int32_t)ph.sdom(); o.step_in[k] = in_local; o.step_in_kind[k] = cur >= 0 ? T.cold[cur].kind : -1;
             o.step_out[k] = -1; o.step_out_kind[k] = -1;
         }
         Segment sg; sg.ok = false; sg.hit = -1; sg.next_plane = -1;
@@ -636,7 +653,7 @@ __global__ void k_traj(const StepParams P, const mcb_traj_desc t, const TrajDev 
         if (collide(P, T, ph, sg)) { escaped = 2; break; }                                                    // :277-294
         if (peri) push(ph.px, ph.py, ph.pz);
         cur = sg.next_plane;
-        if (!ph.active) break;                                                                                // :295
+        if (!ph.active()) break;                                                                              // :295
     }
     o.counts[0] = npts; o.counts[1] = nsteps; o.counts[2] = escaped;
 }

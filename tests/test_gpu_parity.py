@@ -134,7 +134,8 @@ def test_solve_matches_oracle_philox(gpu_ctx, omats, mname, dname, pkind, size):
 
 @pytest.mark.parametrize("opts", [dict(steps_per_launch=1, slots=4096), dict(steps_per_launch=7, slots=1000),
                                   dict(steps_per_launch=64, slots=0, tally_mode=2), dict(block=128, ctas_per_sm=1, slots=30000), dict(block=512, steps_per_launch=5),
-                                  dict(tally_mode=3, steps_per_launch=3), dict(tally_mode=1, block=256, steps_per_launch=2)])
+                                  dict(tally_mode=3, steps_per_launch=3), dict(tally_mode=1, block=256, steps_per_launch=2),
+                                  dict(slots=1001, steps_per_launch=2)])
 def test_schedule_options_do_not_change_results(gpu_ctx, omats, opts):
     """Slots / S / tally mode are scheduling only: Philox keyed by particle id makes the result
     independent of them (up to fp summation order)."""
