@@ -196,6 +196,8 @@ public:
     }
 };
 
+static int g_arg_rtl = 0;   /* orc_set_arg_order(): see Domain::emit */
+
 /* boost::random::uniform_01<double> on a 32-bit engine: x / 2^32, one word (random.h:23) */
 inline double uniform01(Words& g) {
     for (;;) {
@@ -521,7 +523,12 @@ struct orc_domain {
                 for (int k = 0; k < 3; ++k) { m(k, 0) = a[k]; m(k, 1) = b[k]; m(k, 2) = z[k]; }
             }
             /* ParallelepipedImpl::drawPos :275-281 ; TriangularPrismImpl :309-320 ; TetrahedronImpl :351-377 */
-            double c0 = uniform01(g), c1 = uniform01(g), c2 = uniform01(g);
+            /* `Vector3d coord(dist(gen), dist(gen), dist(gen))`: argument evaluation order is unspecified in C++.
+             * Default: left to right (what the GPU path implements).  g_arg_rtl: right to left, which is what g++
+             * does when it compiles the reference (oracle/_ref) -- used to compare against that binary word for word. */
+            double c0, c1, c2;
+            if (g_arg_rtl) { c2 = uniform01(g); c1 = uniform01(g); c0 = uniform01(g); }
+            else           { c0 = uniform01(g); c1 = uniform01(g); c2 = uniform01(g); }
             const bool tet = sd.cell == MCB_CELL_TETRAHEDRON || sd.cell == MCB_CELL_PYRAMID;
             if (sd.cell != MCB_CELL_PARALLELEPIPED) {
                 if (c0 + c1 > 1.) { c0 = 1. - c0; c1 = 1. - c1; }
@@ -1004,6 +1011,8 @@ int solveImpl(const orc_problem* P, int rng_mode, uint64_t seed, int64_t n_begin
 extern "C" {
 
 const char* orc_last_error(void) { return g_err.c_str(); }
+
+void orc_set_arg_order(int right_to_left) { g_arg_rtl = right_to_left ? 1 : 0; }
 
 int orc_max_threads(void) {
 #ifdef _OPENMP

@@ -98,6 +98,9 @@ void   orc_philox_words(uint64_t seed, uint64_t particle, uint32_t event, uint32
 void   orc_mt_draws(uint32_t seed, int which, int64_t m, int64_t n, double* out);
 
 int    orc_max_threads(void);
+/* evaluation order of the three draws in `Vector3d coord(dist(gen), dist(gen), dist(gen))` (subdomain.cpp:279, :312, :354):
+ * 0 (default) = left to right, 1 = right to left (g++'s choice when it compiles the reference into oracle/_ref) */
+void   orc_set_arg_order(int right_to_left);
 
 #ifdef __cplusplus
 }

@@ -68,6 +68,7 @@ def lib():
         L.orc_philox_words.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
         L.orc_mt_draws.argtypes = [C.c_uint32, C.c_int, C.c_int64, C.c_int64, dp]
         L.orc_max_threads.restype = C.c_int
+        L.orc_set_arg_order.argtypes = [C.c_int]
         _lib = L
     return _lib
 
@@ -256,3 +257,9 @@ def mt_draws(seed, which, n, m=0):
 
 def max_threads():
     return lib().orc_max_threads()
+
+
+def set_arg_order(right_to_left):
+    """Order of the three position draws at subdomain.cpp:279/:312/:354 (unspecified in C++): False = x,y,z (default, the
+    GPU path's order), True = z,y,x (what g++ does for the reference binary oracle/_ref/montecarlo_ref)."""
+    lib().orc_set_arg_order(1 if right_to_left else 0)

@@ -1,0 +1,60 @@
+"""Runs the REFERENCE ITSELF: oracle/_ref/montecarlo_ref, the reference's own sources compiled by oracle/Makefile against
+the Eigen/Boost stand-ins under oracle/shim/.  TEST INFRASTRUCTURE: only tests/, smoke() and bench.py's cpu_baseline /
+--impl reference legs may use it.  Nothing here reads /root/reference at run time (the binary is prebuilt).
+
+The binary keeps the reference's positional grammar (main.cpp:216-235):
+    <dir> <material> <T> <domain> <dims...> <divs...> <problem> <nemit> [size] <maxscat> <maxloop> <nsim>
+and its stdout blocks ("Output", "Averaged", "Mean", "Standard Deviation").  MCREF_SEED makes the seeds deterministic
+(oracle/shim/boost/random/random_device.hpp): thread t of solve k gets seed MCREF_SEED + (calls so far).
+"""
+import os
+import re
+import subprocess
+import time
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+BIN = os.path.join(_HERE, "_ref", "montecarlo_ref")
+BIN_CHK = os.path.join(_HERE, "_ref", "montecarlo_ref_chk")
+
+
+def available(checked=False):
+    return os.access(BIN_CHK if checked else BIN, os.X_OK)
+
+
+def _blocks(text):
+    """{title: 2-D array} for every 'Title\\n<rows of numbers>\\n\\n' block of the reference's stdout."""
+    out, lines, i = {}, text.splitlines(), 0
+    num = re.compile(r"^\s*[-+]?(\d|nan|inf)", re.I)
+    while i < len(lines):
+        t = lines[i].strip()
+        if t in ("Output", "Averaged", "Mean", "Standard Deviation", "Combined Trajectory"):
+            rows, j = [], i + 1
+            while j < len(lines) and lines[j].strip() and num.match(lines[j]):
+                rows.append([float(x) for x in lines[j].split()])
+                j += 1
+            out.setdefault(t, []).append(np.array(rows))
+            i = j
+        else:
+            i += 1
+    return out
+
+
+def run(matdir, material, T, domain_args, problem_args, seed=0, threads=1, checked=False, timeout=600):
+    """One run of the reference binary.  Returns (blocks, stdout, seconds)."""
+    exe = BIN_CHK if checked else BIN
+    if not os.access(exe, os.X_OK):
+        raise RuntimeError(f"{exe} is missing: run `make -C oracle ref` where /root/reference exists")
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads))
+    if seed is not None:
+        env["MCREF_SEED"] = str(seed)
+    else:
+        env.pop("MCREF_SEED", None)
+    argv = [exe, matdir, material, repr(float(T))] + [str(a) for a in domain_args] + [str(a) for a in problem_args]
+    t0 = time.perf_counter()
+    r = subprocess.run(argv, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
+    dt = time.perf_counter() - t0
+    if r.returncode != 0:
+        raise RuntimeError(f"reference binary failed ({r.returncode}): {r.stderr[-400:]}")
+    return _blocks(r.stdout), r.stdout, dt

@@ -1,0 +1,2 @@
+// oracle/shim/boost/fusion/container/vector/vector10.hpp — TEST INFRASTRUCTURE: forwards to the Fusion/MPL stand-in.
+#include "../../../fusion/fusion_shim.hpp"
