@@ -1,0 +1,105 @@
+"""Pins the oracle restatement (oracle/mc_oracle.cpp) against the REFERENCE ITSELF.
+
+oracle/_ref/montecarlo_ref is the reference's own sources (boundary / domain / field / main / material / phonon / problem /
+random / subdomain .cpp, untouched, compiled where they lie) built against the Eigen/Boost stand-ins of oracle/shim/.  Its
+stdout for the cases in tests/refcases.py (seed 0, one thread) is committed under tests/golden/ref_*.json
+(tests/golden/make_ref_golden.py).  With the same mt19937 stream the oracle must reproduce every printed digit:
+tolerance 2e-9 of the row scale (the reference prints 10 significant digits).
+
+CPU only; no test here reads /root/reference.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as orc, refbin
+from tests import refcases
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 2e-9
+
+
+def _golden(name):
+    return json.load(open(os.path.join(GOLD, f"ref_{name}.json")))
+
+
+def _oracle_solution(case, tmp_path):
+    mat_kw, (disp, relax) = refcases.write_material(case, str(tmp_path))
+    mat = orc.Material(disp, relax, case["T"])
+    kind, dim, div, dT = case["odom"]
+    dom = orc.Domain.create(kind, dim, div, dT)
+    pk, nemit, size, maxscat, maxloop = case["prob"]
+    prob = orc.Problem(mat, dom, pk, nemit, maxscat, maxloop, size)
+    orc.set_arg_order(True)                    # g++ evaluates the three position draws right to left
+    try:
+        sol, st = prob.solve(rng=orc.RNG_MT19937, seed=0, nthreads=1)
+    finally:
+        orc.set_arg_order(False)
+    return sol, st
+
+
+def _close(got, ref):
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    scale[scale == 0] = 1.0
+    return np.abs(got - ref) / scale
+
+
+@pytest.mark.parametrize("name", sorted(refcases.CASES))
+def test_oracle_reproduces_reference_golden(name, tmp_path):
+    case, g = refcases.CASES[name], _golden(name)
+    ref = np.array(g["output"])
+    sol, st = _oracle_solution(case, tmp_path)
+    assert sol.shape == ref.shape
+    assert st["esc"] == g["esc"]
+    err = _close(sol, ref)
+    assert err.max() <= TOL, f"{name}: max rel err {err.max():.3e} at {np.unravel_index(err.argmax(), err.shape)}"
+
+
+def test_arg_order_is_the_only_difference(tmp_path):
+    """With the default (left-to-right) draw order the oracle differs from the g++-built reference exactly where the
+    swapped emission coordinates matter (film: q_z through the specular z faces), and nowhere else."""
+    case, g = refcases.CASES["film_multi_si"], _golden("film_multi_si")
+    ref = np.array(g["output"])
+    mat_kw, (disp, relax) = refcases.write_material(case, str(tmp_path))
+    mat = orc.Material(disp, relax, case["T"])
+    dom = orc.Domain.create(*case["odom"])
+    pk, nemit, size, maxscat, maxloop = case["prob"]
+    sol, _ = orc.Problem(mat, dom, pk, nemit, maxscat, maxloop, size).solve(rng=orc.RNG_MT19937, seed=0, nthreads=1)
+    err = _close(sol, ref)
+    assert err[:3].max() <= TOL          # T, q_x, q_y do not depend on which of x / z got which draw
+    assert err[3].max() > 1e-3           # q_z does
+
+
+@pytest.mark.skipif(not refbin.available(), reason="oracle/_ref/montecarlo_ref not built (make -C oracle ref, dev container only)")
+@pytest.mark.parametrize("name", ["film_multi_si", "tube_multi_si", "bulk_cumflux_grey"])
+def test_live_reference_binary_matches_golden_and_oracle(name, tmp_path):
+    case, g = refcases.CASES[name], _golden(name)
+    mat_kw, _ = refcases.write_material(case, str(tmp_path))
+    dom, prob = refcases.ref_argv(case)
+    blocks, out, _ = refbin.run(str(tmp_path), mat_kw, case["T"], dom, prob, seed=0, threads=1)
+    live = blocks["Output"][0]
+    assert np.array_equal(live, np.array(g["output"]))          # optimised build == checked build that made the golden
+    sol, _ = _oracle_solution(case, tmp_path)
+    assert _close(sol, live).max() <= TOL
+
+
+@pytest.mark.skipif(not refbin.available(), reason="oracle/_ref/montecarlo_ref not built")
+def test_reference_binary_seed_changes_result(tmp_path):
+    """The seed override of the random_device stand-in is honoured (different seed -> different Monte Carlo estimate)."""
+    case = refcases.CASES["bulk_temp_grey"]
+    mat_kw, _ = refcases.write_material(case, str(tmp_path))
+    dom, prob = refcases.ref_argv(case)
+    a = refbin.run(str(tmp_path), mat_kw, case["T"], dom, prob, seed=0)[0]["Output"][0]
+    b = refbin.run(str(tmp_path), mat_kw, case["T"], dom, prob, seed=7)[0]["Output"][0]
+    assert a.shape == b.shape and not np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("name", sorted(refcases.REF_ONLY))
+def test_octet_goldens_are_well_formed(name):
+    """OctetDomain is not restated; its reference output is kept as golden data for that work."""
+    g = _golden(name)
+    out, avg = np.array(g["output"]), np.array(g["averaged"])
+    assert out.shape[0] == 4 and np.isfinite(out).all() and g["esc"] == 0
+    assert avg.shape == (4, 1) and np.isfinite(avg).all()
