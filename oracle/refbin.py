@@ -58,3 +58,38 @@ def run(matdir, material, T, domain_args, problem_args, seed=0, threads=1, check
     if r.returncode != 0:
         raise RuntimeError(f"reference binary failed ({r.returncode}): {r.stderr[-400:]}")
     return _blocks(r.stdout), r.stdout, dt
+
+
+DRIVER = os.path.join(_HERE, "_ref", "ref_driver")
+
+
+def driver_available():
+    return os.access(DRIVER, os.X_OK)
+
+
+def drive(disp, relax, T, domain, dim, div, dT, problem, nemit, maxscat, maxloop=0, size=0, seed=0, threads=1, timeout=3600):
+    """FieldProblem::solve of the reference's own objects through oracle/ref_driver.cpp (domains: bulk film jct tee tube octet
+    + slab / wire composed from the reference's templates).  Thread t uses mt19937(seed + t).
+    Returns dict(output (rows x cols), steps, seconds (solve only), esc, threads)."""
+    if not driver_available():
+        raise RuntimeError(f"{DRIVER} is missing: run `make -C oracle ref` where /root/reference exists")
+    matdir = os.path.dirname(os.path.abspath(disp))
+    argv = [DRIVER, matdir, os.path.basename(disp), os.path.basename(relax), repr(float(T)), domain, str(len(dim))]
+    argv += [repr(float(x)) for x in dim] + [str(len(div))] + [str(int(x)) for x in div] + [repr(float(dT))]
+    argv += [problem, str(int(nemit)), str(int(size)), str(int(maxscat)), str(int(maxloop)), str(int(seed))]
+    env = dict(os.environ)
+    if threads:
+        env["OMP_NUM_THREADS"] = str(threads)
+    r = subprocess.run(argv, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
+    if r.returncode != 0:
+        raise RuntimeError(f"ref_driver failed ({r.returncode}): {r.stderr[-400:]}")
+    lines = r.stdout.splitlines()
+    head = {}
+    i = 0
+    while lines[i].strip() != "Output":
+        k, v = lines[i].split()
+        head[k] = float(v) if k == "seconds" else int(v)
+        i += 1
+    rows = [[float(x) for x in ln.split()] for ln in lines[i + 1:i + 1 + head["rows"]]]
+    out = np.array(rows).reshape(head["rows"], head["cols"])
+    return dict(output=out, steps=head["steps"], seconds=head["seconds"], esc=head["esc"], threads=head["threads"])
