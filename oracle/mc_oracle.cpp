@@ -6,7 +6,7 @@
  * reference's operation order at expression level.  Every function cites the reference
  * file:line it follows (paths relative to /root/reference/montecarlo/).
  *
- * PARITY UNPINNED — see mc_oracle.h.  Third-party arithmetic that is NOT under
+ * Parity is pinned against the reference itself (oracle/_ref) — see mc_oracle.h.  Third-party arithmetic that is NOT under
  * /root/reference and is restated here from its published algorithm:
  *   - Eigen 3.2.x (unpinned; no build files shipped): Hyperplane(n,e) offset = -n.e,
  *     signedDistance = n.p + offset, ParametrizedLine::intersection = -(offset+n.o)/(n.d),

@@ -6,10 +6,12 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load it.  The product library (libmcb.so) never links or calls it.
  *
- * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures
- *  and cannot be built here (needs Eigen 3 + Boost), so
- * this restatement is anchored on the reference's own formulas through known-answer
- * tests authored in tests/ (SURVEY.md §8c KA1-KA6), not on outputs of the reference.
+ * PARITY PINNED AGAINST THE REFERENCE ITSELF: the reference ships no tests, golden
+ * vectors or fixtures, but its own sources are compiled here (oracle/Makefile
+ * target `ref`, against the Eigen/Boost stand-ins of oracle/shim/) into oracle/_ref/, and
+ * this restatement reproduces that binary's output word for word on the same mt19937
+ * stream (tests/test_reference_pin.py, tests/golden/ref_*.json), besides the known-answer
+ * tests of tests/test_oracle_cpu.py.
  *
  * Descriptors are the structs of include/mcb.h so the same tables can be handed to
  * the CUDA library.

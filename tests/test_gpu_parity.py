@@ -187,6 +187,28 @@ def test_statistical_parity_with_mt19937_oracle(gpu_ctx, omats):
     assert abs(qg / qr - 1.0) < 0.01
 
 
+def test_statistical_parity_with_the_reference_itself(gpu_ctx, matfiles, omats):
+    """The same bar against the REFERENCE'S OWN OBJECTS (oracle/_ref/ref_driver: FieldProblem::solve compiled from the
+    reference's sources, mt19937; the slab composed from its templates): T / q_x profiles within 3 sigma of batch-means error,
+    mean flux within 1 %."""
+    from oracle import refbin
+    if not refbin.driver_available():
+        pytest.skip("oracle/_ref/ref_driver not built (make -C oracle ref in the dev container)")
+    disp, relax = matfiles["grey"]
+    mat, dom = omats["grey"], cases.slab(ncell=10)
+    cases.upload(gpu_ctx, mat, dom)
+    prob = orc.Problem(mat, dom, "multi", 100000, 200)
+    B = 8
+    g = np.stack([gpu_ctx.solve(prob.desc, seed=SEED + 100 + b)[0] for b in range(B)])
+    r = np.stack([refbin.drive(disp, relax, 300.0, "slab", [100e-9] * 3, [10, 0, 0], 1.0, "multi", 100000, 200,
+                               seed=4000 + 16 * b, threads=4)["output"] for b in range(B)])
+    mg, mr = g.mean(0), r.mean(0)
+    se = np.sqrt(g.var(0, ddof=1) / B + r.var(0, ddof=1) / B)
+    z = np.abs(mg - mr)[:2] / se[:2]
+    assert (z < 4.0).all() and (z < 3.0).mean() > 0.9
+    assert abs(mg[1].mean() / mr[1].mean() - 1.0) < 0.01
+
+
 def test_bulk_conductivity_within_one_percent(gpu_ctx, omats):
     """KA1: <q_x>/|grad T| -> Material::cond() (material.cpp:160-161)."""
     # grey pins the 1 % bar; the synthetic silicon's heavy-tailed free paths need the looser bound even at 1.6e7
