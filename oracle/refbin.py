@@ -93,3 +93,55 @@ def drive(disp, relax, T, domain, dim, div, dT, problem, nemit, maxscat, maxloop
     rows = [[float(x) for x in ln.split()] for ln in lines[i + 1:i + 1 + head["rows"]]]
     out = np.array(rows).reshape(head["rows"], head["cols"])
     return dict(output=out, steps=head["steps"], seconds=head["seconds"], esc=head["esc"], threads=head["threads"])
+
+
+class Flattened:
+    """C-ABI descriptors (include/mcb.h) of the REFERENCE'S OWN Domain / FieldProblem objects, written by
+    `ref_driver ... flatten <file>` (oracle/ref_driver.cpp: the reference-side half of the drop-in binding)."""
+
+    def __init__(self, path):
+        import ctypes as C
+        from montecarlocpp_b200 import abi
+        raw = open(path, "rb").read()
+        hdr = np.frombuffer(raw, np.int32, 8)
+        assert hdr[0] == 0x4642434D, "not a flatten file"
+        nsdom, nplane, npair, nemit, ncols, ssz, psz = (int(x) for x in hdr[1:8])
+        assert ssz == C.sizeof(abi.SdomDesc) and psz == C.sizeof(abi.PlaneDesc), "descriptor layout mismatch with include/mcb.h"
+        off = 32
+
+        def take(ctype, n):
+            nonlocal off
+            arr = (ctype * max(n, 1)).from_buffer_copy(raw[off:off + C.sizeof(ctype) * n].ljust(C.sizeof(ctype) * max(n, 1), b"\0"))
+            off += C.sizeof(ctype) * n
+            return arr
+        self.sdoms, self.planes = take(abi.SdomDesc, nsdom), take(abi.PlaneDesc, nplane)
+        self.pairs, self.emitters = take(C.c_int32, npair), take(abi.EmitterDesc, nemit)
+        self.cell_vol = take(C.c_double, ncols)
+        self.problem = abi.ProblemDesc.from_buffer_copy(raw[off:off + C.sizeof(abi.ProblemDesc)]); off += C.sizeof(abi.ProblemDesc)
+        self.emit_count = take(C.c_int64, nemit)
+        self.problem.emit_count = C.cast(self.emit_count, abi.c_int64_p)
+        d = abi.DomainDesc()
+        d.nsdom, d.sdoms = nsdom, C.cast(self.sdoms, C.POINTER(abi.SdomDesc))
+        d.nplane, d.planes = nplane, C.cast(self.planes, C.POINTER(abi.PlaneDesc))
+        d.npair, d.pairs = npair, C.cast(self.pairs, abi.c_int32_p)
+        d.nemitter, d.emitters = nemit, C.cast(self.emitters, C.POINTER(abi.EmitterDesc))
+        d.ncols, d.cell_vol = ncols, C.cast(self.cell_vol, abi.c_double_p)
+        self.domain = d
+        self.cols = ncols
+        self.nsdom, self.nplane, self.npair, self.nemitter = nsdom, nplane, npair, nemit
+
+
+def flatten(disp, relax, T, domain, dim, div, dT, problem, nemit, maxscat, maxloop=0, size=0, outdir=None):
+    """Descriptors of the reference's own objects for (domain, problem): see Flattened."""
+    import tempfile
+    if not driver_available():
+        raise RuntimeError(f"{DRIVER} is missing: run `make -C oracle ref` where /root/reference exists")
+    matdir = os.path.dirname(os.path.abspath(disp))
+    path = os.path.join(outdir or tempfile.mkdtemp(prefix="mcflat_"), f"{domain}.mcbf")
+    argv = [DRIVER, matdir, os.path.basename(disp), os.path.basename(relax), repr(float(T)), domain, str(len(dim))]
+    argv += [repr(float(x)) for x in dim] + [str(len(div))] + [str(int(x)) for x in div] + [repr(float(dT))]
+    argv += [problem, str(int(nemit)), str(int(size)), str(int(maxscat)), str(int(maxloop)), "0", "flatten", path]
+    r = subprocess.run(argv, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    if r.returncode != 0:
+        raise RuntimeError(f"ref_driver flatten failed ({r.returncode}): {r.stderr[-400:]}")
+    return Flattened(path)

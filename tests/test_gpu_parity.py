@@ -209,6 +209,40 @@ def test_statistical_parity_with_the_reference_itself(gpu_ctx, matfiles, omats):
     assert abs(mg[1].mean() / mr[1].mean() - 1.0) < 0.01
 
 
+@pytest.mark.parametrize("div", [[0, 0, 0, 0], [2, 2, 2, 1]], ids=["cells", "grid"])
+def test_octet_domain_through_the_reference_binding(gpu_ctx, matfiles, div):
+    """The reference's 42-subdomain OctetDomain (domain.cpp:576-1280; prisms, pyramids, triangular prisms, boxes, 70 Inter
+    pairs, mirror-periodic pairs) is not restated anywhere in this repo.  Its own objects, flattened by the reference-side
+    binding (oracle/ref_driver.cpp `flatten`), run on the device through mcb_upload_domain / mcb_solve; the result must agree
+    with the reference's CPU solve of the same objects: zero escapes (every hand-off finds its partner), per-cell 4-sigma,
+    domain-mean flux within 3 sigma."""
+    from oracle import refbin
+    if not refbin.driver_available():
+        pytest.skip("oracle/_ref/ref_driver not built (make -C oracle ref in the dev container)")
+    from montecarlocpp_b200 import hostapi
+    disp, relax = matfiles["silicon_small"]
+    dim, dT, nemit, maxscat, B = [1e-6, 1e-7, 1e-7, 1e-8], 1.0, 60000, 50, 6
+    fl = refbin.flatten(disp, relax, 300.0, "octet", dim, div, dT, "multi", nemit, maxscat)
+    mat = hostapi.Material(disp, relax, 300.0)
+    gpu_ctx.upload_material(mat.desc)
+    gpu_ctx.upload_domain(fl.domain)
+    g, esc = [], 0
+    for b in range(B):
+        sol, st = gpu_ctx.solve(fl.problem, seed=SEED + 300 + b)
+        g.append(sol); esc += st["esc"]
+    r = [refbin.drive(disp, relax, 300.0, "octet", dim, div, dT, "multi", nemit, maxscat, seed=9000 + 16 * b, threads=4) for b in range(B)]
+    assert esc == 0 and sum(x["esc"] for x in r) == 0
+    g, r = np.stack(g), np.stack([x["output"] for x in r])
+    assert g.shape == r.shape and np.isfinite(g).all()
+    mg, mr = g.mean(0), r.mean(0)
+    se = np.sqrt(g.var(0, ddof=1) / B + r.var(0, ddof=1) / B)
+    z = np.abs(mg - mr) / np.where(se > 0, se, 1.0)
+    assert (z < 4.5).all() and (z < 3.0).mean() > 0.9, z.max()
+    # domain-mean x flux (the quantity OctetDomain::average weights): batch means agree within 3 sigma
+    qg, qr = g[:, 1, :].mean(1), r[:, 1, :].mean(1)
+    assert abs(qg.mean() - qr.mean()) <= 3.0 * np.sqrt(qg.var(ddof=1) / B + qr.var(ddof=1) / B)
+
+
 def test_bulk_conductivity_within_one_percent(gpu_ctx, omats):
     """KA1: <q_x>/|grad T| -> Material::cond() (material.cpp:160-161)."""
     # grey pins the 1 % bar; the synthetic silicon's heavy-tailed free paths need the looser bound even at 1.6e7

@@ -143,3 +143,65 @@ def test_oracle_matches_reference_objects_full_precision(name, tmp_path):
     assert st["esc"] == ref["esc"]
     err = _close(sol, ref["output"])
     assert err.max() <= 1e-11, f"{name}: {err.max():.3e}"
+
+
+# ---- the reference-side binding: descriptors flattened from the reference's OWN objects (ref_driver ... flatten) must equal
+#      what the host mirror (montecarlocpp_b200/host, same class names) flattens for the same constructor arguments
+FLATTEN_CASES = [("bulk", [1e-6] * 3, [8, 0, 0], 1.0), ("film", [1e-6, 1e-7, 1e-6], [0, 10, 0], 1.0),
+                 ("jct", [1e-7, 1e-7, 1e-7, 5e-8], [2, 3, 2, 2], 0.2), ("tee", [1e-7, 1.2e-7, 1e-7, 0.9e-7, 5e-8], [3, 2, 3, 2, 0], 0.3),
+                 ("tube", [1e-6, 5e-8, 5e-8, 2e-8], [0, 6, 6, 3], 1.0), ("slab", [1e-7] * 3, [20, 0, 0], 1.0),
+                 ("wire", [1e-6, 1e-7, 1e-7], [0, 6, 6], 1.0)]
+
+
+def _struct_diff(a, b, rtol=1e-15):
+    bad = []
+    for f, _ in a._fields_:
+        x, y = getattr(a, f), getattr(b, f)
+        if hasattr(x, "__len__"):
+            if not np.allclose(np.array(x[:]), np.array(y[:]), rtol=rtol, atol=0):
+                bad.append(f)
+        elif isinstance(x, (int, float)) and not (x == y or abs(x - y) <= rtol * abs(y)):
+            bad.append(f)
+    return bad
+
+
+@pytest.mark.skipif(not refbin.driver_available(), reason="oracle/_ref/ref_driver not built")
+@pytest.mark.parametrize("kind,dim,div,dT", FLATTEN_CASES, ids=[c[0] for c in FLATTEN_CASES])
+@pytest.mark.parametrize("pkind,size", [("multi", 0), ("cumflux", 4)])
+def test_host_mirror_flattens_like_the_reference_objects(kind, dim, div, dT, pkind, size, tmp_path):
+    from montecarlocpp_b200 import hostapi, materials
+    disp, relax = materials.write_silicon(str(tmp_path), nw=64)
+    fl = refbin.flatten(disp, relax, 300.0, kind, dim, div, dT, pkind, 20000, 100, size=size, outdir=str(tmp_path))
+    mat = hostapi.Material(disp, relax, 300.0)
+    hd = hostapi.Domain(kind, dim, div, dT)
+    hp = hostapi.FieldProblem(mat, hd, pkind, 20000, 100, size=size)
+    d = hd.desc
+    assert (fl.nsdom, fl.nplane, fl.npair, fl.nemitter, fl.cols) == (d.nsdom, d.nplane, d.npair, d.nemitter, d.ncols)
+    for i in range(d.nsdom):
+        assert _struct_diff(fl.sdoms[i], d.sdoms[i]) == [], f"subdomain {i}"
+    for i in range(d.nplane):
+        assert _struct_diff(fl.planes[i], d.planes[i]) == [], f"plane {i}"
+    assert list(fl.pairs[:fl.npair]) == list(d.pairs[:d.npair])                      # integer work: exact
+    for i in range(d.nemitter):
+        assert _struct_diff(fl.emitters[i], d.emitters[i]) == [], f"emitter {i}"
+    assert np.allclose(np.array(fl.cell_vol[:fl.cols]), np.ctypeslib.as_array(d.cell_vol, (d.ncols,)), rtol=1e-15, atol=0)
+    assert _struct_diff(fl.problem, hp.desc) == []
+    assert list(fl.emit_count[:fl.nemitter]) == list(hp.emit_count())                # emitPdf_: exact
+
+
+@pytest.mark.skipif(not refbin.driver_available(), reason="oracle/_ref/ref_driver not built")
+def test_octet_domain_flattens(tmp_path):
+    """The reference's 42-subdomain OctetDomain through the binding: structure checks (the GPU run is in test_gpu_parity)."""
+    from montecarlocpp_b200 import abi, materials
+    disp, relax = materials.write_silicon(str(tmp_path), nw=64)
+    fl = refbin.flatten(disp, relax, 300.0, "octet", [1e-6, 1e-7, 1e-7, 1e-8], [2, 2, 2, 1], 1.0, "multi", 4000, 50, outdir=str(tmp_path))
+    assert fl.nsdom == 42 and fl.cols == 32 and fl.nemitter > 0
+    kinds = {fl.sdoms[i].cell for i in range(42)}
+    assert kinds == {abi.CELL_PARALLELEPIPED, abi.CELL_TRIPRISM, abi.CELL_PRISM, abi.CELL_PYRAMID} or len(kinds) >= 3
+    for q in range(fl.nplane):                                             # every hand-off / periodic partner is mutual
+        p = fl.planes[q]
+        for k in range(p.pair_count):
+            r = fl.planes[fl.pairs[p.pair_begin + k]]
+            back = [fl.pairs[r.pair_begin + j] for j in range(r.pair_count)]
+            assert q in back
+            assert p.kind == r.kind and p.kind in (abi.BDRY_INTER, abi.BDRY_PERI)
