@@ -362,4 +362,19 @@ def run_ours(args):
 
 if __name__ == "__main__":
     a = parse()
-    sys.exit(run_reference(a) if a.impl == "reference" else run_ours(a))
+    # stdout carries exactly ONE JSON line: anything libraries print there (NCCL's version banner, torchrun notices) is
+    # sent to stderr by pointing fd 1 at fd 2 for the duration of the run; the JSON line goes to the real stdout
+    sys.stdout.flush()
+    _real = os.dup(1)
+    os.dup2(2, 1)
+    _buf = []
+    _print = print
+
+    def print(*args, **kw):                                  # noqa: A001  (the two arms print their line through this)
+        _buf.append(" ".join(str(x) for x in args))
+    rc = run_reference(a) if a.impl == "reference" else run_ours(a)
+    sys.stdout.flush()
+    os.dup2(_real, 1)
+    for ln in _buf:
+        os.write(1, (ln + "\n").encode())
+    sys.exit(rc)
