@@ -232,24 +232,28 @@ void fill_params(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, StepPa
 }
 
 // Fixed-point scale of the shared-memory tally (mcb_device.cuh: deposit).  Payload component k of a flight is accepted
-// up to fx_max = 2^E >= 2 * flight_max (* the 99.9 % slowness for the dt row; anything larger takes the exact fp64
-// path).  A histogram is flushed at least every `trips` loop trips (k_step flushes between tiles and the schedule keeps
-// steps_per_launch <= trips), so an entry receives at most `bound` deposits between flushes, and q = v * 2^(QB-1-E) with
-// 2^QB * bound <= 2^62 can never overflow 64 bits (QB <= 50 keeps q inside the DFMA rounding trick's range):
-// 32 lanes x 128 trips -> QB = 49.  Only the warp histograms are fixed point.
-#define MCB_FX_FLUSH_TRIPS 128
+// up to fx_max = 2^E > flight_max (* the 99.9 % slowness for the dt row; anything larger takes the exact fp64 path).
+// A histogram is flushed at least every `trips` loop trips (k_step flushes between tiles and the schedule keeps
+// steps_per_launch <= trips), so an entry receives at most N = f * 32 * trips <= 2^n deposits between flushes: f = 1
+// deposit per flight and cell (f = 2 only for the cooperative N-D walk, whose pieces can share a cell).  Each deposit
+// adds q mod 2^B to the low limb and q >> B to the high limb (no carries): B = 32 - n keeps the low sums below 2^32, and
+// |q| <= 2^(Q-1) with Q = 63 - 2n keeps the high sums inside int32.  16 trips -> n = 9, B = 23, Q = 45: quantum
+// 2^-44 of fx_max.  (An in-kernel flush every `trips` trips of a longer tile was measured: the extra code in the hot
+// loop costs more -- registers -- than the carry-free limbs gain, so the tail runs in launches of `trips` trips.)
+#define MCB_FX_FLUSH_TRIPS 16
 #ifndef MCB_COMPACT_PCT
 #define MCB_COMPACT_PCT 90
 #endif
 void set_fixed_point(mcb_ctx* c, const mcb_problem_desc* prob, StepParams* P) {
-    const double bound = 2.0 * 32.0 * (double)MCB_FX_FLUSH_TRIPS;                          // <= 2 deposits per cell per flight (cooperative N-D pieces)
-    int bits = 0; std::frexp(bound, &bits);                                                // bound <= 2^bits
-    const int QB = std::min(50, 62 - bits);
+    const long long bound = (c->any_nd == 2 ? 2ll : 1ll) * 32ll * MCB_FX_FLUSH_TRIPS;
+    int n = 0; while ((1ll << n) < bound) ++n;                                             // bound <= 2^n
+    const int B = 32 - n, QB = std::min(50, 63 - 2 * n);
+    P->fx_limb_bits = B;
     for (int k = 0; k < 4; ++k) {
         const bool is_dt = (prob->kind == MCB_PROB_TEMP || prob->kind == MCB_PROB_CUMTEMP || prob->kind == MCB_PROB_MULTI) && k == 0;
         const double amax = c->flight_max * (is_dt ? c->inv_vel_fx : 1.0);
         int e = 0; std::frexp(amax > 0.0 ? amax : 1.0, &e);                                // amax < 2^e
-        const int E = e + 1;
+        const int E = e;
         P->fx_max[k] = std::ldexp(1.0, E); P->fx_scale[k] = std::ldexp(1.0, QB - 1 - E); P->fx_inv[k] = std::ldexp(1.0, E + 1 - QB);
     }
     P->fx_flush_trips = MCB_FX_FLUSH_TRIPS;

@@ -344,17 +344,17 @@ __device__ __forceinline__ uint32_t collide(const StepParams& P, const Tables& T
     return esc;
 }
 
-// Flush `ncopy` fixed-point histogram copies (two 32-bit planes each, mcb_device.cuh: deposit) into the global fp64
-// field: the copies are summed as 64-bit integers (exact, order-free), converted once, transposed from the histograms'
-// row-major layout to the field's column-major one, and re-armed with zeros.  `tid`/`nthr` = the cooperating threads
-// (a warp for its private copies in the middle of a launch, the CTA at the end).
+// Flush `ncopy` fixed-point histogram copies (two 32-bit limb planes each, mcb_device.cuh: deposit) into the global fp64
+// field: every copy's entry is recombined as (int32 high limb << B) + low limb, the copies are summed as 64-bit integers
+// (exact, order-free), converted once, transposed from the histograms' row-major layout to the field's column-major one,
+// and re-armed with zeros.  `tid`/`nthr` = the cooperating threads (the CTA, between tiles and at the end of a launch).
 template <int NCOMP>
 __device__ __forceinline__ void flush_fixed_point(uint32_t* words, unsigned ncopy, const StepParams& P, unsigned tid, unsigned nthr) {
     for (long long i = tid; i < P.field_len; i += nthr) {                         // i = r*cols + c in the histograms
         long long acc = 0;
         for (unsigned w = 0; w < ncopy; ++w) {
             uint32_t* h = words + 2ll * w * P.field_len;
-            acc += (long long)(((unsigned long long)h[P.field_len + i] << 32) | (unsigned long long)h[i]);
+            acc += (long long)(int32_t)h[P.field_len + i] * (1ll << P.fx_limb_bits) + (long long)h[i];
             h[i] = 0u; h[P.field_len + i] = 0u;
         }
         if (acc != 0) {
@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : (NDM == 1 ? MCB_
                 if (NCOMP == 1) amt[0] = sg_ * (sg.d * T.inv_vel[ph.wp()]);
                 else if (NCOMP == 4) { amt[0] = sg_ * (sg.d * T.inv_vel[ph.wp()]); amt[1 % NCOMP] = sg_ * (sg.ex - sg.bx); amt[2 % NCOMP] = sg_ * (sg.ey - sg.by); amt[3 % NCOMP] = sg_ * (sg.ez - sg.bz); }
                 else { amt[0] = sg_ * (sg.ex - sg.bx); amt[1 % NCOMP] = sg_ * (sg.ey - sg.by); amt[2 % NCOMP] = sg_ * (sg.ez - sg.bz); }
-                FxArgs fx{hi_off, false, &P};
+                FxArgs fx{hi_off, (uint32_t)P.fx_limb_bits, (1u << P.fx_limb_bits) - 1u, false, &P};
                 if (FX) {
                     // fixed-point histograms: scale by the launch's power of two (exact); a payload beyond the chosen range
                     // (rare: a long flight of a very slow mode) is deposited exactly through the global fp64 path instead
