@@ -435,15 +435,17 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : (NDM == 1 ? MCB_
         const bool valid = i < P.nslots;
         Particle ph; ph.mlo = 0; ph.nscat = 0; ph.ps = 0;
         ph.px = ph.py = ph.pz = ph.dx = ph.dy = ph.dz = ph.sn = 0.0;
+        // all nine loads are issued together (one memory round trip, not meta first and the rest behind its branch); while
+        // the population is full nearly every slot is active, so nothing extra is read
         if (valid) {
             const unsigned long long meta = ld_stream(P.st.meta + i);
-            if (MCB_META_ACTIVE(meta)) {
-                ph.mlo = (uint32_t)meta & ~(1u << 22); ph.nscat = (uint32_t)(meta >> 32);
-                ph.ps = ld_stream(P.st.pidstep + i);
-                ph.px = ld_stream(P.st.px + i); ph.py = ld_stream(P.st.py + i); ph.pz = ld_stream(P.st.pz + i);
-                ph.dx = ld_stream(P.st.dx + i); ph.dy = ld_stream(P.st.dy + i); ph.dz = ld_stream(P.st.dz + i);
-                ph.sn = ld_stream(P.st.sn + i);
-            }
+            ph.ps = ld_stream(P.st.pidstep + i);
+            ph.px = ld_stream(P.st.px + i); ph.py = ld_stream(P.st.py + i); ph.pz = ld_stream(P.st.pz + i);
+            ph.dx = ld_stream(P.st.dx + i); ph.dy = ld_stream(P.st.dy + i); ph.dz = ld_stream(P.st.dz + i);
+            ph.sn = ld_stream(P.st.sn + i);
+            const bool act = MCB_META_ACTIVE(meta);
+            ph.mlo = act ? ((uint32_t)meta & ~(1u << 22)) : 0u; ph.nscat = act ? (uint32_t)(meta >> 32) : 0u;
+            if (!act) ph.ps = 0;
         }
         bool dirty = false;
         if (FX && P.do_tally) {
