@@ -299,7 +299,7 @@ def run_ours(args):
         achieved = tot["steady_stores"] * B_ALG / sdy_s / 1e9 if sdy_s > 0 else 0.0
         dec_ms = tot["step_ms"] - tot["steady_ms"]
         dec_steps = tot["steps"] - tot["steady_steps"]
-        slots = args.slots if args.slots else 148 * 768 * 32
+        slots = args.slots if args.slots else 148 * 896 * 32          # library default: 32 tiles per CTA (896 threads for 1-D tallies)
         # DRAM traffic of that kernel from the committed ncu --set full capture (profiles/ncu_traffic.json), per launch
         traffic = None
         try:
