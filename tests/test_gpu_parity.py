@@ -170,6 +170,27 @@ def test_particle_ranges_add_up(gpu_ctx, omats):
     assert est["steps"] == 0 and not empty.any()
 
 
+@pytest.mark.parametrize("S", [1, 16])
+def test_single_cell_ballistic_tally_does_not_overflow_the_limbs(gpu_ctx, tmp_path, S):
+    """Worst case for the carry-free fixed-point histograms (mcb_device.cuh: deposit): a one-cell domain (accumFlag -1: every
+    lane of every warp deposits into the SAME entry on every loop trip) with a ballistic grey material (flights span the
+    domain, payloads near fx_max).  The limb widths are chosen so that neither limb can overflow between two flushes; the
+    field must still match the oracle to 1e-9 and the counters exactly."""
+    from montecarlocpp_b200 import materials
+    disp, relax = materials.write_grey(str(tmp_path), inv_tau=1e7)            # mean free path 600 um >> domain
+    mat = orc.Material(disp, relax, 300.0)
+    dom = orc.Domain.create("bulk", [1e-6, 1e-6, 1e-6], [0, 0, 0], 1.0)
+    cases.upload(gpu_ctx, mat, dom)
+    gpu_ctx.set_options(slots=148 * 896 * 2, steps_per_launch=S, tally_mode=1)     # warp histograms, every lane busy
+    prob = orc.Problem(mat, dom, "multi", 300000, 40, maxloop=400)
+    ref, rst = prob.solve(rng=orc.RNG_PHILOX, seed=SEED)
+    got, gst = gpu_ctx.solve(prob.desc, seed=SEED)
+    gpu_ctx.set_options(slots=0, steps_per_launch=0, tally_mode=0)
+    assert gst["steps"] == rst["steps"] and gst["esc"] == rst["esc"] == 0
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    assert (np.abs(got - ref) <= 1e-9 * scale).all(), np.abs(got - ref).max(axis=1) / scale[:, 0]
+
+
 def test_statistical_parity_with_mt19937_oracle(gpu_ctx, omats):
     """North-star bar: T and q profiles within 3 sigma of batch-means error against the oracle run
     with the reference's own RNG family (mt19937), k_eff within 1 %."""
