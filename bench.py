@@ -272,15 +272,16 @@ def run_ours(args):
         other = (osteps, time.perf_counter() - t2)
         ctx.set_options(steps_per_launch=S, slots=args.slots)
 
-    vals = torch.tensor([elapsed, e2e_elapsed, float(tot["steps"]), float(e2e_steps), float(tot["launches"])],
+    vals = torch.tensor([elapsed, e2e_elapsed, float(tot["steps"]), float(e2e_steps), float(tot["launches"]), float(tot["device_ms"])],
                         dtype=torch.float64, device="cuda")
     if world > 1:
         mx = vals.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = vals.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        elapsed, e2e_elapsed = mx[0].item(), mx[1].item()
+        elapsed, e2e_elapsed, device_ms = mx[0].item(), mx[1].item(), mx[5].item()
         all_steps, all_e2e_steps, all_launches = sm[2].item(), sm[3].item(), sm[4].item()
     else:
         all_steps, all_e2e_steps, all_launches = float(tot["steps"]), float(e2e_steps), float(tot["launches"])
+        device_ms = float(tot["device_ms"])
 
     if rank == 0:
         nw, npol = mat.desc.nw, mat.desc.np
@@ -313,6 +314,11 @@ def run_ours(args):
             "metric": "phonon_steps_per_s", "value": all_steps / elapsed, "unit": "phonon-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "timing": {"value_from": "host clock around the K steps, barrier + cuda synchronize on both sides, max over ranks",
+                       "device_ms_per_step": device_ms / args.steps,
+                       "device_value": all_steps / (device_ms * 1e-3) if device_ms > 0 else None,
+                       "device_note": "CUDA events on the library's stream around each solve (mcb_stats.device_ms), summed over "
+                                      "the K steps, max over ranks; excludes the all-reduce and the host gaps between solves"},
             "config": {"workload": args.workload, "nemit_per_gpu": args.nemit, "maxscat": maxscat, "problem": pkind,
                        "material": f"{mkind} nw={nw} np={npol}", "mode": args.mode, "steps_per_launch": S,
                        "l2": f"resident state {slots} slots x 72 B = {slots * 72 / 1e6:.0f} MB > 126 MB L2 (no flush needed)",
