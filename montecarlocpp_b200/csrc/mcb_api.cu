@@ -241,6 +241,9 @@ void fill_params(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, StepPa
 // 2^-44 of fx_max.  (An in-kernel flush every `trips` trips of a longer tile was measured: the extra code in the hot
 // loop costs more -- registers -- than the carry-free limbs gain, so the tail runs in launches of `trips` trips.)
 #define MCB_FX_FLUSH_TRIPS 16
+#ifndef MCB_COOP_ND_CELLS
+#define MCB_COOP_ND_CELLS 64      // grids at least this fine along an axis take the warp-cooperative N-D walk
+#endif
 #ifndef MCB_COMPACT_PCT
 #define MCB_COMPACT_PCT 90
 #endif
@@ -578,7 +581,7 @@ int mcb_upload_domain(mcb_ctx* c, const mcb_domain_desc* d) {
             for (int k = 0; k < ncol; ++k) diam += std::sqrt(cols3[3 * k] * cols3[3 * k] + cols3[3 * k + 1] * cols3[3 * k + 1] + cols3[3 * k + 2] * cols3[3 * k + 2]);
             flight_max = std::max(flight_max, diam + 4.0 * std::fabs(S.eps));
         }
-        if (S.accum >= 3) any_nd = std::max(any_nd, (S.shape[0] >= 64 || S.shape[1] >= 64 || S.shape[2] >= 64) ? 2 : 1);
+        if (S.accum >= 3) any_nd = std::max(any_nd, (S.shape[0] >= MCB_COOP_ND_CELLS || S.shape[1] >= MCB_COOP_ND_CELLS || S.shape[2] >= MCB_COOP_ND_CELLS) ? 2 : 1);
         const long long sp = S.shape[0] * S.shape[1] * S.shape[2];
         if (S.accum < -2 || S.accum > 4 || sp < 0) { c->err = "bad accum flag / shape"; return MCB_EINVAL; }
         if (sp == 0) D.col_offset = -1;                                                                    // field.cpp:34
