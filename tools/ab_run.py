@@ -13,6 +13,8 @@ for wl in (sys.argv[1:] or ["slab", "film", "wire"]):
         dom = hostapi.Domain("slab", [100e-9] * 3, [100, 0, 0], 1.0); prob = hostapi.FieldProblem(mat, dom, "multi", 10_000_000, 1000)
     elif wl == "wire":
         dom = hostapi.Domain("wire", [1e-6, 1e-7, 1e-7], [0, 32, 32], 1.0); prob = hostapi.FieldProblem(mat, dom, "multi", 4_000_000, 100)
+    elif wl == "tube":
+        dom = hostapi.Domain("tube", [1e-6, 5e-8, 5e-8, 2e-8], [0, 8, 8, 4], 1.0); prob = hostapi.FieldProblem(mat, dom, "multi", 4_000_000, 100)
     elif wl == "bulk":
         dom = hostapi.Domain("bulk", [1e-6] * 3, [128, 128, 128], 1.0); prob = hostapi.FieldProblem(mat, dom, "multi", 4_000_000, 100)
     else:
