@@ -216,6 +216,9 @@ int  mcb_create(int device, mcb_ctx** out);
 void mcb_destroy(mcb_ctx* ctx);
 const char* mcb_last_error(const mcb_ctx* ctx);   /* ctx may be NULL: last create() error */
 int  mcb_abi_version(void);
+/* "<sha1 of the CUDA sources>|<extra compile flags>": lets tests refuse a library that was not built from the tree it sits
+ * in, or that was built with experiment flags (no reference analogue) */
+const char* mcb_build_info(void);
 
 int  mcb_set_options(mcb_ctx* ctx, const mcb_options* opt);
 int  mcb_get_options(const mcb_ctx* ctx, mcb_options* opt);

@@ -401,6 +401,14 @@ extern "C" {
 
 int mcb_abi_version(void) { return MCB_ABI_VERSION; }
 
+#ifndef MCB_SRC_HASH
+#define MCB_SRC_HASH "unknown"
+#endif
+#ifndef MCB_EXTRA_FLAGS
+#define MCB_EXTRA_FLAGS ""
+#endif
+const char* mcb_build_info(void) { return MCB_SRC_HASH "|" MCB_EXTRA_FLAGS; }
+
 const char* mcb_last_error(const mcb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
 int mcb_create(int device, mcb_ctx** out) {

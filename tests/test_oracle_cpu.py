@@ -298,5 +298,17 @@ def test_c_abi_library_exports_every_declared_symbol():
         assert hasattr(L, name), name
     L.mcb_abi_version.restype = C.c_int
     assert L.mcb_abi_version() == abi.MCB_ABI_VERSION
+    # the library in the tree was built from the sources in the tree, with the default flags (an A/B experiment build left
+    # behind would otherwise be what the GPU tests and the bench load)
+    import hashlib
+    csrc = os.path.join(ROOT, "montecarlocpp_b200", "csrc")
+    h = hashlib.sha1()
+    for f in (os.path.join(csrc, "mcb_api.cu"), os.path.join(csrc, "mcb_kernels.cuh"), os.path.join(csrc, "mcb_device.cuh"),
+              os.path.join(ROOT, "include", "mcb.h")):
+        h.update(open(f, "rb").read())
+    L.mcb_build_info.restype = C.c_char_p
+    src_hash, _, extra = L.mcb_build_info().decode().partition("|")
+    assert extra == "", f"libmcb.so was built with experiment flags: {extra!r}"
+    assert src_hash == h.hexdigest(), "libmcb.so is stale: rebuild with `make -C montecarlocpp_b200/csrc`"
     # struct layouts agree with the C compiler's (sizes baked into the oracle, which includes the same header)
     assert C.sizeof(abi.PlaneDesc) == 8 * (4 + 2 + 9 + 9 + 3 + 1 + 3 + 1 + 24) and C.sizeof(abi.SdomDesc) % 8 == 0
