@@ -189,19 +189,25 @@ struct RunPlan { long long slots; int S, block, grid; int tm, copies; size_t sme
 
 int plan_run(mcb_ctx* c, const mcb_problem_desc* prob, long long nparticles, RunPlan* r) {
     const mcb_options& o = c->opt;
-    const int block_max = c->any_nd == 2 ? MCB_BLOCK_MAX_ND : (c->any_nd == 1 ? MCB_BLOCK_MAX_ND1 : MCB_BLOCK_MAX);  // the N-D kernels are built for fewer, fatter threads
+    // the N-D kernels are built for fewer, fatter threads; the serial N-D walk with warp-private histograms wants 128 registers
+    // (512 threads), with the CTA histogram / the global field 80 (768 threads): try the warp-histogram shape first
+    const int per_sm = o.ctas_per_sm > 0 ? o.ctas_per_sm : 1;
+    const size_t base = 16 + (size_t)c->mv.bytes + (size_t)c->gv.bytes;
+    const size_t hist = (size_t)prob->rows * (size_t)c->cols * sizeof(double);
+    const size_t budget = c->smem_optin / (size_t)per_sm > 1024 ? c->smem_optin / (size_t)per_sm - 1024 : 0;
+    int block_max = c->any_nd == 2 ? MCB_BLOCK_MAX_ND : (c->any_nd == 1 ? MCB_BLOCK_MAX_ND1 : MCB_BLOCK_MAX);
+    if (c->any_nd == 1 && o.tally_mode != 2 && o.tally_mode != 3) {
+        const int bw = o.block > 0 ? std::min(o.block, MCB_BLOCK_MAX_ND1W) : MCB_BLOCK_MAX_ND1W;
+        if (o.tally_mode == 1 || base + hist * (size_t)(bw / 32) <= budget) block_max = MCB_BLOCK_MAX_ND1W;
+    }
     r->block = o.block > 0 ? std::min(o.block, block_max) : block_max;
     if (r->block % 32 != 0 || o.block > MCB_BLOCK_MAX) { c->err = "block must be a multiple of 32, <= " + std::to_string(MCB_BLOCK_MAX); return MCB_EINVAL; }
-    const int per_sm = o.ctas_per_sm > 0 ? o.ctas_per_sm : 1;
     r->S = o.steps_per_launch > 0 ? o.steps_per_launch : 16;
     long long slots = o.slots > 0 ? o.slots : (long long)c->sm_count * r->block * 32;   // ~2.4 M resident phonons
     slots = std::min(slots, std::max<long long>(nparticles, 1));
     r->slots = slots;
     const long long tiles = (slots + r->block - 1) / r->block;
     r->grid = (int)std::min<long long>((long long)c->sm_count * per_sm, std::max<long long>(tiles, 1));
-    const size_t base = 16 + (size_t)c->mv.bytes + (size_t)c->gv.bytes;
-    const size_t hist = (size_t)prob->rows * (size_t)c->cols * sizeof(double);
-    const size_t budget = c->smem_optin / (size_t)per_sm > 1024 ? c->smem_optin / (size_t)per_sm - 1024 : 0;
     const size_t nwarps = (size_t)r->block / 32;
     // tally placement: warp-private histograms when they fit, else one per CTA, else the global field in L2
     int tm = MCB_TM_GLOBAL;
@@ -210,6 +216,8 @@ int plan_run(mcb_ctx* c, const mcb_problem_desc* prob, long long nparticles, Run
     if (o.tally_mode == 1) { tm = MCB_TM_WARP; if (base + hist * nwarps > c->smem_optin) { c->err = "tally_mode=1 (warp histograms) does not fit in shared memory"; return MCB_ELIMIT; } }
     if (o.tally_mode == 3) { tm = MCB_TM_BLOCK; if (base + hist > c->smem_optin) { c->err = "tally_mode=3 (CTA histogram) does not fit in shared memory"; return MCB_ELIMIT; } }
     if (o.tally_mode == 2) tm = MCB_TM_GLOBAL;
+    // a kernel built for 512 threads must not be launched with more: the warp-histogram N-D kernel is only reachable with block <= 512
+    if (c->any_nd == 1 && tm == MCB_TM_WARP && r->block > MCB_BLOCK_MAX_ND1W) { c->err = "internal: warp-histogram N-D kernel launched too wide"; return MCB_EINVAL; }
     r->tm = tm; r->copies = 1;
     if (tm == MCB_TM_WARP) for (int cp = 4; cp > 1; cp >>= 1) if (base + hist * nwarps * cp <= budget) { r->copies = cp; break; }
     r->smem = base + (tm == MCB_TM_WARP ? hist * nwarps * r->copies : (tm == MCB_TM_BLOCK ? hist : 0));
