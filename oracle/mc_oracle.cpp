@@ -1316,8 +1316,13 @@ int orc_domain_locate(const orc_domain* d, const double pos[3]) {
 
 /* TrajProblem::solve problem.cpp:226-299 with TrkPhonon's recording (phonon.cpp:129-170) */
 int orc_traj(const orc_material* M, const orc_domain* D, const mcb_traj_desc* t, uint64_t seed, mcb_traj_out* o) {
+    return orc_traj_rng(M, D, t, ORC_RNG_PHILOX, seed, o);
+}
+/* rng_mode = ORC_RNG_MT19937: one sequential mt19937(seed) like `Rng gen(s)` in solveTraj (main.cpp:86-103), to compare with
+ * the reference binary word for word; ORC_RNG_PHILOX: the device's per-event streams of particle 0 */
+int orc_traj_rng(const orc_material* M, const orc_domain* D, const mcb_traj_desc* t, int rng_mode, uint64_t seed, mcb_traj_out* o) {
     if (!M || !D || !t || !o) { set_err("null argument"); return MCB_EINVAL; }
-    Words g(ORC_RNG_PHILOX, seed);
+    Words g(rng_mode, seed);
     g.begin(0, 0);
     auto push = [&](const V3& p) {
         if (o->npoints < o->max_points) { o->points[3 * o->npoints] = p.x; o->points[3 * o->npoints + 1] = p.y; o->points[3 * o->npoints + 2] = p.z; }

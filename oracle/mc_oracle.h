@@ -85,6 +85,7 @@ int    orc_trace(const orc_problem*, uint64_t seed, int64_t n_begin, int64_t n_e
 
 /* TrajProblem::solve (problem.cpp:226-299), Philox word source (particle id 0): same records as mcb_traj */
 int    orc_traj(const orc_material*, const orc_domain*, const mcb_traj_desc*, uint64_t seed, mcb_traj_out* out);
+int    orc_traj_rng(const orc_material*, const orc_domain*, const mcb_traj_desc*, int rng_mode, uint64_t seed, mcb_traj_out* out);
 /* Domain::locate (domain.cpp:59-67): index of the first subdomain containing pos, -1 if none */
 int    orc_domain_locate(const orc_domain*, const double pos[3]);
 

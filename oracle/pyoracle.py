@@ -63,6 +63,7 @@ def lib():
         L.orc_trace.argtypes = [vp, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.POINTER(abi.TraceOut)]
         L.orc_cell_index.argtypes = [vp, C.c_int64, dp, ip, lp]
         L.orc_traj.argtypes = [vp, vp, C.POINTER(abi.TrajDesc), C.c_uint64, C.POINTER(abi.TrajOut)]
+        L.orc_traj_rng.argtypes = [vp, vp, C.POINTER(abi.TrajDesc), C.c_int, C.c_uint64, C.POINTER(abi.TrajOut)]
         L.orc_domain_locate.argtypes = [vp, dp]
         L.orc_accumulate.argtypes = [vp, C.c_int32, C.c_int64, ip, dp, dp, dp, dp]
         L.orc_philox_words.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
@@ -220,11 +221,12 @@ class Problem:
             lib().orc_problem_free(self.h); self.h = None
 
 
-def traj(mat, dom, seed, maxscat, maxloop=0, prop=None, pos=None, dir=None):
-    """TrajProblem(mat, dom, [prop], [pos], [dir], maxscat, maxloop).solve() -> dict of records."""
+def traj(mat, dom, seed, maxscat, maxloop=0, prop=None, pos=None, dir=None, rng=RNG_PHILOX):
+    """TrajProblem(mat, dom, [prop], [pos], [dir], maxscat, maxloop).solve() -> dict of records.
+    rng=RNG_MT19937: one sequential mt19937(seed), the reference's own stream (main.cpp:86-103)."""
     t = make_traj_desc(dom, maxscat, maxloop, prop, pos, dir, lambda q: lib().orc_domain_locate(dom.h, _dp(q)))
     bufs, out = abi.traj_buffers(t.maxloop)
-    if lib().orc_traj(mat.h, dom.h, C.byref(t), seed, C.byref(out)) != 0:
+    if lib().orc_traj_rng(mat.h, dom.h, C.byref(t), rng, seed, C.byref(out)) != 0:
         raise RuntimeError(_err())
     return abi.traj_result(bufs, out)
 

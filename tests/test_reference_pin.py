@@ -205,3 +205,37 @@ def test_octet_domain_flattens(tmp_path):
             back = [fl.pairs[r.pair_begin + j] for j in range(r.pair_count)]
             assert q in back
             assert p.kind == r.kind and p.kind in (abi.BDRY_INTER, abi.BDRY_PERI)
+
+
+# ---- N4: TrajProblem / the reference's `traj` mode (main.cpp:86-103, problem.cpp:226-299).  The reference prints the boundary
+#      trace of every loop trip ("<sdom>: <in> <type> -> <out> <type>") and the polyline; the oracle's mt19937 trajectory must
+#      reproduce both: integers exactly, points to the printed precision.
+TRAJ_CASES = {
+    "tube": (["tube", 1e-6, 5e-8, 2e-8, 4, 2], ("tube", [1e-6, 5e-8, 5e-8, 2e-8], [0, 4, 4, 2], 1.0), [5e-7, 6e-8, 1e-8], [0.3, 0.5, 0.81], 12),
+    "jct": (["jct", 1e-7, 5e-8], ("jct", [1e-7, 1e-7, 1e-7, 5e-8], [0, 0, 0, 0], 2e6 * 1e-7), [5e-8, 5e-8, 2.5e-8], [0.2, 0.9, 0.1], 12),
+    "film": (["film", 1e-6, 1e-7, 10], ("film", [1e-6, 1e-7, 1e-6], [0, 10, 0], 1.0), [9.5e-7, 5e-8, 5e-7], [0.9, 0.3, -0.2], 10),
+}
+_KIND_NAMES = {"Spec": 0, "Diff": 1, "Inter": 2, "Isot": 3, "Peri": 4, "Null": -1}
+
+
+@pytest.mark.skipif(not refbin.available(), reason="oracle/_ref/montecarlo_ref not built")
+@pytest.mark.parametrize("name", sorted(TRAJ_CASES))
+def test_trajectory_mode_matches_the_reference_binary(name, tmp_path):
+    import re
+    from montecarlocpp_b200 import materials
+    dom_argv, odom, pos, dirv, maxscat = TRAJ_CASES[name]
+    disp, relax = materials.write_grey(str(tmp_path), inv_tau=2e10)             # mean free path 300 nm: mostly boundary events
+    _, out, _ = refbin.run(str(tmp_path), "grey", 300.0, dom_argv, ["traj"] + pos + dirv + [maxscat, 0], seed=0, threads=1)
+    body = out[out.index("Trajectory 0"):]
+    trace = re.findall(r"^\s*(-?\d+):\s+(-?\d+)\s+(\w+?)[PT\d]?\s+->\s+(-?\d+)\s+(\w+?)[PT\d]?\s*$", body, re.M)
+    rows = [ln.split() for ln in body.splitlines() if ln.strip() and re.fullmatch(r"[\s\d.eE+\-nan]+", ln) and "e" in ln.lower()]
+    pts = np.array([[float(x) for x in r] for r in rows]).T                       # N x 3
+    mat = orc.Material(disp, relax, 300.0)
+    dom = orc.Domain.create(*odom)
+    r = orc.traj(mat, dom, 0, maxscat, 0, pos=pos, dir=dirv, rng=orc.RNG_MT19937)
+    assert len(trace) == len(r["step_sdom"]) and len(trace) > 3
+    for k, (sd, bin_, tin, bout, tout) in enumerate(trace):
+        assert int(sd) == r["step_sdom"][k] and int(bin_) == r["step_in"][k] and int(bout) == r["step_out"][k], k
+        assert _KIND_NAMES[tin] == r["step_in_kind"][k] and _KIND_NAMES[tout] == r["step_out_kind"][k], k
+    assert pts.shape == r["points"].shape
+    assert np.allclose(pts, r["points"], rtol=2e-9, atol=1e-18)
