@@ -2,7 +2,7 @@
 # A/B a compile-time variant on the GPU box: tools/ab.sh "<EXTRA flags>" -> rebuild libmcb.so there and run the sweep
 set -e
 cd montecarlocpp_b200/csrc && make clean >/dev/null && make EXTRA="$1" 2>&1 | grep -E "rror" || true
-grep -A2 "k_stepILi4ELi0ELb0" ptxas.log | grep -E "Used|spill" | tr '\n' ' '; echo
+grep -A2 "k_stepILi4ELi0ELi0ELb0" ptxas.log | grep -E "Used|spill" | tr '\n' ' '; echo
 cd ../..
 python - <<'PY'
 import sys, time, tempfile
