@@ -92,6 +92,22 @@ public:
     Matrix3Xd checkpoints() const { return Matrix3Xd(); }
 };
 
+// one non-box cell of the reference's own templates as a domain (the reference only uses these inside OctetDomain):
+// pins the tri-prism / tetrahedron / prism emission folds, cellVol and Triangle / Polygon emitters of N3
+template <class Cell> class OneCellDomain : public Domain {
+public:
+    Cell sdom_;
+private:
+    std::string info() const { return "OneCellDomain"; }
+public:
+    explicit OneCellDomain(const Cell& c) : Domain(), sdom_(c) { addSdom(&sdom_); }      // Cell's copy constructor re-registers its boundaries
+    Matrix3Xd checkpoints() const { return Matrix3Xd(); }
+};
+typedef TriangularPrism<DiffBoundary, SpecBoundary, DiffBoundary, SpecBoundary, DiffBoundary> TriPrismCell;
+typedef Tetrahedron<IsotBoundary<Triangle>, SpecBoundary, DiffBoundary, DiffBoundary> TetCell;
+typedef Prism<IsotBoundary<Polygon<5> >, IsotBoundary<Polygon<5> >,
+              boost::fusion::vector5<DiffBoundary, SpecBoundary, DiffBoundary, SpecBoundary, DiffBoundary> > Prism5Cell;
+
 void die(const char* msg) { std::fprintf(stderr, "ref_driver: %s\n", msg); std::exit(2); }
 
 // ---------------------------------------------------------------------------------------------- flatten
@@ -264,6 +280,30 @@ int main(int argc, char** argv) {
     else if (domStr == "octet") { OctetDomain* d = new OctetDomain(dim, div, dT); boost::fusion::for_each(d->sdomCont_, vis); dom = d; }
     else if (domStr == "slab") { SlabDomain* d = new SlabDomain(dim, div, dT); vis(d->sdom_); dom = d; }
     else if (domStr == "wire") { WireDomain* d = new WireDomain(dim, div, dT); vis(d->sdom_); dom = d; }
+    // HexDomain(dim, dT) / PyrDomain(dim, dT) never call their own init() in the reference (the domain is unusable as shipped:
+    // "Domain setup not complete"); calling it is the one-line fix a user would make (domain.cpp:224-336)
+    else if (domStr == "hex") { HexDomain* d = new HexDomain(dim, dT); d->init(); vis(d->sdom_); dom = d; }
+    else if (domStr == "pyr") { PyrDomain* d = new PyrDomain(dim, dT); d->init(); vis(d->sdom_); dom = d; }
+    else if (domStr == "triprism" || domStr == "tet" || domStr == "prism5") {
+        // dim = origin(3), edge columns (3 each), gradT(3); div as the cell's constructor takes it; dT = wall temperature scale
+        const int ncol = domStr == "prism5" ? 5 : 3;
+        if (ndim != 3 + 3 * ncol + 3) die("non-box cell: dim must hold origin, columns and gradT");
+        const Vector3d o(dim(0), dim(1), dim(2)), gradT(dim(3 + 3 * ncol), dim(4 + 3 * ncol), dim(5 + 3 * ncol));
+        Matrix3Xd cols(3, ncol);
+        for (int j = 0; j < ncol; ++j) for (int k = 0; k < 3; ++k) cols(k, j) = dim(3 + 3 * j + k);
+        if (domStr == "triprism") {
+            OneCellDomain<TriPrismCell>* d = new OneCellDomain<TriPrismCell>(TriPrismCell(o, Matrix3d(cols), Vector3l(div(0), div(1), div(2)), gradT));
+            vis(d->sdom_); dom = d;
+        } else if (domStr == "tet") {
+            VectorXd T = VectorXd::Zero(4); T(0) = dT;
+            OneCellDomain<TetCell>* d = new OneCellDomain<TetCell>(TetCell(o, Matrix3d(cols), Vector3l(div(0), div(1), div(2)), gradT, T));
+            vis(d->sdom_); dom = d;
+        } else {
+            VectorXd T = VectorXd::Zero(7); T(0) = dT / 2.; T(1) = -dT / 2.;
+            OneCellDomain<Prism5Cell>* d = new OneCellDomain<Prism5Cell>(Prism5Cell(o, cols, div(0), gradT, T));
+            vis(d->sdom_); dom = d;
+        }
+    }
     else die("invalid domain");
 
     const FieldProblem* prob = 0;
