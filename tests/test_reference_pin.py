@@ -150,7 +150,8 @@ def test_oracle_matches_reference_objects_full_precision(name, tmp_path):
 FLATTEN_CASES = [("bulk", [1e-6] * 3, [8, 0, 0], 1.0), ("film", [1e-6, 1e-7, 1e-6], [0, 10, 0], 1.0),
                  ("jct", [1e-7, 1e-7, 1e-7, 5e-8], [2, 3, 2, 2], 0.2), ("tee", [1e-7, 1.2e-7, 1e-7, 0.9e-7, 5e-8], [3, 2, 3, 2, 0], 0.3),
                  ("tube", [1e-6, 5e-8, 5e-8, 2e-8], [0, 6, 6, 3], 1.0), ("slab", [1e-7] * 3, [20, 0, 0], 1.0),
-                 ("wire", [1e-6, 1e-7, 1e-7], [0, 6, 6], 1.0)]
+                 ("wire", [1e-6, 1e-7, 1e-7], [0, 6, 6], 1.0),
+                 ("hex", [1e-6, 5e-8, 8e-8, 3e-8], [], 1.0), ("pyr", [1e-7, 1e-7, 1e-7], [], 0.1)]
 
 
 def _struct_diff(a, b, rtol=1e-15):
