@@ -245,6 +245,16 @@ int flatten(const Domain* dom, const std::vector<CellInfo>& cells, const FieldPr
     std::fwrite(cellVol.data(), sizeof(double), cellVol.size(), f);
     std::fwrite(&pd, sizeof pd, 1, f);
     std::fwrite(counts.data(), sizeof(int64_t), counts.size(), f);
+    // Domain::average (domain.cpp:78-81, 1252-1280): the per-column weights of OctetDomain::WeightF (none for the other domains,
+    // whose average() is the identity)
+    std::vector<double> weights;
+    if (const OctetDomain* oct = dynamic_cast<const OctetDomain*>(dom)) {
+        Eigen::Array<double, 1, Eigen::Dynamic> w = Field(1, oct, OctetDomain::WeightF(*oct)).data().row(0);
+        for (long j = 0; j < w.cols(); ++j) weights.push_back(w(0, j));
+    }
+    const int32_t nw = (int32_t)weights.size();
+    std::fwrite(&nw, sizeof nw, 1, f);
+    std::fwrite(weights.data(), sizeof(double), weights.size(), f);
     std::fclose(f);
     return 0;
 }

@@ -120,6 +120,8 @@ class Flattened:
         self.problem = abi.ProblemDesc.from_buffer_copy(raw[off:off + C.sizeof(abi.ProblemDesc)]); off += C.sizeof(abi.ProblemDesc)
         self.emit_count = take(C.c_int64, nemit)
         self.problem.emit_count = C.cast(self.emit_count, abi.c_int64_p)
+        nweights = int(np.frombuffer(raw[off:off + 4], np.int32)[0]); off += 4
+        self.weights = np.frombuffer(raw[off:off + 8 * nweights], np.float64).copy() if nweights else None
         d = abi.DomainDesc()
         d.nsdom, d.sdoms = nsdom, C.cast(self.sdoms, C.POINTER(abi.SdomDesc))
         d.nplane, d.planes = nplane, C.cast(self.planes, C.POINTER(abi.PlaneDesc))
@@ -129,6 +131,14 @@ class Flattened:
         self.domain = d
         self.cols = ncols
         self.nsdom, self.nplane, self.npair, self.nemitter = nsdom, nplane, npair, nemit
+
+
+    def average(self, sol):
+        """Domain::average of a rows x cols solution: OctetDomain's weighted mean over its averaging subdomains
+        (domain.cpp:1252-1257, rows x 1), the identity for every other domain (domain.cpp:78-81)."""
+        if self.weights is None:
+            return sol
+        return (sol * self.weights[None, :]).sum(axis=1, keepdims=True) / self.weights.sum()
 
 
 def flatten(disp, relax, T, domain, dim, div, dT, problem, nemit, maxscat, maxloop=0, size=0, outdir=None):

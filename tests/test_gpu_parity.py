@@ -259,9 +259,10 @@ def test_octet_domain_through_the_reference_binding(gpu_ctx, matfiles, div):
     se = np.sqrt(g.var(0, ddof=1) / B + r.var(0, ddof=1) / B)
     z = np.abs(mg - mr) / np.where(se > 0, se, 1.0)
     assert (z < 4.5).all() and (z < 3.0).mean() > 0.9, z.max()
-    # domain-mean x flux (the quantity OctetDomain::average weights): batch means agree within 3 sigma
-    qg, qr = g[:, 1, :].mean(1), r[:, 1, :].mean(1)
-    assert abs(qg.mean() - qr.mean()) <= 3.0 * np.sqrt(qg.var(ddof=1) / B + qr.var(ddof=1) / B)
+    # Domain::average (OctetDomain::WeightF weights exported by the binding): the averaged rows of the batches agree within 3.5 sigma
+    ag = np.stack([fl.average(x)[:, 0] for x in g]); ar = np.stack([fl.average(x)[:, 0] for x in r])
+    sa = np.sqrt(ag.var(0, ddof=1) / B + ar.var(0, ddof=1) / B)
+    assert (np.abs(ag.mean(0) - ar.mean(0)) <= 3.5 * sa).all(), (ag.mean(0), ar.mean(0), sa)
 
 
 def test_bulk_conductivity_within_one_percent(gpu_ctx, omats):

@@ -287,3 +287,19 @@ def test_nonbox_cells_match_the_reference_templates(name, pk, tmp_path):
 @pytest.mark.parametrize("name,dim,dT", [("hex", [1e-6, 5e-8, 8e-8, 3e-8], 1.0), ("pyr", [1e-7, 1e-7, 1e-7], 0.1)])
 def test_hex_and_pyr_domains_match_the_reference(name, dim, dT, tmp_path):
     _compare_with_driver(name, dim, [], dT, orc.Domain.create(name, dim, [], dT), "multi", tmp_path)
+
+
+@pytest.mark.skipif(not refbin.driver_available(), reason="oracle/_ref/ref_driver not built")
+@pytest.mark.parametrize("name", sorted(refcases.REF_ONLY))
+def test_octet_average_weights_reproduce_the_reference_averaged_block(name, tmp_path):
+    """Domain::average for the octet truss: the WeightF weights exported by the binding, applied to the reference's printed
+    Output, give the reference's printed Averaged block (domain.cpp:1252-1280)."""
+    case, g = refcases.REF_ONLY[name], _golden(name)
+    _, (disp, relax) = refcases.write_material(case, str(tmp_path))
+    d = case["dom"]
+    fl = refbin.flatten(disp, relax, case["T"], "octet", d[1:5], d[5:9], d[9], "multi", case["prob"][1], case["prob"][3], outdir=str(tmp_path))
+    out, avg = np.array(g["output"]), np.array(g["averaged"])
+    assert fl.weights is not None and fl.weights.shape == (out.shape[1],) and (fl.weights >= 0).all() and fl.weights.sum() > 0
+    got = fl.average(out)
+    assert got.shape == avg.shape
+    assert np.allclose(got, avg, rtol=5e-9, atol=0)
