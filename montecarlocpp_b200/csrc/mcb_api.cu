@@ -3,6 +3,7 @@
 // Flattens the POD descriptors into device tables, drives the slot schedule (emit/refill + step
 // launches, tail compaction), finalises the field.  No CPU fallback: every entry point needs a
 // working sm_100 device.  Reference citations: file:line relative to /root/reference/montecarlo/.
+#define MCB_AUX_KERNELS
 #include "mcb_kernels.cuh"
 
 #include <algorithm>
@@ -13,6 +14,12 @@
 #include <vector>
 
 using namespace mcb;
+
+namespace mcb {
+cudaError_t launch_step_n1(const StepParams&, int, int, int, int, int, int, size_t, cudaStream_t);
+cudaError_t launch_step_n3(const StepParams&, int, int, int, int, int, int, size_t, cudaStream_t);
+cudaError_t launch_step_n4(const StepParams&, int, int, int, int, int, int, size_t, cudaStream_t);
+}
 
 namespace {
 
@@ -38,6 +45,9 @@ struct DevBuf {
         return e;
     }
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete; DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }                       // scratch buffers of the diagnostic entry points are freed on every return path
 };
 
 // boost::random::discrete_distribution<long,double>: Walker alias table (random.h:26), as used by
@@ -98,10 +108,12 @@ struct mcb_ctx {
     // geometry
     bool has_dom = false; GeometryView gv{}; DevBuf<unsigned char> geo_blob;
     std::vector<DSdom> h_sdom; int nemitter = 0; int any_nd = 0;      // 0 / 1 / 2: see k_step's NDM
+    int all_box = 0;             // every subdomain is an axis-aligned box (k_step's BOX)
+    int t1_ok = 0;               // every 1-D tally grid has unit column stride (the difference-array histograms apply)
     DevBuf<DEmitter> emitters; DevBuf<double> cell_vol; long long cols = 0;
     // problem / run state
     DevBuf<long long> emit_cdf;
-    DevBuf<double> state[2]; DevBuf<unsigned long long> imeta[2]; long long slots_alloc = 0;
+    DevBuf<unsigned char> state[2]; long long slots_alloc = 0;          // warp-tiled slot state (mcb_device.cuh: StateView)
     DevBuf<Counters> ctr; Counters* h_ctr = nullptr;     // pinned mirror
     DevBuf<uint32_t> free_list;
     DevBuf<double> field;
@@ -109,13 +121,7 @@ struct mcb_ctx {
 
 namespace {
 
-StateSoA soa_of(mcb_ctx* c, int which, long long n) {
-    StateSoA s;
-    double* d = c->state[which].p;
-    s.px = d; s.py = d + n; s.pz = d + 2 * n; s.dx = d + 3 * n; s.dy = d + 4 * n; s.dz = d + 5 * n; s.sn = d + 6 * n;
-    s.meta = c->imeta[which].p; s.pidstep = c->imeta[which].p + n;
-    return s;
-}
+StateView view_of(mcb_ctx* c, int which) { return StateView{c->state[which].p}; }
 
 int check_problem(mcb_ctx* c, const mcb_problem_desc* p) {
     if (!p) { c->err = "null problem"; return MCB_EINVAL; }
@@ -137,55 +143,43 @@ int check_problem(mcb_ctx* c, const mcb_problem_desc* p) {
     long long tot = 0;
     for (int i = 0; i < c->nemitter; ++i) { if (p->emit_count[i] < 0) { c->err = "negative emit_count"; return MCB_EINVAL; } tot += p->emit_count[i]; }
     if (tot != p->nemit) { c->err = "nemit != sum(emit_count)"; return MCB_EINVAL; }
-    if (p->maxloop < 0 || p->maxloop > MCB_MAX_LOOP) { c->err = "maxloop out of range (< 2^24)"; return MCB_EINVAL; }
+    if (p->maxloop < 0 || p->maxloop > MCB_MAX_LOOP) { c->err = "maxloop out of range (< 2^28)"; return MCB_EINVAL; }
     if (p->maxscat < 0 || p->maxscat > 0x7FFFFFFFll) { c->err = "maxscat out of range"; return MCB_EINVAL; }
-    if ((unsigned long long)p->nemit > MCB_MAX_PID) { c->err = "nemit out of range (< 2^40)"; return MCB_EINVAL; }
+    if ((unsigned long long)p->nemit > MCB_MAX_PID) { c->err = "nemit out of range (< 2^36)"; return MCB_EINVAL; }
     return MCB_OK;
 }
 
-template <int NCOMP, int TM, int NDM, bool EMIT>
-cudaError_t launch_step_inst(const StepParams& P, int grid, int block, size_t smem, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(k_step<NCOMP, TM, NDM, EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    k_step<NCOMP, TM, NDM, EMIT><<<grid, block, smem, s>>>(P);
-    return cudaGetLastError();
-}
-template <int NCOMP, int TM>
-cudaError_t launch_step_nd(const StepParams& P, int ndm, int grid, int block, size_t smem, cudaStream_t s) {
-    const bool emit = P.free_list == nullptr;          // no free list -> emission happens inside k_step
-    if (ndm == 2) return emit ? launch_step_inst<NCOMP, TM, 2, true>(P, grid, block, smem, s) : launch_step_inst<NCOMP, TM, 2, false>(P, grid, block, smem, s);
-    if (ndm == 1) return emit ? launch_step_inst<NCOMP, TM, 1, true>(P, grid, block, smem, s) : launch_step_inst<NCOMP, TM, 1, false>(P, grid, block, smem, s);
-    return emit ? launch_step_inst<NCOMP, TM, 0, true>(P, grid, block, smem, s) : launch_step_inst<NCOMP, TM, 0, false>(P, grid, block, smem, s);
-}
-template <int NCOMP>
-cudaError_t launch_step_tm(const StepParams& P, int tm, int nd, int grid, int block, size_t smem, cudaStream_t s) {
-    switch (tm) {
-    case MCB_TM_WARP: return launch_step_nd<NCOMP, MCB_TM_WARP>(P, nd, grid, block, smem, s);
-    case MCB_TM_BLOCK: return launch_step_nd<NCOMP, MCB_TM_BLOCK>(P, nd, grid, block, smem, s);
-    default: return launch_step_nd<NCOMP, MCB_TM_GLOBAL>(P, nd, grid, block, smem, s);
-    }
-}
-// payload rows per deposit: Temp/CumTemp 1 (dt), Flux/CumFlux 3 (dpos), Multi 4 (dt, dpos)
-cudaError_t launch_step(const StepParams& P, int tm, int nd, int grid, int block, size_t smem, cudaStream_t s) {
+// payload rows per deposit: Temp/CumTemp 1 (dt), Flux/CumFlux 3 (dpos), Multi 4 (dt, dpos); one translation unit each
+cudaError_t launch_step(const StepParams& P, int tm, int nd, int box, int pad, int grid, int block, size_t smem, cudaStream_t s) {
     switch (P.kind) {
-    case MCB_PROB_TEMP: case MCB_PROB_CUMTEMP: return launch_step_tm<1>(P, tm, nd, grid, block, smem, s);
-    case MCB_PROB_FLUX: case MCB_PROB_CUMFLUX: return launch_step_tm<3>(P, tm, nd, grid, block, smem, s);
-    default: return launch_step_tm<4>(P, tm, nd, grid, block, smem, s);
+    case MCB_PROB_TEMP: case MCB_PROB_CUMTEMP: return mcb::launch_step_n1(P, tm, nd, box, pad, grid, block, smem, s);
+    case MCB_PROB_FLUX: case MCB_PROB_CUMFLUX: return mcb::launch_step_n3(P, tm, nd, box, pad, grid, block, smem, s);
+    default: return mcb::launch_step_n4(P, tm, nd, box, pad, grid, block, smem, s);
     }
 }
 
 int ensure_slots(mcb_ctx* c, long long slots) {
     slots = (slots + 31) / 32 * 32;          // whole warps
     if (slots <= c->slots_alloc) return MCB_OK;
-    for (int w = 0; w < 2; ++w) {
-        CUDA_TRY(c, c->state[w].alloc((size_t)slots * 7));
-        CUDA_TRY(c, c->imeta[w].alloc((size_t)slots * 2));
-    }
+    for (int w = 0; w < 2; ++w) CUDA_TRY(c, c->state[w].alloc(state_bytes(slots)));
     c->slots_alloc = slots;
     return MCB_OK;
 }
 
-struct RunPlan { long long slots; int S, block, grid; int tm, copies; size_t smem; };
+struct RunPlan {
+    long long slots; int S, block, grid; int tm, copies; size_t smem;
+    // 1-D difference-array histograms (tm == MCB_TM_WARP, no N-D grid): padded columns (0 = run-time stride), plane stride,
+    // warps per histogram group, flush interval in loop trips, offset of the flush scratch
+    int t1d, pad, trips; uint32_t ps, inst_bytes, scratch_off, stage_off, wbar_off;
+};
+
+#define MCB_FX_FLUSH_TRIPS 16
+#ifndef MCB_COOP_ND_CELLS
+#define MCB_COOP_ND_CELLS 64      // grids at least this fine along an axis take the warp-cooperative N-D walk
+#endif
+#ifndef MCB_COMPACT_PCT
+#define MCB_COMPACT_PCT 90
+#endif
 
 int plan_run(mcb_ctx* c, const mcb_problem_desc* prob, long long nparticles, RunPlan* r) {
     const mcb_options& o = c->opt;
@@ -209,11 +203,41 @@ int plan_run(mcb_ctx* c, const mcb_problem_desc* prob, long long nparticles, Run
     const long long tiles = (slots + r->block - 1) / r->block;
     r->grid = (int)std::min<long long>((long long)c->sm_count * per_sm, std::max<long long>(tiles, 1));
     const size_t nwarps = (size_t)r->block / 32;
+    r->t1d = 0; r->pad = 0; r->trips = MCB_FX_FLUSH_TRIPS; r->ps = 0; r->inst_bytes = 0; r->scratch_off = 0; r->stage_off = 0; r->wbar_off = 0; r->copies = 1;
+    // 1-D / single-cell tallies: difference-array histograms (mcb_device.cuh: deposit_fx).  An instance holds
+    // [direct | difference][row][limb 0 | 1 | 2] planes of `ps` bytes and is shared by the whole CTA; up to 4 copies (picked by
+    // lane id) thin out same-word hits inside a warp instruction.  The per-warp staging buffers of the TMA state prefetch
+    // come first; copies take what is left.
+    if (c->any_nd == 0 && c->t1_ok && o.tally_mode != 2 && o.tally_mode != 3) {
+        const int pad = c->cols <= 32 ? 32 : (c->cols <= 128 ? 128 : (c->cols <= 512 ? 512 : 0));
+        const uint32_t ps = 4u * (uint32_t)(pad > 0 ? pad : (int)((c->cols + 31) / 32 * 32));
+        const size_t inst = (size_t)prob->rows * 2u * MCB_T1D_LIMBS * ps;
+        const size_t scratch = ((size_t)prob->rows * (size_t)c->cols * 2 + (size_t)prob->rows * (size_t)((c->cols + 31) / 32)) * 8 + 16;
+        const size_t stage = nwarps * (MCB_GROUP_BYTES + 8);
+        for (int st = 1; st >= 0 && !r->t1d; --st)
+            for (int cp = 4; cp >= 1; cp >>= 1)
+                if (base + inst * (size_t)cp + scratch + (st ? stage + 128 : 0) <= budget) {
+                    r->t1d = 1; r->pad = c->all_box ? pad : 0; r->copies = cp; r->ps = ps; r->inst_bytes = (uint32_t)inst;
+                    // an entry receives at most (threads sharing the copy) deposits per loop trip; 2^16 between two flushes
+                    r->trips = (int)std::min<long long>(256, 65536ll / std::max(1, r->block / cp));
+                    r->tm = MCB_TM_WARP;
+                    r->scratch_off = (uint32_t)((base + inst * (size_t)cp + 15) / 16 * 16);
+                    size_t end = r->scratch_off + scratch;
+                    if (st) { r->stage_off = (uint32_t)((end + 127) / 128 * 128); r->wbar_off = r->stage_off + (uint32_t)(nwarps * MCB_GROUP_BYTES); end = r->wbar_off + nwarps * 8; }
+                    r->smem = end;
+                    break;
+                }
+        if (r->t1d) return MCB_OK;
+        if (o.tally_mode == 1) { c->err = "tally_mode=1 (shared-memory histograms) does not fit in shared memory"; return MCB_ELIMIT; }
+    }
     // tally placement: warp-private histograms when they fit, else one per CTA, else the global field in L2
     int tm = MCB_TM_GLOBAL;
-    if (base + hist * nwarps <= budget) tm = MCB_TM_WARP;
+    if (c->any_nd != 0 && base + hist * nwarps <= budget) tm = MCB_TM_WARP;
     else if (base + hist <= budget) tm = MCB_TM_BLOCK;
-    if (o.tally_mode == 1) { tm = MCB_TM_WARP; if (base + hist * nwarps > c->smem_optin) { c->err = "tally_mode=1 (warp histograms) does not fit in shared memory"; return MCB_ELIMIT; } }
+    if (o.tally_mode == 1) {
+        if (c->any_nd == 0) { c->err = "tally_mode=1 needs unit-stride 1-D tally grids"; return MCB_ELIMIT; }
+        tm = MCB_TM_WARP; if (base + hist * nwarps > c->smem_optin) { c->err = "tally_mode=1 (warp histograms) does not fit in shared memory"; return MCB_ELIMIT; }
+    }
     if (o.tally_mode == 3) { tm = MCB_TM_BLOCK; if (base + hist > c->smem_optin) { c->err = "tally_mode=3 (CTA histogram) does not fit in shared memory"; return MCB_ELIMIT; } }
     if (o.tally_mode == 2) tm = MCB_TM_GLOBAL;
     // a kernel built for 512 threads must not be launched with more: the warp-histogram N-D kernel is only reachable with block <= 512
@@ -237,28 +261,28 @@ void fill_params(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, StepPa
     P->so_lambda = P->so_mat + c->mv.off_lambda; P->so_inv_vel = P->so_mat + c->mv.off_inv_vel; P->so_wprob = P->so_mat + c->mv.off_wprob;
     P->so_pprob = P->so_mat + c->mv.off_pprob; P->so_walias = P->so_mat + c->mv.off_walias; P->so_palias = P->so_mat + c->mv.off_palias;
     P->so_hot = P->so_geo + c->gv.off_hot; P->so_cold = P->so_geo + c->gv.off_cold; P->so_sdom = P->so_geo + c->gv.off_sdom; P->so_pairs = P->so_geo + c->gv.off_pairs;
+    P->hist_copies = 1;
+}
+void apply_plan(const RunPlan& plan, const mcb_problem_desc* prob, StepParams* P) {
+    P->tally_smem = plan.tm; P->hist_copies = plan.copies;
+    P->fx_ps = plan.ps; P->fx_diff_off = (uint32_t)prob->rows * MCB_T1D_LIMBS * plan.ps; P->hist_bytes = plan.inst_bytes; P->so_scratch = plan.scratch_off;
+    P->so_stage = plan.stage_off; P->so_wbar = plan.wbar_off;
 }
 
-// Fixed-point scale of the shared-memory tally (mcb_device.cuh: deposit).  Payload component k of a flight is accepted
-// up to fx_max = 2^E > flight_max (* the 99.9 % slowness for the dt row; anything larger takes the exact fp64 path).
-// A histogram is flushed at least every `trips` loop trips (k_step flushes between tiles and the schedule keeps
-// steps_per_launch <= trips), so an entry receives at most N = f * 32 * trips <= 2^n deposits between flushes: f = 1
-// deposit per flight and cell (f = 2 only for the cooperative N-D walk, whose pieces can share a cell).  Each deposit
-// adds q mod 2^B to the low limb and q >> B to the high limb (no carries): B = 32 - n keeps the low sums below 2^32, and
-// |q| <= 2^(Q-1) with Q = 63 - 2n keeps the high sums inside int32.  16 trips -> n = 9, B = 23, Q = 45: quantum
-// 2^-44 of fx_max.  (An in-kernel flush every `trips` trips of a longer tile was measured: the extra code in the hot
-// loop costs more -- registers -- than the carry-free limbs gain, so the tail runs in launches of `trips` trips.)
-#define MCB_FX_FLUSH_TRIPS 16
-#ifndef MCB_COOP_ND_CELLS
-#define MCB_COOP_ND_CELLS 64      // grids at least this fine along an axis take the warp-cooperative N-D walk
-#endif
-#ifndef MCB_COMPACT_PCT
-#define MCB_COMPACT_PCT 90
-#endif
-void set_fixed_point(mcb_ctx* c, const mcb_problem_desc* prob, StepParams* P) {
-    const long long bound = (c->any_nd == 2 ? 2ll : 1ll) * 32ll * MCB_FX_FLUSH_TRIPS;
+// Fixed-point scale of the shared-memory tallies.  Payload component k of a flight is accepted up to fx_max = 2^E >
+// flight_max (* the 99.9 % slowness for the dt row; anything larger takes the exact fp64 path) and deposited as
+// q = rint(v 2^(Q-1-E)), |q| <= 2^(Q-1).  A histogram is flushed at least every `trips` loop trips (k_step flushes between
+// tiles and the schedule keeps steps_per_launch <= trips), so an entry receives at most N <= 2^n deposits between flushes.
+//  * N-D walks, warp-private two-limb histograms (mcb_device.cuh: deposit): N = f x 32 lanes x 16 trips, f = 1 deposit per
+//    flight and cell (3 for the cooperative N-D walk, whose pieces can share a cell); low limb B = 32 - n bits, Q = 63 - 2n
+//    (n = 9: B = 23, Q = 45).
+//  * 1-D difference-array histograms, three limbs shared by the CTA (deposit_fx): N = (threads per copy) x trips <= 2^16,
+//    Q = 64 - n capped at 50 (the rounding trick holds |q| < 2^51): quantum 2^-47 .. 2^-49 of fx_max.
+void set_fixed_point(mcb_ctx* c, const mcb_problem_desc* prob, const RunPlan& plan, StepParams* P) {
+    const long long bound = plan.t1d ? (long long)std::max(1, plan.block / plan.copies) * plan.trips
+                                     : (c->any_nd == 2 ? 3ll : 1ll) * 32ll * plan.trips;
     int n = 0; while ((1ll << n) < bound) ++n;                                             // bound <= 2^n
-    const int B = 32 - n, QB = std::min(50, 63 - 2 * n);
+    const int B = 32 - n, QB = plan.t1d ? std::min(50, 64 - n) : std::min(50, 63 - 2 * n);
     P->fx_limb_bits = B;
     for (int k = 0; k < 4; ++k) {
         const bool is_dt = (prob->kind == MCB_PROB_TEMP || prob->kind == MCB_PROB_CUMTEMP || prob->kind == MCB_PROB_MULTI) && k == 0;
@@ -267,7 +291,7 @@ void set_fixed_point(mcb_ctx* c, const mcb_problem_desc* prob, StepParams* P) {
         const int E = e;
         P->fx_max[k] = std::ldexp(1.0, E); P->fx_scale[k] = std::ldexp(1.0, QB - 1 - E); P->fx_inv[k] = std::ldexp(1.0, E + 1 - QB);
     }
-    P->fx_flush_trips = MCB_FX_FLUSH_TRIPS;
+    P->fx_flush_trips = plan.trips;
 }
 
 int upload_cdf(mcb_ctx* c, const mcb_problem_desc* prob) {
@@ -297,14 +321,15 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
     if (rc) return rc;
 
     StepParams P; fill_params(c, prob, seed, &P);
-    P.field = raw_field_dev; P.tally_smem = plan.tm; P.hist_copies = plan.copies; P.do_tally = 1; P.refill = 1;
+    P.field = raw_field_dev; P.do_tally = 1;
     P.steps_per_launch = plan.S; P.n_end = (unsigned long long)n_end;
-    set_fixed_point(c, prob, &P);
+    apply_plan(plan, prob, &P);
+    set_fixed_point(c, prob, plan, &P);
 
     Counters init{}; init.next = (unsigned long long)n_begin;
     CUDA_TRY(c, cudaMemcpyAsync(c->ctr.p, &init, sizeof init, cudaMemcpyHostToDevice, c->stream));
     int cur = 0; long long nslots = plan.slots;
-    CUDA_TRY(c, cudaMemsetAsync(c->imeta[cur].p, 0, (size_t)nslots * sizeof(unsigned long long), c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(c->state[cur].p, 0, state_bytes(nslots), c->stream));        // every slot inactive
 
     long long launches = 0, step_launches = 0, slot_steps = 0;
     CUDA_TRY(c, cudaEventRecord(c->ev0, c->stream));
@@ -315,9 +340,8 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
     // previous launch; after the last particle dies one extra, empty launch has already been queued.
     const long long tail_slots = (long long)plan.grid * plan.block;      // one tile per CTA: finish in one launch
     int S_cur = plan.S;
-    // dense emission (default): k_step only lists free slots, k_emit fills them between launches; emit_mode = 1
-    // selects emission inside k_step instead
-    const bool dense = c->opt.emit_mode != 1;
+    // dense emission: k_step only lists free slots, k_emit fills them between launches
+    const bool dense = true;
     const long long compact_pct = c->opt.compact_pct > 0 ? c->opt.compact_pct : MCB_COMPACT_PCT;
     bool host_all_emitted = false;
     if (dense) {
@@ -332,8 +356,8 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
     if (total > 0) for (long long it = 0;; ++it) {
         const int slot = (int)(it & 1);
         // fixed-point histograms are flushed between tiles: keep a tile's loop trips within the flush interval
-        if (MCB_TALLY_FX && plan.tm == MCB_TM_WARP) S_cur = std::min(S_cur, MCB_FX_FLUSH_TRIPS);
-        P.st = soa_of(c, cur, c->slots_alloc); P.nslots = nslots; P.steps_per_launch = S_cur;
+        if (MCB_TALLY_FX && plan.tm == MCB_TM_WARP) S_cur = std::min(S_cur, plan.trips);
+        P.st = view_of(c, cur); P.nslots = nslots; P.steps_per_launch = S_cur;
         if (dense && !host_all_emitted) {
             // K1: fill the free slots listed by the previous k_step (all of them before the first), with full warps
             k_emit<<<(unsigned)(c->sm_count * 4), 256, 0, c->stream>>>(P);
@@ -345,7 +369,7 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
         const long long tiles = (nslots + plan.block - 1) / plan.block;
         const int grid = (int)std::min<long long>(plan.grid, std::max<long long>(tiles, 1));
         CUDA_TRY(c, cudaEventRecord(c->evA[slot], c->stream));
-        CUDA_TRY(c, launch_step(P, plan.tm, c->any_nd, grid, plan.block, plan.smem, c->stream));
+        CUDA_TRY(c, launch_step(P, plan.tm, c->any_nd, c->all_box, plan.pad, grid, plan.block, plan.smem, c->stream));
         CUDA_TRY(c, cudaEventRecord(c->evB[slot], c->stream));
         CUDA_TRY(c, cudaMemcpyAsync(&c->h_ctr[slot], c->ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(c, cudaEventRecord(c->evC[slot], c->stream));
@@ -373,9 +397,9 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
             const int other = cur ^ 1;
             const long long bound = std::max<long long>((long long)live, 1);
             CUDA_TRY(c, cudaMemsetAsync(&c->ctr.p->compact_cursor, 0, sizeof(unsigned long long), c->stream));
-            CUDA_TRY(c, cudaMemsetAsync(c->imeta[other].p, 0, (size_t)bound * sizeof(unsigned long long), c->stream));
+            CUDA_TRY(c, cudaMemsetAsync(c->state[other].p, 0, state_bytes(bound), c->stream));
             k_compact<<<(unsigned)std::min<long long>((nslots + 255) / 256, (long long)c->sm_count * 8), 256, 0, c->stream>>>(
-                soa_of(c, cur, c->slots_alloc), soa_of(c, other, c->slots_alloc), nslots, c->ctr.p);
+                view_of(c, cur), view_of(c, other), nslots, c->ctr.p);
             CUDA_TRY(c, cudaGetLastError());
             launches++;
             cur = other; nslots = bound;
@@ -457,7 +481,7 @@ void mcb_destroy(mcb_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->mat_blob.release(); c->f_wprob.release(); c->f_pprob.release(); c->f_walias.release(); c->f_palias.release();
     c->geo_blob.release(); c->emitters.release(); c->cell_vol.release(); c->emit_cdf.release();
-    for (int w = 0; w < 2; ++w) { c->state[w].release(); c->imeta[w].release(); }
+    for (int w = 0; w < 2; ++w) c->state[w].release();
     c->ctr.release(); c->field.release(); c->free_list.release();
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
     if (c->ev0) cudaEventDestroy(c->ev0); if (c->ev1) cudaEventDestroy(c->ev1);
@@ -468,7 +492,7 @@ void mcb_destroy(mcb_ctx* c) {
 
 int mcb_set_options(mcb_ctx* c, const mcb_options* o) {
     if (!c || !o) return MCB_EINVAL;
-    if (o->slots < 0 || o->steps_per_launch < 0 || o->block < 0 || o->ctas_per_sm < 0 || o->tally_mode < 0 || o->tally_mode > 3 || o->decay_mode < 0 || o->decay_mode > 1 || o->emit_mode < 0 || o->emit_mode > 1 || o->compact_pct < 0 || o->compact_pct > 100) {
+    if (o->slots < 0 || o->steps_per_launch < 0 || o->block < 0 || o->ctas_per_sm < 0 || o->tally_mode < 0 || o->tally_mode > 3 || o->decay_mode < 0 || o->decay_mode > 1 || o->emit_mode != 0 || o->compact_pct < 0 || o->compact_pct > 100) {
         c->err = "negative / unknown option"; return MCB_EINVAL;
     }
     c->opt = *o;
@@ -571,6 +595,7 @@ int mcb_upload_domain(mcb_ctx* c, const mcb_domain_desc* d) {
     }
     for (int i = 0; i < d->npair; ++i) if (d->pairs[i] < 0 || d->pairs[i] >= d->nplane) { c->err = "pair id out of range"; return MCB_EINVAL; }
     std::vector<DSdom> sd(d->nsdom); std::vector<double> cell_vol; int any_nd = 0; double flight_max = 0.0;
+    int all_box = 1, t1_ok = 1;
     long long cols = 0;
     for (int s = 0; s < d->nsdom; ++s) {
         const mcb_sdom_desc& S = d->sdoms[s]; DSdom& D = sd[s]; std::memset(&D, 0, sizeof D);
@@ -590,11 +615,28 @@ int mcb_upload_domain(mcb_ctx* c, const mcb_domain_desc* d) {
             for (int k = 0; k < 3; ++k) if (pl.normal[k] != (k == b ? 1.0 : 0.0)) D.aabb = 0;
         }
         for (int b = 0; b < 3; ++b) { D.offl[b] = d->planes[S.plane_begin + b].offset; D.offh[b] = D.is_box ? d->planes[S.plane_begin + b + 3].offset : 0.0; }
+        if (!D.aabb) all_box = 0;
+        if (S.accum >= 0 && S.accum <= 2) {          // 1-D tally grid along axis `accum` (subdomain.cpp:47-70)
+            const int ax = S.accum;
+            D.t1_axis = ax; D.t1_o = S.origin[ax]; D.t1_inv = S.inv[4 * ax]; D.t1_div = (double)S.div[ax]; D.t1_max = (int32_t)S.max[ax];
+            const long long stride = ax == 0 ? 1 : (ax == 1 ? S.shape[0] : S.shape[0] * S.shape[1]);
+            if (stride != 1) t1_ok = 0;
+            if (D.aabb) for (int k = 0; k < 3; ++k) if (k != ax && S.inv[ax + 3 * k] != 0.0) all_box = 0;   // inv_ row must be diagonal for the 1-term coord
+        }
         {   // a flight stays inside its (convex) subdomain: its length is bounded by the sum of the edge-vector lengths
             double diam = 0.0;
             const int ncol = S.nbase > 0 ? std::min<int>(S.nbase, MCB_MAX_BASE) : 3;
             const double* cols3 = S.nbase > 0 ? S.base : S.mat;
             for (int k = 0; k < ncol; ++k) diam += std::sqrt(cols3[3 * k] * cols3[3 * k] + cols3[3 * k + 1] * cols3[3 * k + 1] + cols3[3 * k + 2] * cols3[3 * k + 2]);
+            if (S.cell == MCB_CELL_PARALLELEPIPED && S.nbase <= 0) {      // parallelepiped: the longest of its four body diagonals
+                double best = 0.0;
+                for (int sg = 0; sg < 4; ++sg) {
+                    double v[3];
+                    for (int k = 0; k < 3; ++k) v[k] = S.mat[k] + ((sg & 1) ? -1.0 : 1.0) * S.mat[3 + k] + ((sg & 2) ? -1.0 : 1.0) * S.mat[6 + k];
+                    best = std::max(best, std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]));
+                }
+                diam = std::min(diam, best * (1.0 + 1e-12));
+            }
             flight_max = std::max(flight_max, diam + 4.0 * std::fabs(S.eps));
         }
         if (S.accum >= 3) any_nd = std::max(any_nd, (S.shape[0] >= MCB_COOP_ND_CELLS || S.shape[1] >= MCB_COOP_ND_CELLS || S.shape[2] >= MCB_COOP_ND_CELLS) ? 2 : 1);
@@ -681,6 +723,7 @@ int mcb_upload_domain(mcb_ctx* c, const mcb_domain_desc* d) {
     CUDA_TRY(c, c->cell_vol.alloc(cell_vol.size()));
     if (!cell_vol.empty()) CUDA_TRY(c, cudaMemcpy(c->cell_vol.p, cell_vol.data(), cell_vol.size() * 8, cudaMemcpyHostToDevice));
     c->gv = v; c->h_sdom = sd; c->nemitter = d->nemitter; c->cols = cols; c->any_nd = any_nd; c->flight_max = flight_max; c->has_dom = true;
+    c->all_box = all_box; c->t1_ok = t1_ok;
     return MCB_OK;
 }
 
@@ -740,6 +783,8 @@ int mcb_trace(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
     const long long n = n_end - n_begin;
     if (n == 0) return MCB_OK;
     CUDA_TRY(c, cudaSetDevice(c->device));
+    // the production kernels without the tally: every particle of the range is emitted into its own slot (k_emit), then
+    // one k_step launch runs `nsteps` loop trips
     RunPlan plan;
     mcb_options saved = c->opt; c->opt.slots = n; c->opt.tally_mode = 2; c->opt.block = 0;
     rc = plan_run(c, prob, n, &plan);
@@ -747,15 +792,22 @@ int mcb_trace(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
     if (rc) return rc;
     if ((rc = ensure_slots(c, n))) return rc;
     if ((rc = upload_cdf(c, prob))) return rc;
+    CUDA_TRY(c, c->free_list.alloc((size_t)c->slots_alloc));
     StepParams P; fill_params(c, prob, seed, &P);
+    apply_plan(plan, prob, &P);
     P.maxloop = std::min<long long>(prob->maxloop, nsteps);
-    P.field = nullptr; P.tally_smem = 0; P.hist_copies = 1; P.do_tally = 0; P.refill = 0;
+    P.field = nullptr; P.do_tally = 0;
     P.steps_per_launch = (int)std::max<long long>(1, std::min<long long>(P.maxloop, 0x7FFFFFFF)); P.n_end = (unsigned long long)n_end;
-    P.st = soa_of(c, 0, c->slots_alloc); P.nslots = n;
+    P.st = view_of(c, 0); P.nslots = n; P.free_list = c->free_list.p;
     Counters init{}; init.next = (unsigned long long)n_begin;
     CUDA_TRY(c, cudaMemcpyAsync(c->ctr.p, &init, sizeof init, cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(c, cudaMemsetAsync(c->imeta[0].p, 0, (size_t)c->slots_alloc * 2 * sizeof(unsigned long long), c->stream));
-    CUDA_TRY(c, launch_step(P, MCB_TM_GLOBAL, c->any_nd, plan.grid, plan.block, plan.smem, c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(c->state[0].p, 0, state_bytes(c->slots_alloc), c->stream));
+    k_free_init<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->free_list.p, n, c->ctr.p);
+    k_emit<<<(unsigned)(c->sm_count * 4), 256, 0, c->stream>>>(P);
+    k_emit_commit<<<1, 1, 0, c->stream>>>(c->ctr.p, (unsigned long long)n_end);
+    CUDA_TRY(c, cudaGetLastError());
+    P.free_list = nullptr;                                   // nothing to list afterwards
+    if (P.maxloop > 0) CUDA_TRY(c, launch_step(P, plan.tm, c->any_nd, c->all_box, plan.pad, plan.grid, plan.block, plan.smem, c->stream));
     DevBuf<double> dpos, ddir, dsn; DevBuf<long long> dw, dp, dnscat, dsteps; DevBuf<int32_t> dsign, dalive, dsdom, dcell;
     CUDA_TRY(c, dpos.alloc(3 * n)); CUDA_TRY(c, ddir.alloc(3 * n)); CUDA_TRY(c, dsn.alloc(n));
     CUDA_TRY(c, dw.alloc(n)); CUDA_TRY(c, dp.alloc(n)); CUDA_TRY(c, dnscat.alloc(n)); CUDA_TRY(c, dsteps.alloc(n));

@@ -40,17 +40,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t phase) {
     return ok != 0;
 }
 
-// streaming state access: keep L1 for the tables' spill-over, do not allocate state lines
-__device__ __forceinline__ double ld_stream(const double* p) {
-    double v; asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v;
+// streaming state access (warp-tiled layout, mcb_device.cuh: StateView): 128-bit accesses that do not allocate in L1
+__device__ __forceinline__ void ld_stream2(const void* p, double& a, double& b) {
+    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(p));
 }
-__device__ __forceinline__ unsigned long long ld_stream(const unsigned long long* p) {
-    unsigned long long v; asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p)); return v;
+__device__ __forceinline__ void ld_stream2(const void* p, double& a, unsigned long long& b) {
+    asm volatile("ld.global.L1::no_allocate.v2.b64 {%0, %1}, [%2];" : "=d"(a), "=l"(b) : "l"(p));
 }
-__device__ __forceinline__ void st_stream(double* p, double v) {
-    asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+__device__ __forceinline__ unsigned long long ld_stream1(const void* p) {
+    unsigned long long v; asm volatile("ld.global.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p)); return v;
 }
-__device__ __forceinline__ void st_stream(unsigned long long* p, unsigned long long v) {
+__device__ __forceinline__ void st_stream2(void* p, double a, double b) {
+    asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+}
+__device__ __forceinline__ void st_stream2(void* p, double a, unsigned long long b) {
+    asm volatile("st.global.L1::no_allocate.v2.b64 [%0], {%1, %2};" ::"l"(p), "d"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ void st_stream1(void* p, unsigned long long v) {
     asm volatile("st.global.L1::no_allocate.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
@@ -61,24 +67,59 @@ struct Particle {
     double px, py, pz, dx, dy, dz, sn;
     uint32_t mlo;                 // wp:20 | sign:1 | active:1 | killed:1 | sdom:9   (low word of meta)
     uint32_t nscat;               // high word of meta
-    unsigned long long ps;        // pid:40 | step:24
+    unsigned long long ps;        // pid:36 | step:28
     __device__ __forceinline__ uint32_t wp() const { return mlo & 0xFFFFFu; }
     __device__ __forceinline__ bool sign() const { return (mlo >> 20) & 1u; }
     __device__ __forceinline__ bool active() const { return (mlo >> 21) & 1u; }
     __device__ __forceinline__ bool killed() const { return (mlo >> 22) & 1u; }
     __device__ __forceinline__ uint32_t sdom() const { return mlo >> 23; }
-    __device__ __forceinline__ uint32_t step() const { return (uint32_t)ps & 0xFFFFFFu; }
-    __device__ __forceinline__ unsigned long long pid() const { return ps >> 24; }
-    __device__ __forceinline__ uint32_t pid_lo() const { return (uint32_t)(ps >> 24); }
-    __device__ __forceinline__ uint32_t pid_hi() const { return (uint32_t)(ps >> 56); }
+    __device__ __forceinline__ uint32_t step() const { return (uint32_t)ps & ((1u << MCB_STEP_BITS) - 1u); }
+    __device__ __forceinline__ unsigned long long pid() const { return ps >> MCB_STEP_BITS; }
+    __device__ __forceinline__ uint32_t pid_lo() const { return (uint32_t)(ps >> MCB_STEP_BITS); }
+    __device__ __forceinline__ uint32_t pid_hi() const { return (uint32_t)(ps >> (32 + MCB_STEP_BITS)); }
     __device__ __forceinline__ void set_wp(uint32_t v) { mlo = (mlo & ~0xFFFFFu) | v; }
     __device__ __forceinline__ void set_sdom(uint32_t v) { mlo = (mlo & 0x7FFFFFu) | (v << 23); }
     __device__ __forceinline__ void stop() { mlo &= ~(1u << 21); }                       // alive but finished (or never started)
     __device__ __forceinline__ void kill() { mlo = (mlo | (1u << 22)) & ~(1u << 21); }  // Phonon::kill phonon.cpp:47-50
     __device__ __forceinline__ void init(uint32_t wp_, bool sign_, bool active_, uint32_t sdom_, unsigned long long pid_) {
-        mlo = wp_ | ((uint32_t)sign_ << 20) | ((uint32_t)active_ << 21) | (sdom_ << 23); nscat = 0; ps = pid_ << 24;
+        mlo = wp_ | ((uint32_t)sign_ << 20) | ((uint32_t)active_ << 21) | (sdom_ << 23); nscat = 0; ps = pid_ << MCB_STEP_BITS;
     }
     __device__ __forceinline__ unsigned long long meta() const { return (unsigned long long)mlo | ((unsigned long long)nscat << 32); }
+    // the slot's bytes: four 16-B vectors at v, v+512, v+1024, v+1536 and the 8-B pid|step word at w (StateView layout)
+    static __device__ __forceinline__ unsigned char* vec_ptr(const StateView& st, long long i) {
+        return st.base + (i >> 5) * MCB_GROUP_BYTES + (i & 31) * 16;
+    }
+    static __device__ __forceinline__ unsigned char* word_ptr(const StateView& st, long long i) {
+        return st.base + (i >> 5) * MCB_GROUP_BYTES + 2048 + (i & 31) * 8;
+    }
+    __device__ __forceinline__ unsigned long long load(const StateView& st, long long i) {       // returns the raw meta word
+        const unsigned char* v = vec_ptr(st, i);
+        unsigned long long m;
+        ld_stream2(v, px, py); ld_stream2(v + 512, pz, dx); ld_stream2(v + 1024, dy, dz); ld_stream2(v + 1536, sn, m);
+        ps = ld_stream1(word_ptr(st, i));
+        mlo = (uint32_t)m; nscat = (uint32_t)(m >> 32);
+        return m;
+    }
+    // the same slot out of a staged copy of its 2304-B group in shared memory (k_step's TMA prefetch)
+    __device__ __forceinline__ void load_shared(const unsigned char* buf, unsigned lane) {
+        const double2 a = *reinterpret_cast<const double2*>(buf + lane * 16), b = *reinterpret_cast<const double2*>(buf + 512 + lane * 16);
+        const double2 c = *reinterpret_cast<const double2*>(buf + 1024 + lane * 16);
+        const ulonglong2 d = *reinterpret_cast<const ulonglong2*>(buf + 1536 + lane * 16);
+        ps = *reinterpret_cast<const unsigned long long*>(buf + 2048 + lane * 8);
+        px = a.x; py = a.y; pz = b.x; dx = b.y; dy = c.x; dz = c.y; sn = __longlong_as_double((long long)d.x);
+        mlo = (uint32_t)d.y; nscat = (uint32_t)(d.y >> 32);
+    }
+    __device__ __forceinline__ void store(const StateView& st, long long i) const {
+        unsigned char* v = vec_ptr(st, i);
+        st_stream2(v, px, py); st_stream2(v + 512, pz, dx); st_stream2(v + 1024, dy, dz); st_stream2(v + 1536, sn, meta());
+        st_stream1(word_ptr(st, i), ps);
+    }
+    static __device__ __forceinline__ unsigned long long load_meta(const StateView& st, long long i) {
+        return *reinterpret_cast<const unsigned long long*>(vec_ptr(st, i) + 1536 + 8);
+    }
+    static __device__ __forceinline__ void clear_meta(const StateView& st, long long i) {          // marks the slot inactive
+        *reinterpret_cast<unsigned long long*>(vec_ptr(st, i) + 1536 + 8) = 0ull;
+    }
 };
 
 // Material::Dist::drawProp (material.cpp:71-75) on the two-level Walker tables; entry (w,p) at w*np+p
@@ -155,7 +196,7 @@ __device__ __forceinline__ void emit_from(const DEmitter& E, Rng& g, Particle& p
 }
 
 // problem.cpp:386-399 for particle `pid`: pick emitter, drawFluxProp, Emitter::emit, drawScatNext
-__device__ __noinline__ void emit_particle(const StepParams& P, const Tables& T, unsigned long long pid, Particle& ph) {
+static __device__ __noinline__ void emit_particle(const StepParams& P, const Tables& T, unsigned long long pid, Particle& ph) {
     // emitter = upper_bound(emitCdf, n)  (problem.cpp:386-387)
     int lo = 0, hi = P.nemitter;
     while (lo < hi) { int mid = (lo + hi) >> 1; if ((long long)pid < P.emit_cdf[mid]) hi = mid; else lo = mid + 1; }
@@ -167,13 +208,15 @@ __device__ __noinline__ void emit_particle(const StepParams& P, const Tables& T,
     ph.sn = draw_scat_next(g, T.lambda[wp]);
 }
 
-// Subdomain::isInside subdomain.cpp:108-116
+// Subdomain::isInside subdomain.cpp:108-116.  BOX: every subdomain of the domain is an axis-aligned box (the host checks).
+template <bool BOX>
 __device__ __forceinline__ bool is_inside(const Tables& T, const DSdom& sd, double x, double y, double z) {
     bool in = true;
-    if (sd.aabb) {                   // axis-aligned box: n_b.x is x[b]
+    if (BOX || sd.aabb) {            // axis-aligned box: n_b.x is x[b]
         const double p3[3] = {x, y, z};
+        const double neps = -sd.eps;
 #pragma unroll
-        for (int b = 0; b < 3; ++b) in = in && !(p3[b] + sd.offl[b] < -sd.eps) && !(sd.offh[b] - p3[b] < -sd.eps);
+        for (int b = 0; b < 3; ++b) in = in && !(p3[b] + sd.offl[b] < neps) && !(sd.offh[b] - p3[b] < neps);
         return in;
     }
     if (sd.is_box) {                 // planes b and b+3 share n.pos up to sign: three dot products
@@ -200,28 +243,29 @@ struct Segment {                  // what one advect produced
 };
 
 // First half of a loop trip (problem.cpp:403-412): Subdomain::advect + Phonon::move.  Returns escapes (0/1).
+template <bool BOX>
 __device__ __forceinline__ uint32_t advect_move(const Tables& T, Particle& ph, Segment& sg) {
     const DSdom& sd = T.sdom[ph.sdom()];
     // Subdomain::advect subdomain.cpp:161-192
     double d = ph.sn; int hit = -1;
-    if (sd.aabb) {
-        // axis-aligned box (every shipped domain): n_b = +e_b, n_{b+3} = -e_b, so n.dir and n.pos are single
-        // components -- the same values the dot products produce, without the multiplies by 0 and 1
+    if (BOX || sd.aabb) {
+        // Axis-aligned box (every shipped domain): n_b = +e_b, n_{b+3} = -e_b, so n.dir and n.pos are single components
+        // -- the very values the dot products produce.  Per axis at most one face is approached: face b when dir_b < 0,
+        //   t = -(off_b + pos_b) / dir_b = (off_b + pos_b) / |dir_b|, else face b+3, t = (off_{b+3} - pos_b) / |dir_b|
+        // (boundary.cpp:107-110; same operations, the two sign flips cancel exactly).  dir_b = 0 gives NaN or +inf,
+        // which loses every comparison.  Candidates are taken in the reference's declaration order (faces 0,1,2,3,4,5)
+        // with its strict `<`: among equal distances the lowest face index wins, and a tie with scatNext scatters.
         const double dr[3] = {ph.dx, ph.dy, ph.dz}, ps[3] = {ph.px, ph.py, ph.pz};
-        double t3[3]; int id3[3];
+        int key = 6;
 #pragma unroll
         for (int b = 0; b < 3; ++b) {
-            const double c = dr[b], s = ps[b];
-            const bool front = c < 0.0;
-            const double num = front ? -(sd.offl[b] + s) : -(sd.offh[b] - s);
-            const double den = front ? c : -c;
-            t3[b] = num / den;
-            id3[b] = c == 0.0 ? -1 : (front ? b : b + 3);
+            const bool front = dr[b] < 0.0;
+            const double num = front ? sd.offl[b] + ps[b] : sd.offh[b] - ps[b];
+            const double t = div_fast(num, fabs(dr[b]));
+            const int k = front ? b : b + 3;
+            if (t < d || (t == d && k < key)) { d = t; key = k; }
         }
-#pragma unroll
-        for (int b = 0; b < 3; ++b) if (id3[b] == b && t3[b] < d) { d = t3[b]; hit = sd.plane_begin + b; }
-#pragma unroll
-        for (int b = 0; b < 3; ++b) if (id3[b] == b + 3 && t3[b] < d) { d = t3[b]; hit = sd.plane_begin + b + 3; }
+        if (key < 6) hit = sd.plane_begin + key;
     } else if (sd.is_box) {
         // A parallelepiped's faces b and b+3 have exactly opposite normals, so n.dir < 0 holds for at most one
         // of each pair: three divisions, no divergence.  Candidates are then compared in the reference's
@@ -254,21 +298,50 @@ __device__ __forceinline__ uint32_t advect_move(const Tables& T, Particle& ph, S
     }
     // Phonon::move phonon.cpp:95-105
     double sn = ph.sn - d;
-    if (sn < 2.2250738585072014e-308) sn = 0.0;
+    if (sn < c_k[27]) sn = 0.0;
     ph.sn = sn;
     sg.bx = ph.px; sg.by = ph.py; sg.bz = ph.pz;
     sg.ex = sg.bx + ph.dx * d; sg.ey = sg.by + ph.dy * d; sg.ez = sg.bz + ph.dz * d;
     ph.px = sg.ex; ph.py = sg.ey; ph.pz = sg.ez;
     sg.d = d; sg.hit = hit; sg.nscat_before = ph.nscat;
     ph.ps++;                                                                   // step is the low field of ps
-    if (d < -sd.eps || !is_inside(T, sd, sg.ex, sg.ey, sg.ez)) {              // subdomain.cpp:182-189
+    if (d < -sd.eps || !is_inside<BOX>(T, sd, sg.ex, sg.ey, sg.ez)) {         // subdomain.cpp:182-189
         ph.kill(); sg.ok = false; return 1u;                                  // problem.cpp:408-412
     }
     sg.ok = true;
     return 0u;
 }
 
+// The random part of Material::scatter (material.cpp:226-231): its seven words (w int, w real, p int, p real, iso mu,
+// iso phi, free path) sit at fixed positions of two Philox blocks, valid when no draw is rejected (probability ~ nw / 2^32);
+// a rejection (ok = false) replays the event through the sequential generator in collide(), so the consumed stream is
+// always the CPU oracle's.  (Drawing the event ahead of the flight, to interleave its dependency chain with advect / tally,
+// was measured: -4 ... -14 %, the extra live registers cost more than the overlap gains.)
+struct Draw {
+    uint32_t wp; double dx, dy, dz, dist; bool ok;
+};
+__device__ __forceinline__ void draw_event(const StepParams& P, const Tables& T, uint32_t pid_lo, uint32_t pid_hi, uint32_t event, Draw& o) {
+    uint32_t a[4], b[4];
+    philox4x32_10(pid_lo, pid_hi, event, 0u, (uint32_t)P.seed, (uint32_t)(P.seed >> 32), a);
+    philox4x32_10(pid_lo, pid_hi, event, 1u, (uint32_t)P.seed, (uint32_t)(P.seed >> 32), b);
+    uint32_t r = (uint32_t)(((double)a[0] + 0.5) * T.inv_bucket_w);
+    uint32_t q = (uint32_t)(((double)a[2] + 0.5) * T.inv_bucket_p);
+    bool ok = r < (uint32_t)T.nw && q < (uint32_t)T.np;
+    r = min(r, (uint32_t)T.nw - 1u); q = min(q, (uint32_t)T.np - 1u);
+    const uint32_t w = (double)a[1] * c_k[25] < T.wprob[r] ? r : (uint32_t)T.walias[r];
+    const uint32_t k = w * (uint32_t)T.np + q;
+    const uint32_t wp = (double)a[3] * c_k[25] < T.pprob[k] ? k : w * (uint32_t)T.np + (uint32_t)T.palias[k];
+    const double c = fma((double)b[0], c_k[26], -1.0);                // drawIso random.cpp:16-27
+    const double sth = sqrt(fma(-c, c, 1.0));
+    double sp, cp; sincospi_unit(fma((double)b[1], c_k[26], -1.0), &sp, &cp);
+    const double dist = T.lambda[wp] * neg_log1m_u32(b[2]);           // drawScatNext material.cpp:215-224
+    o.ok = ok && !(dist < c_k[27]);
+    o.wp = wp; o.dx = sth * cp; o.dy = sth * sp; o.dz = c; o.dist = dist;
+    renorm_drawn(o.dx, o.dy, o.dz);
+}
+
 // Second half of a loop trip (problem.cpp:418-434): Boundary::scatter or Material::scatter, then the stop test.
+template <bool BOX>
 __device__ __forceinline__ uint32_t collide(const StepParams& P, const Tables& T, Particle& ph, Segment& sg) {
     uint32_t esc = 0;
     const int hit = sg.hit;
@@ -300,7 +373,7 @@ __device__ __forceinline__ uint32_t collide(const StepParams& P, const Tables& T
             if (cb.pair_count == 1) target = T.pairs[cb.pair_begin];
             else for (int q = 0; q < cb.pair_count && target < 0; ++q) {
                 const int cand = T.pairs[cb.pair_begin + q];
-                if (is_inside(T, T.sdom[T.cold[cand].sdom], sg.ex, sg.ey, sg.ez)) target = cand;
+                if (is_inside<BOX>(T, T.sdom[T.cold[cand].sdom], sg.ex, sg.ey, sg.ez)) target = cand;
             }
             if (target < 0) { ph.kill(); esc = 1; }                            // problem.cpp:422-426
             else ph.set_sdom((uint32_t)T.cold[target].sdom);
@@ -309,35 +382,19 @@ __device__ __forceinline__ uint32_t collide(const StepParams& P, const Tables& T
             ph.kill();
         }
     } else {                                                                   // Material::scatter material.cpp:226-231
-        // Fast path: the event's seven words (w int, w real, p int, p real, iso mu, iso phi, free path) come from two
-        // Philox blocks at fixed positions, valid when no draw is rejected (probability ~ nw / 2^32); any rejection
-        // replays the event through the sequential generator so the stream stays identical to the CPU's.
-        bool fast = T.nw > 1 && T.np > 1;
-        if (fast) {
-            uint32_t a[4], b[4];
-            philox4x32_10(ph.pid_lo(), ph.pid_hi(), ph.step(), 0u, (uint32_t)P.seed, (uint32_t)(P.seed >> 32), a);
-            philox4x32_10(ph.pid_lo(), ph.pid_hi(), ph.step(), 1u, (uint32_t)P.seed, (uint32_t)(P.seed >> 32), b);
-            uint32_t r = (uint32_t)(((double)a[0] + 0.5) * T.inv_bucket_w);
-            uint32_t q = (uint32_t)(((double)a[2] + 0.5) * T.inv_bucket_p);
-            fast = r < (uint32_t)T.nw && q < (uint32_t)T.np;
-            r = min(r, (uint32_t)T.nw - 1u); q = min(q, (uint32_t)T.np - 1u);
-            const uint32_t w = (double)a[1] * (1.0 / 4294967296.0) < T.wprob[r] ? r : (uint32_t)T.walias[r];
-            const uint32_t k = w * (uint32_t)T.np + q;
-            const uint32_t wp = (double)a[3] * (1.0 / 4294967296.0) < T.pprob[k] ? k : w * (uint32_t)T.np + (uint32_t)T.palias[k];
-            const double c = (double)b[0] * (1.0 / 2147483648.0) - 1.0;       // drawIso random.cpp:16-27
-            const double sth = sqrt(1.0 - c * c);
-            double sp, cp; sincospi_unit((double)b[1] * (1.0 / 2147483648.0) - 1.0, &sp, &cp);
-            const double dist = T.lambda[wp] * neg_log1m_u32(b[2]);
-            fast = fast && !(dist < 2.2250738585072014e-308);
-            if (fast) { ph.set_wp(wp); ph.dx = sth * cp; ph.dy = sth * sp; ph.dz = c; ph.sn = dist; }
+        bool fast = false;
+        if (T.nw > 1 && T.np > 1) {
+            Draw d2; draw_event(P, T, ph.pid_lo(), ph.pid_hi(), ph.step(), d2);
+            fast = d2.ok;
+            if (fast) { ph.set_wp(d2.wp); ph.dx = d2.dx; ph.dy = d2.dy; ph.dz = d2.dz; ph.sn = d2.dist; }
         }
         if (!fast) {
             Rng g; g.begin(P.seed, ph.pid(), ph.step());
             ph.set_wp(draw_prop(g, T, T.wprob, T.walias, T.pprob, T.palias));
             draw_iso(g, ph.dx, ph.dy, ph.dz);
             ph.sn = draw_scat_next(g, T.lambda[ph.wp()]);
+            renorm_unit(ph.dx, ph.dy, ph.dz);
         }
-        renorm_unit(ph.dx, ph.dy, ph.dz);
         ph.nscat++;
     }
     if ((long long)ph.nscat >= P.maxscat || (long long)ph.step() >= P.maxloop) ph.stop();     // :434, :401
@@ -363,15 +420,68 @@ __device__ __forceinline__ void flush_fixed_point(uint32_t* words, unsigned ncop
         }
     }
 }
+// Flush the 1-D difference-array histograms (mcb_device.cuh: deposit_fx) with the whole CTA, in three phases:
+//  1. per field entry (r, c): the `ninst` instances' direct and difference entries are recombined from their three limbs,
+//     summed as 64-bit integers (exact, order-free) into the scratch arrays and re-armed with zeros;
+//  2. per (row, 32-column chunk), one warp: inclusive scan of the difference sums, chunk totals kept;
+//  3. per entry: direct + running difference sum (scan + the totals of the chunks before it) is converted once and added
+//     to the global field (column-major, fp64 RED).
+// Callers place a __syncthreads() before (all deposits done); the next deposits only touch the instances, which are zero
+// after phase 1.
+__device__ __forceinline__ long long limbs_value(uint32_t p0, uint32_t p1, uint32_t p2) {
+    const uint32_t sb = p1 - (p2 << 16), sa = p0 - (sb << 16);
+    return (long long)(int32_t)p2 * 4294967296ll + (long long)sb * 65536ll + (long long)sa;
+}
+template <int NCOMP>
+__device__ __forceinline__ void flush_tally1d(unsigned char* hist, unsigned ninst, long long* scratch, const StepParams& P,
+                                              unsigned warp, unsigned nwarps, unsigned lane) {
+    const int E = P.rows * P.cols, nthr = (int)nwarps * 32, tid = (int)(warp * 32u + lane);
+    long long* sdir = scratch; long long* sdiff = scratch + E; long long* ctot = scratch + 2 * E;
+    for (int e = tid; e < E; e += nthr) {
+        const int r = e / P.cols, c = e - r * P.cols;
+        long long direct = 0, diff = 0;
+        for (unsigned w = 0; w < ninst; ++w) {
+            unsigned char* q0 = hist + (size_t)w * P.hist_bytes + (size_t)(3 * r) * P.fx_ps + 4u * (unsigned)c;
+            uint32_t v[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                uint32_t* q = reinterpret_cast<uint32_t*>(q0 + (k >= 3 ? P.fx_diff_off : 0u) + (unsigned)(k % 3) * P.fx_ps);
+                v[k] = *q; *q = 0u;
+            }
+            direct += limbs_value(v[0], v[1], v[2]); diff += limbs_value(v[3], v[4], v[5]);
+        }
+        sdir[e] = direct; sdiff[e] = diff;
+    }
+    __syncthreads();
+    const int nchunk = (P.cols + 31) / 32, ntask = P.rows * nchunk;
+    for (int task = (int)warp; task < ntask; task += (int)nwarps) {
+        const int r = task / nchunk, c = (task - r * nchunk) * 32 + (int)lane;
+        long long run = c < P.cols ? sdiff[r * P.cols + c] : 0ll;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const long long v = __shfl_up_sync(0xFFFFFFFFu, run, o); if ((int)lane >= o) run += v; }
+        if (c < P.cols) sdiff[r * P.cols + c] = run;
+        if (lane == 31u) ctot[task] = run;
+    }
+    __syncthreads();
+    for (int e = tid; e < E; e += nthr) {
+        const int r = e / P.cols, c = e - r * P.cols;
+        long long total = sdir[e] + sdiff[e];
+        for (int k = 0; k < (c >> 5); ++k) total += ctot[r * nchunk + k];
+        if (total != 0) atomicAdd(P.field + (long long)c * P.rows + r, (double)total * P.fx_inv[r % NCOMP]);
+    }
+}
 
 // ------------------------------------------------------------------------------- k_step
 // NCOMP: payload rows per deposit (1: Temp/CumTemp dt ; 3: Flux/CumFlux dpos ; 4: Multi dt,dpos)
 // TM   : MCB_TM_WARP / MCB_TM_BLOCK / MCB_TM_GLOBAL
 // NDM  : 0 only 1-D / single-cell tally grids; 1 some subdomain has a 2-D/3-D grid; 2 same, and the grid is fine enough
 //        (>= 64 cells along an axis) for the warp-cooperative N-D walk to pay for its registers
+// BOX  : every subdomain is an axis-aligned box (all shipped box domains): only the single-component plane code is built
+// PAD  : NDM == 0 with TM == MCB_TM_WARP uses the 1-D difference-array histograms (mcb_device.cuh: tally_1d); PAD > 0 is
+//        the compile-time padded column count of a histogram plane (cols <= PAD), 0 = run-time plane stride
 // Dynamic shared memory: [mbarrier 16 B][material blob][geometry blob][histogram(s)]
 #ifndef MCB_BLOCK_MAX
-#define MCB_BLOCK_MAX 896         // 1-D / single-cell tallies: 72 registers x 28 warps (measured best of 768 / 896 / 1024)
+#define MCB_BLOCK_MAX 768         // 1-D / single-cell tallies: 80 registers x 24 warps (round 2, with the TMA state prefetch: 896 x 72 -11 %, 640 x 96 -1 %)
 #endif
 #ifndef MCB_BLOCK_MAX_ND1
 #define MCB_BLOCK_MAX_ND1 768     // serial N-D walk, CTA histogram / global tally: 80 registers (measured: 640 +-1 %, 512 -15 % on C3)
@@ -382,7 +492,7 @@ __device__ __forceinline__ void flush_fixed_point(uint32_t* words, unsigned ncop
 #ifndef MCB_BLOCK_MAX_ND
 #define MCB_BLOCK_MAX_ND 512      // the cooperative N-D walk keeps two crossing iterators live: give it 128 registers
 #endif
-template <int NCOMP, int TM, int NDM, bool EMIT>
+template <int NCOMP, int TM, int NDM, bool BOX, int PAD>
 __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : (NDM == 1 ? (TM == MCB_TM_WARP ? MCB_BLOCK_MAX_ND1W : MCB_BLOCK_MAX_ND1) : MCB_BLOCK_MAX), 1) k_step(const StepParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
@@ -390,7 +500,10 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : (NDM == 1 ? (TM 
     unsigned char* s_geo = smem + P.so_geo;
     double* s_hist = reinterpret_cast<double*>(smem + P.so_hist);
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const long long hist_elems = TM == MCB_TM_WARP ? P.field_len * nwarps * P.hist_copies : (TM == MCB_TM_BLOCK ? P.field_len : 0);
+    constexpr bool T1D = NDM == 0 && TM == MCB_TM_WARP && MCB_TALLY_FX;          // 1-D difference-array histograms
+    const unsigned ninst = T1D ? (unsigned)P.hist_copies : 0u;
+    const long long hist_words = T1D ? (long long)ninst * (P.hist_bytes / 4u)
+                                     : 2ll * (TM == MCB_TM_WARP ? P.field_len * nwarps * P.hist_copies : (TM == MCB_TM_BLOCK ? P.field_len : 0));
 
     // --- stage tables: one elected thread arms the mbarrier and issues the TMA bulk copies
     if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
@@ -401,7 +514,7 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : (NDM == 1 ? (TM 
         for (uint32_t o = 0; o < P.mv.bytes; o += CH) tma_bulk_g2s(s_mat + o, P.mat_blob + o, min(CH, P.mv.bytes - o), bar);
         for (uint32_t o = 0; o < P.gv.bytes; o += CH) tma_bulk_g2s(s_geo + o, P.geo_blob + o, min(CH, P.gv.bytes - o), bar);
     }
-    for (long long i = threadIdx.x; i < hist_elems; i += blockDim.x) s_hist[i] = 0.0;
+    for (long long i = threadIdx.x; i < hist_words; i += blockDim.x) reinterpret_cast<uint32_t*>(s_hist)[i] = 0u;
     while (!mbar_try_wait(bar, 0)) {}
     __syncthreads();
 
@@ -420,139 +533,172 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : (NDM == 1 ? (TM 
     // warp-private histograms, `hist_copies` interleaved copies per warp (by lane) to thin out same-cell collisions
     T.hist = TM == MCB_TM_WARP ? s_hist + ((long long)warp * P.hist_copies + (lane & (unsigned)(P.hist_copies - 1))) * P.field_len
                                : (TM == MCB_TM_BLOCK ? s_hist : P.field);
+    // 1-D difference-array histograms: shared by the CTA, a lane picks its copy by lane id
+    const uint32_t my_hist = T1D ? smem_u32(s_hist) + (lane & (unsigned)(P.hist_copies - 1)) * P.hist_bytes : 0u;
     const bool cum = P.kind == MCB_PROB_CUMTEMP || P.kind == MCB_PROB_CUMFLUX;
     constexpr bool FX = MCB_TALLY_FX && TM == MCB_TM_WARP;        // fixed-point warp histograms (mcb_device.cuh: deposit)
     const uint32_t hi_off = 4u * (uint32_t)P.field_len;            // low-word plane, then high-word plane
 
-    unsigned my_steps = 0, my_esc = 0, my_emitted = 0, my_live = 0, my_stores = 0;     // per thread and launch: < 2^32
-    bool exhausted = false;
+    // counters of this launch: warp-uniform values from ballots, added by lane 0 to four CTA-wide words in shared memory
+    // where they arise -- no per-thread counter registers live across the loop trip
+    __shared__ unsigned s_cnt[4];                               // steps, esc, live, stores  (< 2^32 per CTA and launch)
+    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0u;
     // fixed-point histograms are flushed by the CTA between tiles at least every fx_flush_trips loop trips (the host keeps
     // steps_per_launch below that), which bounds the number of deposits an entry can receive (set_fixed_point, mcb_api.cu)
     int since_flush = 0;
-    // dense emission (EMIT == false): free slots are only LISTED here; k_emit fills them between launches with full
-    // warps (in-kernel emission of a few dead lanes per warp runs the long emission path at ~5 % lane efficiency)
-    const bool list_free = !EMIT && P.free_list != nullptr && P.ctr->next < P.n_end;
+    // dense emission: free slots are only LISTED here; k_emit fills them between launches with full warps (emitting
+    // inside this kernel runs the long emission path for a few dead lanes per warp at ~5 % lane efficiency)
+    const bool list_free = P.free_list != nullptr && P.ctr->next < P.n_end;
 
-    for (long long base = (long long)blockIdx.x * blockDim.x; base < P.nslots; base += (long long)gridDim.x * blockDim.x) {
-        const long long i = base + threadIdx.x;
+    // TMA state prefetch: a warp's 32 slots are one contiguous 2304-B group (StateView), bulk-copied into the warp's staging
+    // buffer while the warp works on the group before it.  The buffer is free again as soon as the lanes have moved their
+    // slot into registers, so ONE buffer per warp keeps a full tile in flight.
+    const bool staged = P.so_stage != 0u;
+    const uint32_t wbuf = P.so_stage + warp * MCB_GROUP_BYTES, wbar = P.so_wbar + warp * 8u;     // offsets into smem[]
+    const int ngroups = (int)((P.nslots + 31) >> 5);            // slots < 2^31 (plan_run)
+    const int gstride = (int)(gridDim.x * nwarps);
+    uint32_t wphase = 0;
+    if (staged) {
+        const int g0 = (int)(blockIdx.x * nwarps + warp);
+        if (lane == 0) { mbar_init(reinterpret_cast<uint64_t*>(smem + wbar), 1); fence_mbar_init(); }
+        __syncwarp();
+        if (lane == 0 && g0 < ngroups) {
+            mbar_expect_tx(reinterpret_cast<uint64_t*>(smem + wbar), MCB_GROUP_BYTES);
+            tma_bulk_g2s(smem + wbuf, P.st.base + (size_t)g0 * MCB_GROUP_BYTES, MCB_GROUP_BYTES, reinterpret_cast<uint64_t*>(smem + wbar));
+        }
+    }
+    __syncthreads();                                            // s_cnt is armed
+
+    // tile = one group of 32 slots per warp: group g = (blockIdx + k gridDim) nwarps + warp; the trip count is CTA-uniform
+    for (int g = (int)(blockIdx.x * nwarps + warp), gt = (int)(blockIdx.x * nwarps); gt < ngroups; g += gstride, gt += gstride) {
+        const long long i = (long long)g * 32 + lane;
         const bool valid = i < P.nslots;
         Particle ph; ph.mlo = 0; ph.nscat = 0; ph.ps = 0;
         ph.px = ph.py = ph.pz = ph.dx = ph.dy = ph.dz = ph.sn = 0.0;
-        // all nine loads are issued together (one memory round trip, not meta first and the rest behind its branch); while
+        // the whole slot is loaded at once (one memory round trip, not meta first and the rest behind its branch); while
         // the population is full nearly every slot is active, so nothing extra is read
-        if (valid) {
-            const unsigned long long meta = ld_stream(P.st.meta + i);
-            ph.ps = ld_stream(P.st.pidstep + i);
-            ph.px = ld_stream(P.st.px + i); ph.py = ld_stream(P.st.py + i); ph.pz = ld_stream(P.st.pz + i);
-            ph.dx = ld_stream(P.st.dx + i); ph.dy = ld_stream(P.st.dy + i); ph.dz = ld_stream(P.st.dz + i);
-            ph.sn = ld_stream(P.st.sn + i);
-            const bool act = MCB_META_ACTIVE(meta);
-            ph.mlo = act ? ((uint32_t)meta & ~(1u << 22)) : 0u; ph.nscat = act ? (uint32_t)(meta >> 32) : 0u;
-            if (!act) ph.ps = 0;
-        }
-        bool dirty = false;
+        if (staged) {
+            if (g < ngroups) {                                  // warp-uniform
+                uint64_t* bar_ = reinterpret_cast<uint64_t*>(smem + wbar);
+                while (!mbar_try_wait(bar_, wphase)) {}
+                wphase ^= 1u;
+                ph.load_shared(smem + wbuf, lane);
+                __syncwarp();
+                if (lane == 0 && g + gstride < ngroups) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the lanes' reads before the async write
+                    mbar_expect_tx(bar_, MCB_GROUP_BYTES);
+                    tma_bulk_g2s(smem + wbuf, P.st.base + (size_t)(g + gstride) * MCB_GROUP_BYTES, MCB_GROUP_BYTES, bar_);
+                }
+            }
+        } else if (valid) ph.load(P.st, i);
+        if (!valid || !ph.active()) ph.mlo = 0u; else ph.mlo &= ~(1u << 22);
+        const bool was_active = ph.active();
         if (FX && P.do_tally) {
             // between tiles (CTA-uniform): flush before an entry could have received more than fx_flush_trips rounds of deposits
             if (since_flush + P.steps_per_launch > P.fx_flush_trips) {
                 __syncthreads();
-                flush_fixed_point<NCOMP>(reinterpret_cast<uint32_t*>(s_hist), TM == MCB_TM_WARP ? nwarps * (unsigned)P.hist_copies : 1u, P, threadIdx.x, blockDim.x);
+                if (T1D) flush_tally1d<NCOMP>(reinterpret_cast<unsigned char*>(s_hist), ninst, reinterpret_cast<long long*>(smem + P.so_scratch), P, warp, nwarps, lane);
+                else flush_fixed_point<NCOMP>(reinterpret_cast<uint32_t*>(s_hist), nwarps * (unsigned)P.hist_copies, P, threadIdx.x, blockDim.x);
                 __syncthreads();
                 since_flush = 0;
             }
             since_flush += P.steps_per_launch;
         }
-        for (int s = 0; s < P.steps_per_launch; ++s) {
-            // refill: a freed slot takes the next particle id (warp-aggregated ticket)
-            const bool want = EMIT && valid && !ph.active() && !exhausted && (P.refill || s == 0);
-            const unsigned m = EMIT ? __ballot_sync(0xFFFFFFFFu, want) : 0u;
-            if (EMIT && m) {
-                unsigned long long ticket = 0;
-                const int leader = __ffs(m) - 1;
-                if ((int)lane == leader) ticket = atomicAdd(&P.ctr->next, (unsigned long long)__popc(m));
-                ticket = __shfl_sync(0xFFFFFFFFu, ticket, leader);
-                if (want) {
-                    const unsigned long long pid = ticket + __popc(m & ((1u << lane) - 1u));
-                    if (pid < P.n_end) { emit_particle(P, T, pid, ph); my_emitted++; dirty = true; }
-                    else exhausted = true;
-                }
-            }
+        unsigned run_mask = __ballot_sync(0xFFFFFFFFu, was_active);
+        for (int s = 0; s < P.steps_per_launch && run_mask != 0u; ++s) {
             // one loop trip (problem.cpp:401-435) in three phases; the tally phase is warp-synchronous
             const bool run = ph.active();
+            if (lane == 0) atomicAdd(&s_cnt[0], (unsigned)__popc(run_mask));
             Segment sg; sg.ok = false; sg.hit = -1; sg.d = 0.0; sg.nscat_before = 0;
             sg.bx = sg.by = sg.bz = sg.ex = sg.ey = sg.ez = 0.0;
-            if (run) { my_esc += advect_move(T, ph, sg); my_steps++; dirty = true; }
+            bool escaped = false;
+            if (run) escaped = advect_move<BOX>(T, ph, sg) != 0u;
             if (P.do_tally) {
-                __syncwarp();
                 // accumAmt (problem.cpp:473-476,506-509,539-544,581-589,629-637) times sign (:414)
-                const double sg_ = ph.sign() ? 1.0 : -1.0;
-                double amt[NCOMP];
-                if (NCOMP == 1) amt[0] = sg_ * (sg.d * T.inv_vel[ph.wp()]);
-                else if (NCOMP == 4) { amt[0] = sg_ * (sg.d * T.inv_vel[ph.wp()]); amt[1 % NCOMP] = sg_ * (sg.ex - sg.bx); amt[2 % NCOMP] = sg_ * (sg.ey - sg.by); amt[3 % NCOMP] = sg_ * (sg.ez - sg.bz); }
-                else { amt[0] = sg_ * (sg.ex - sg.bx); amt[1 % NCOMP] = sg_ * (sg.ey - sg.by); amt[2 % NCOMP] = sg_ * (sg.ez - sg.bz); }
-                FxArgs fx{hi_off, (uint32_t)P.fx_limb_bits, (1u << P.fx_limb_bits) - 1u, false, &P};
-                if (FX) {
-                    // fixed-point histograms: scale by the launch's power of two (exact); a payload beyond the chosen range
-                    // (rare: a long flight of a very slow mode) is deposited exactly through the global fp64 path instead
-                    bool fits = true;
-#pragma unroll
-                    for (int k = 0; k < NCOMP; ++k) { fits = fits && fabs(amt[k]) <= P.fx_max[k]; amt[k] *= P.fx_scale[k]; }
-                    fx.slow = !fits;
-                }
+                const DSdom& sd = T.sdom[ph.sdom()];
                 const int rbase = cum ? NCOMP * (int)(((long long)sg.nscat_before + P.cum_step - 1) / P.cum_step) : 0;
-                tally_segments<NCOMP, TM, (NDM > 0), true, (NDM == 2)>(T.sdom[ph.sdom()], T.hist, P.rows, P.cols, rbase, sg.ok, sg.bx, sg.by, sg.bz, sg.ex, sg.ey, sg.ez, amt, lane, fx);
+                if (T1D) {
+                    // fixed point: sign and the launch's power-of-two scale in one factor per component (exact); only the
+                    // dt row can exceed the fixed-point range (a flight of one of the few very slow modes): those
+                    // flights are deposited exactly, fp64 RED straight to the global field, by the generic walk
+                    const bool neg = !ph.sign();
+                    double amt[NCOMP];
+                    bool slow = false;
+                    if (NCOMP != 3) {
+                        const double dt = sg.d * T.inv_vel[ph.wp()];
+                        slow = sg.ok && !(dt <= P.fx_max[0]);
+                        amt[0] = dt * (neg ? -P.fx_scale[0] : P.fx_scale[0]);
+                    }
+                    if (NCOMP != 1) {
+                        const double f = neg ? -P.fx_scale[NCOMP - 1] : P.fx_scale[NCOMP - 1];
+                        amt[NCOMP - 3] = (sg.ex - sg.bx) * f; amt[NCOMP - 2] = (sg.ey - sg.by) * f; amt[NCOMP - 1] = (sg.ez - sg.bz) * f;
+                    }
+                    if (__any_sync(0xFFFFFFFFu, slow)) {
+                        if (slow) {
+                            double raw[NCOMP];
+#pragma unroll
+                            for (int k = 0; k < NCOMP; ++k) raw[k] = amt[k] * P.fx_inv[k];
+                            tally_segments<NCOMP, MCB_TM_GLOBAL, false, false>(sd, P.field, P.rows, P.cols, rbase, true, sg.bx, sg.by, sg.bz, sg.ex, sg.ey, sg.ez, raw, lane);
+                        }
+                        __syncwarp();
+                    }
+                    Tally1D t1;
+                    tally1d_setup<BOX>(sd, sg.ok && !slow, sg.bx, sg.by, sg.bz, sg.ex, sg.ey, sg.ez, t1);
+                    const uint32_t ps3 = 3u * (PAD > 0 ? (uint32_t)PAD * 4u : P.fx_ps);
+                    tally1d_deposit<NCOMP, PAD>(t1, my_hist, (uint32_t)rbase * ps3, P.fx_ps, P.fx_diff_off, amt);
+                } else {
+                    __syncwarp();
+                    const double sg_ = ph.sign() ? 1.0 : -1.0;
+                    double amt[NCOMP];
+                    if (NCOMP == 1) amt[0] = sg_ * (sg.d * T.inv_vel[ph.wp()]);
+                    else if (NCOMP == 4) { amt[0] = sg_ * (sg.d * T.inv_vel[ph.wp()]); amt[1 % NCOMP] = sg_ * (sg.ex - sg.bx); amt[2 % NCOMP] = sg_ * (sg.ey - sg.by); amt[3 % NCOMP] = sg_ * (sg.ez - sg.bz); }
+                    else { amt[0] = sg_ * (sg.ex - sg.bx); amt[1 % NCOMP] = sg_ * (sg.ey - sg.by); amt[2 % NCOMP] = sg_ * (sg.ez - sg.bz); }
+                    FxArgs fx{hi_off, (uint32_t)P.fx_limb_bits, (1u << P.fx_limb_bits) - 1u, false, &P};
+                    if (FX) {
+                        // fixed-point histograms: scale by the launch's power of two (exact); a payload beyond the chosen range
+                        // (rare: a long flight of a very slow mode) is deposited exactly through the global fp64 path instead
+                        bool fits = true;
+#pragma unroll
+                        for (int k = 0; k < NCOMP; ++k) { fits = fits && fabs(amt[k]) <= P.fx_max[k]; amt[k] *= P.fx_scale[k]; }
+                        fx.slow = !fits;
+                    }
+                    tally_segments<NCOMP, TM, (NDM > 0), true, (NDM == 2)>(sd, T.hist, P.rows, P.cols, rbase, sg.ok, sg.bx, sg.by, sg.bz, sg.ex, sg.ey, sg.ez, amt, lane, fx);
+                }
             }
-            if (sg.ok) my_esc += collide(P, T, ph, sg);
-            if (__all_sync(0xFFFFFFFFu, !ph.active() && (!EMIT || exhausted || !valid || !P.refill))) break;
+            if (sg.ok) escaped = collide<BOX>(P, T, ph, sg) != 0u;
+            const unsigned em = __ballot_sync(0xFFFFFFFFu, escaped);           // rare: Progress::incrEsc problem.cpp:111-118
+            if (em && lane == 0) atomicAdd(&s_cnt[1], (unsigned)__popc(em));
+            run_mask = __ballot_sync(0xFFFFFFFFu, ph.active());
         }
-        if (valid && dirty) {
-            my_stores++;
-            st_stream(P.st.px + i, ph.px); st_stream(P.st.py + i, ph.py); st_stream(P.st.pz + i, ph.pz);
-            st_stream(P.st.dx + i, ph.dx); st_stream(P.st.dy + i, ph.dy); st_stream(P.st.dz + i, ph.dz);
-            st_stream(P.st.sn + i, ph.sn);
-            st_stream(P.st.meta + i, ph.meta());
-            st_stream(P.st.pidstep + i, ph.ps);
-        }
-        if (ph.active()) my_live++;
-        if (!EMIT && list_free) {
-            const bool fr = valid && !ph.active();
-            const unsigned fm = __ballot_sync(0xFFFFFFFFu, fr);
+        if (was_active) ph.store(P.st, i);
+        const unsigned st_mask = __ballot_sync(0xFFFFFFFFu, was_active);
+        if (lane == 0) { atomicAdd(&s_cnt[3], (unsigned)__popc(st_mask)); atomicAdd(&s_cnt[2], (unsigned)__popc(run_mask)); }
+        if (list_free) {
+            const unsigned fm = __ballot_sync(0xFFFFFFFFu, valid) & ~run_mask;  // valid slots that ended inactive
             if (fm) {
                 unsigned long long pos = 0;
                 const int leader = __ffs(fm) - 1;
                 if ((int)lane == leader) pos = atomicAdd(&P.ctr->nfree, (unsigned long long)__popc(fm));
                 pos = __shfl_sync(0xFFFFFFFFu, pos, leader);
-                if (fr) P.free_list[pos + __popc(fm & ((1u << lane) - 1u))] = (uint32_t)i;
+                if ((fm >> lane) & 1u) P.free_list[pos + __popc(fm & ((1u << lane) - 1u))] = (uint32_t)i;
             }
         }
     }
 
-    // --- block-level reduction of the counters, one atomic per CTA
-    __shared__ unsigned long long s_red[5];
-    if (threadIdx.x < 5) s_red[threadIdx.x] = 0;
-    __syncthreads();
-    my_steps = __reduce_add_sync(0xFFFFFFFFu, my_steps); my_esc = __reduce_add_sync(0xFFFFFFFFu, my_esc);       // REDUX
-    my_emitted = __reduce_add_sync(0xFFFFFFFFu, my_emitted); my_live = __reduce_add_sync(0xFFFFFFFFu, my_live);
-    my_stores = __reduce_add_sync(0xFFFFFFFFu, my_stores);
-    if (lane == 0) {
-        if (my_steps) atomicAdd(&s_red[0], (unsigned long long)my_steps);
-        if (my_esc) atomicAdd(&s_red[1], (unsigned long long)my_esc);
-        if (my_emitted) atomicAdd(&s_red[2], (unsigned long long)my_emitted);
-        if (my_live) atomicAdd(&s_red[3], (unsigned long long)my_live);
-        if (my_stores) atomicAdd(&s_red[4], (unsigned long long)my_stores);
-    }
+    // --- the CTA's counters: one global atomic each
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (s_red[0]) atomicAdd(&P.ctr->steps, s_red[0]);
-        if (s_red[1]) atomicAdd(&P.ctr->esc, s_red[1]);
-        if (s_red[2]) atomicAdd(&P.ctr->emitted, s_red[2]);
-        if (s_red[3]) atomicAdd(&P.ctr->live, s_red[3]);
-        if (s_red[4]) atomicAdd(&P.ctr->stores, s_red[4]);
+        if (s_cnt[0]) atomicAdd(&P.ctr->steps, (unsigned long long)s_cnt[0]);
+        if (s_cnt[1]) atomicAdd(&P.ctr->esc, (unsigned long long)s_cnt[1]);
+        if (s_cnt[2]) atomicAdd(&P.ctr->live, (unsigned long long)s_cnt[2]);
+        if (s_cnt[3]) atomicAdd(&P.ctr->stores, (unsigned long long)s_cnt[3]);
     }
     // --- flush the shared-memory histogram(s): sum the copies, transpose row-major -> the field's column-major layout,
     //     one fp64 RED per non-zero entry
     if (TM != MCB_TM_GLOBAL && P.do_tally) {
         const unsigned ncopy = TM == MCB_TM_WARP ? nwarps * (unsigned)P.hist_copies : 1u;
-        if (FX) flush_fixed_point<NCOMP>(reinterpret_cast<uint32_t*>(s_hist), ncopy, P, threadIdx.x, blockDim.x);
+        if (T1D) flush_tally1d<NCOMP>(reinterpret_cast<unsigned char*>(s_hist), ninst, reinterpret_cast<long long*>(smem + P.so_scratch), P, warp, nwarps, lane);
+        else if (FX) flush_fixed_point<NCOMP>(reinterpret_cast<uint32_t*>(s_hist), ncopy, P, threadIdx.x, blockDim.x);
         else for (long long i = threadIdx.x; i < P.field_len; i += blockDim.x) {   // i = r*cols + c in the histograms
             double v = 0.0;
             for (unsigned w = 0; w < ncopy; ++w) v += s_hist[(long long)w * P.field_len + i];
@@ -562,6 +708,7 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : (NDM == 1 ? (TM 
     }
 }
 
+#ifdef MCB_AUX_KERNELS      // the non-template kernels live in ONE translation unit (mcb_api.cu)
 // ------------------------------------------------------------------------------- k_emit
 // K1, dense: particle next+j is emitted into free slot free_list[j] (problem.cpp:386-399), all lanes busy.
 __global__ void __launch_bounds__(256) k_emit(const StepParams P) {
@@ -575,10 +722,7 @@ __global__ void __launch_bounds__(256) k_emit(const StepParams P) {
         const long long i = (long long)P.free_list[j];
         Particle ph;
         emit_particle(P, T, next + j, ph);
-        P.st.px[i] = ph.px; P.st.py[i] = ph.py; P.st.pz[i] = ph.pz;
-        P.st.dx[i] = ph.dx; P.st.dy[i] = ph.dy; P.st.dz[i] = ph.dz; P.st.sn[i] = ph.sn;
-        P.st.meta[i] = ph.meta();
-        P.st.pidstep[i] = ph.ps;
+        ph.store(P.st, i);
     }
 }
 // after k_emit: advance the particle counter, empty the free list (one thread)
@@ -650,12 +794,12 @@ __global__ void k_traj(const StepParams P, const mcb_traj_desc t, const TrajDev 
             o.step_out[k] = -1; o.step_out_kind[k] = -1;
         }
         Segment sg; sg.ok = false; sg.hit = -1; sg.next_plane = -1;
-        const uint32_t esc = advect_move(T, ph, sg);                                                          // :265
+        const uint32_t esc = advect_move<false>(T, ph, sg);                                                          // :265
         push(ph.px, ph.py, ph.pz);
         if (esc) { escaped = 1; break; }                                                                      // :267-271
         if (k < o.max_steps) { o.step_out[k] = sg.hit >= 0 ? sg.hit - sd.plane_begin : -1; o.step_out_kind[k] = sg.hit >= 0 ? T.cold[sg.hit].kind : -1; }
         const bool peri = sg.hit >= 0 && T.cold[sg.hit].kind == MCB_BDRY_PERI;
-        if (collide(P, T, ph, sg)) { escaped = 2; break; }                                                    // :277-294
+        if (collide<false>(P, T, ph, sg)) { escaped = 2; break; }                                                    // :277-294
         if (peri) push(ph.px, ph.py, ph.pz);
         cur = sg.next_plane;
         if (!ph.active()) break;                                                                              // :295
@@ -665,25 +809,20 @@ __global__ void k_traj(const StepParams P, const mcb_traj_desc t, const TrajDev 
 
 // ---------------------------------------------------------------------------- k_compact
 // Unordered stream compaction of active slots from `src` into `dst` (tail of the solve).
-__global__ void k_compact(StateSoA src, StateSoA dst, long long n, Counters* ctr) {
+__global__ void k_compact(StateView src, StateView dst, long long n, Counters* ctr) {
     const unsigned lane = threadIdx.x & 31u;
     for (long long base = (long long)blockIdx.x * blockDim.x; base < n; base += (long long)gridDim.x * blockDim.x) {
         const long long i = base + threadIdx.x;
-        unsigned long long meta = 0;
-        if (i < n) meta = src.meta[i];
-        const bool act = (i < n) && MCB_META_ACTIVE(meta);
+        Particle ph; ph.mlo = 0;
+        if (i < n) ph.load(src, i);
+        const bool act = (i < n) && ph.active();
         const unsigned m = __ballot_sync(0xFFFFFFFFu, act);
         if (!m) continue;
         unsigned long long pos = 0;
         const int leader = __ffs(m) - 1;
         if ((int)lane == leader) pos = atomicAdd(&ctr->compact_cursor, (unsigned long long)__popc(m));
         pos = __shfl_sync(0xFFFFFFFFu, pos, leader);
-        if (act) {
-            const long long o = (long long)(pos + __popc(m & ((1u << lane) - 1u)));
-            dst.px[o] = src.px[i]; dst.py[o] = src.py[i]; dst.pz[o] = src.pz[i];
-            dst.dx[o] = src.dx[i]; dst.dy[o] = src.dy[i]; dst.dz[o] = src.dz[i];
-            dst.sn[o] = src.sn[i]; dst.meta[o] = meta; dst.pidstep[o] = src.pidstep[i];
-        }
+        if (act) ph.store(dst, (long long)(pos + __popc(m & ((1u << lane) - 1u))));
     }
 }
 
@@ -739,18 +878,19 @@ __global__ void k_philox(unsigned long long seed, unsigned long long pid, uint32
 }
 
 // scatter the slot state to per-particle trace arrays (slot order is not particle order)
-__global__ void k_gather_trace(StateSoA st, long long nslots, unsigned long long n_begin, long long n, int np,
+__global__ void k_gather_trace(StateView st, long long nslots, unsigned long long n_begin, long long n, int np,
                                const unsigned char* geo_blob, GeometryView gv,
                                double* pos, double* dir, double* sn, long long* w, long long* p, int32_t* sign,
                                int32_t* alive, int32_t* sdom, long long* nscat, long long* steps, int32_t* cell) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nslots) return;
-    const unsigned long long meta = st.meta[i], ps = st.pidstep[i];
+    Particle ph;
+    const unsigned long long meta = ph.load(st, i), ps = ph.ps;
     const long long o = (long long)(MCB_PID(ps) - n_begin);
     if (o < 0 || o >= n) return;
-    pos[3 * o] = st.px[i]; pos[3 * o + 1] = st.py[i]; pos[3 * o + 2] = st.pz[i];
-    dir[3 * o] = st.dx[i]; dir[3 * o + 1] = st.dy[i]; dir[3 * o + 2] = st.dz[i];
-    sn[o] = st.sn[i];
+    pos[3 * o] = ph.px; pos[3 * o + 1] = ph.py; pos[3 * o + 2] = ph.pz;
+    dir[3 * o] = ph.dx; dir[3 * o + 1] = ph.dy; dir[3 * o + 2] = ph.dz;
+    sn[o] = ph.sn;
     const uint32_t wp = MCB_META_WP(meta);
     w[o] = wp / np; p[o] = wp % np;
     sign[o] = MCB_META_SIGN(meta) ? 1 : -1;
@@ -760,8 +900,10 @@ __global__ void k_gather_trace(StateSoA st, long long nslots, unsigned long long
     steps[o] = MCB_STEP(ps);
     const DSdom* sds = reinterpret_cast<const DSdom*>(geo_blob + gv.off_sdom);
     const DSdom& sd = sds[MCB_META_SDOM(meta)];
-    double c[3]; sdom_coord(sd, st.px[i], st.py[i], st.pz[i], c);
+    double c[3]; sdom_coord(sd, ph.px, ph.py, ph.pz, c);
     for (int d = 0; d < 3; ++d) cell[3 * o + d] = (int32_t)coord2index1(c[d], sd.max[d]);
 }
+
+#endif // MCB_AUX_KERNELS
 
 } // namespace mcb

@@ -303,8 +303,8 @@ def test_c_abi_library_exports_every_declared_symbol():
     import hashlib
     csrc = os.path.join(ROOT, "montecarlocpp_b200", "csrc")
     h = hashlib.sha1()
-    for f in (os.path.join(csrc, "mcb_api.cu"), os.path.join(csrc, "mcb_kernels.cuh"), os.path.join(csrc, "mcb_device.cuh"),
-              os.path.join(ROOT, "include", "mcb.h")):
+    units = ["mcb_api.cu", "mcb_step_n1.cu", "mcb_step_n3.cu", "mcb_step_n4.cu", "mcb_kernels.cuh", "mcb_device.cuh", "mcb_step_inst.cuh"]
+    for f in [os.path.join(csrc, u) for u in units] + [os.path.join(ROOT, "include", "mcb.h")]:
         h.update(open(f, "rb").read())
     L.mcb_build_info.restype = C.c_char_p
     src_hash, _, extra = L.mcb_build_info().decode().partition("|")

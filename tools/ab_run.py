@@ -23,7 +23,8 @@ for wl in (sys.argv[1:] or ["slab", "film", "wire"]):
     raw = torch.zeros(prob.rows * dom.cols, dtype=torch.float64, device="cuda")
     for S, k in ((1, 32), (16, 8)):
         extra = {k_: int(v_) for k_, v_ in (kv.split("=") for kv in os.environ.get("AB_OPTS", "").split())}
-        ctx.set_options(steps_per_launch=S, slots=148 * 768 * k, **extra)
+        blk = int(os.environ.get("AB_BLOCK") or "768")
+        ctx.set_options(steps_per_launch=S, slots=148 * blk * k, **extra)
         best, bs = 1e9, 0.0
         for rep in range(3):
             raw.zero_(); torch.cuda.synchronize()
