@@ -115,7 +115,7 @@ struct mcb_ctx {
     DevBuf<long long> emit_cdf;
     DevBuf<unsigned char> state[2]; long long slots_alloc = 0;          // warp-tiled slot state (mcb_device.cuh: StateView)
     DevBuf<Counters> ctr; Counters* h_ctr = nullptr;     // pinned mirror
-    DevBuf<uint32_t> free_list;
+    DevBuf<uint32_t> free_list, free_cnt;     // dense emission: per-CTA segments of free slot ids + their counts
     DevBuf<double> field;
 };
 
@@ -199,6 +199,7 @@ int plan_run(mcb_ctx* c, const mcb_problem_desc* prob, long long nparticles, Run
     r->S = o.steps_per_launch > 0 ? o.steps_per_launch : 16;
     long long slots = o.slots > 0 ? o.slots : (long long)c->sm_count * r->block * 32;   // ~2.4 M resident phonons
     slots = std::min(slots, std::max<long long>(nparticles, 1));
+    if (slots > 0x7FFFFF00ll) { c->err = "too many resident slots (< 2^31)"; return MCB_ELIMIT; }
     r->slots = slots;
     const long long tiles = (slots + r->block - 1) / r->block;
     r->grid = (int)std::min<long long>((long long)c->sm_count * per_sm, std::max<long long>(tiles, 1));
@@ -344,12 +345,17 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
     const bool dense = true;
     const long long compact_pct = c->opt.compact_pct > 0 ? c->opt.compact_pct : MCB_COMPACT_PCT;
     bool host_all_emitted = false;
+    int nseg = 0;                        // free-list segments filled by the previous k_step (0: the first fill, every slot free)
     if (dense) {
-        CUDA_TRY(c, c->free_list.alloc((size_t)c->slots_alloc));
-        P.free_list = c->free_list.p;
-        k_free_init<<<(unsigned)((nslots + 255) / 256), 256, 0, c->stream>>>(c->free_list.p, nslots, c->ctr.p);
-        CUDA_TRY(c, cudaGetLastError());
-        launches++;
+        // one segment per k_step CTA, long enough for every slot the CTA visits
+        const long long tiles0 = (nslots + plan.block - 1) / plan.block;
+        const long long grid0 = std::min<long long>(plan.grid, std::max<long long>(tiles0, 1));
+        if (grid0 > MCB_MAX_SEG) { c->err = "persistent grid too large for the free-list segments"; return MCB_ELIMIT; }
+        P.free_seg = (uint32_t)(((tiles0 + grid0 - 1) / grid0) * plan.block);
+        CUDA_TRY(c, c->free_list.alloc((size_t)grid0 * P.free_seg));
+        CUDA_TRY(c, c->free_cnt.alloc(MCB_MAX_SEG));
+        CUDA_TRY(c, cudaMemsetAsync(c->free_cnt.p, 0, MCB_MAX_SEG * sizeof(uint32_t), c->stream));
+        P.free_list = c->free_list.p; P.free_cnt = c->free_cnt.p;
     } else P.free_list = nullptr;
     long long steady_launches = 0; float steady_ms = 0.f;
     unsigned long long steady_steps = 0, steady_stores = 0, prev_steps = 0, prev_stores = 0;
@@ -360,14 +366,14 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
         P.st = view_of(c, cur); P.nslots = nslots; P.steps_per_launch = S_cur;
         if (dense && !host_all_emitted) {
             // K1: fill the free slots listed by the previous k_step (all of them before the first), with full warps
-            k_emit<<<(unsigned)(c->sm_count * 4), 256, 0, c->stream>>>(P);
-            k_emit_commit<<<1, 1, 0, c->stream>>>(c->ctr.p, (unsigned long long)n_end);
+            k_emit<<<(unsigned)(c->sm_count * 4), 256, 0, c->stream>>>(P, nseg);
+            k_emit_commit<<<1, 1, 0, c->stream>>>(P, nseg);         // also re-arms ctr->live
             CUDA_TRY(c, cudaGetLastError());
             launches += 2;
-        }
-        CUDA_TRY(c, cudaMemsetAsync(&c->ctr.p->live, 0, sizeof(unsigned long long), c->stream));   // rewritten by every launch
+        } else CUDA_TRY(c, cudaMemsetAsync(&c->ctr.p->live, 0, sizeof(unsigned long long), c->stream));   // rewritten by every launch
         const long long tiles = (nslots + plan.block - 1) / plan.block;
         const int grid = (int)std::min<long long>(plan.grid, std::max<long long>(tiles, 1));
+        nseg = grid;
         CUDA_TRY(c, cudaEventRecord(c->evA[slot], c->stream));
         CUDA_TRY(c, launch_step(P, plan.tm, c->any_nd, c->all_box, plan.pad, grid, plan.block, plan.smem, c->stream));
         CUDA_TRY(c, cudaEventRecord(c->evB[slot], c->stream));
@@ -482,7 +488,7 @@ void mcb_destroy(mcb_ctx* c) {
     c->mat_blob.release(); c->f_wprob.release(); c->f_pprob.release(); c->f_walias.release(); c->f_palias.release();
     c->geo_blob.release(); c->emitters.release(); c->cell_vol.release(); c->emit_cdf.release();
     for (int w = 0; w < 2; ++w) c->state[w].release();
-    c->ctr.release(); c->field.release(); c->free_list.release();
+    c->ctr.release(); c->field.release(); c->free_list.release(); c->free_cnt.release();
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
     if (c->ev0) cudaEventDestroy(c->ev0); if (c->ev1) cudaEventDestroy(c->ev1);
     for (int k = 0; k < 2; ++k) { if (c->evA[k]) cudaEventDestroy(c->evA[k]); if (c->evB[k]) cudaEventDestroy(c->evB[k]); if (c->evC[k]) cudaEventDestroy(c->evC[k]); }
@@ -792,21 +798,18 @@ int mcb_trace(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
     if (rc) return rc;
     if ((rc = ensure_slots(c, n))) return rc;
     if ((rc = upload_cdf(c, prob))) return rc;
-    CUDA_TRY(c, c->free_list.alloc((size_t)c->slots_alloc));
     StepParams P; fill_params(c, prob, seed, &P);
     apply_plan(plan, prob, &P);
     P.maxloop = std::min<long long>(prob->maxloop, nsteps);
     P.field = nullptr; P.do_tally = 0;
     P.steps_per_launch = (int)std::max<long long>(1, std::min<long long>(P.maxloop, 0x7FFFFFFF)); P.n_end = (unsigned long long)n_end;
-    P.st = view_of(c, 0); P.nslots = n; P.free_list = c->free_list.p;
+    P.st = view_of(c, 0); P.nslots = n; P.free_list = nullptr; P.free_cnt = nullptr;
     Counters init{}; init.next = (unsigned long long)n_begin;
     CUDA_TRY(c, cudaMemcpyAsync(c->ctr.p, &init, sizeof init, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaMemsetAsync(c->state[0].p, 0, state_bytes(c->slots_alloc), c->stream));
-    k_free_init<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->free_list.p, n, c->ctr.p);
-    k_emit<<<(unsigned)(c->sm_count * 4), 256, 0, c->stream>>>(P);
-    k_emit_commit<<<1, 1, 0, c->stream>>>(c->ctr.p, (unsigned long long)n_end);
+    k_emit<<<(unsigned)(c->sm_count * 4), 256, 0, c->stream>>>(P, 0);     // first fill: particle n_begin + j into slot j
+    k_emit_commit<<<1, 1, 0, c->stream>>>(P, 0);
     CUDA_TRY(c, cudaGetLastError());
-    P.free_list = nullptr;                                   // nothing to list afterwards
     if (P.maxloop > 0) CUDA_TRY(c, launch_step(P, plan.tm, c->any_nd, c->all_box, plan.pad, plan.grid, plan.block, plan.smem, c->stream));
     DevBuf<double> dpos, ddir, dsn; DevBuf<long long> dw, dp, dnscat, dsteps; DevBuf<int32_t> dsign, dalive, dsdom, dcell;
     CUDA_TRY(c, dpos.alloc(3 * n)); CUDA_TRY(c, ddir.alloc(3 * n)); CUDA_TRY(c, dsn.alloc(n));

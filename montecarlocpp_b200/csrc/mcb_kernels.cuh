@@ -1,7 +1,7 @@
 // mcb_kernels.cuh — the CUDA kernels (sm_100a) of the phonon Monte Carlo hot path.
 //
 //   k_emit      K1 (dense): the next particles are emitted into the free slots listed by k_step (problem.cpp:386-399),
-//               one thread per particle, full warps; k_emit_commit advances the particle counter; k_free_init seeds the list.
+//               one thread per particle, full warps; k_emit_commit advances the particle counter.
 //   k_step      K2: S trips of the loop body (problem.cpp:401-435) per resident slot: advect -> tally -> boundary or
 //               intrinsic scattering.  State streams HBM -> registers -> HBM once per launch.  Material + geometry tables
 //               are staged into shared memory with a TMA bulk copy (cp.async.bulk + mbarrier); tallies go to warp-private
@@ -55,6 +55,9 @@ __device__ __forceinline__ void st_stream2(void* p, double a, double b) {
 }
 __device__ __forceinline__ void st_stream2(void* p, double a, unsigned long long b) {
     asm volatile("st.global.L1::no_allocate.v2.b64 [%0], {%1, %2};" ::"l"(p), "d"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ void red_shared_u32(unsigned* p, unsigned v) {          // fire-and-forget shared-memory add
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
 __device__ __forceinline__ void st_stream1(void* p, unsigned long long v) {
     asm volatile("st.global.L1::no_allocate.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -215,9 +218,10 @@ __device__ __forceinline__ bool is_inside(const Tables& T, const DSdom& sd, doub
     if (BOX || sd.aabb) {            // axis-aligned box: n_b.x is x[b]
         const double p3[3] = {x, y, z};
         const double neps = -sd.eps;
+        int out = 0;                                             // branch-free: six independent compares
 #pragma unroll
-        for (int b = 0; b < 3; ++b) in = in && !(p3[b] + sd.offl[b] < neps) && !(sd.offh[b] - p3[b] < neps);
-        return in;
+        for (int b = 0; b < 3; ++b) out |= (int)(p3[b] + sd.offl[b] < neps) | (int)(sd.offh[b] - p3[b] < neps);
+        return out == 0;
     }
     if (sd.is_box) {                 // planes b and b+3 share n.pos up to sign: three dot products
 #pragma unroll
@@ -541,14 +545,17 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : (NDM == 1 ? (TM 
 
     // counters of this launch: warp-uniform values from ballots, added by lane 0 to four CTA-wide words in shared memory
     // where they arise -- no per-thread counter registers live across the loop trip
-    __shared__ unsigned s_cnt[4];                               // steps, esc, live, stores  (< 2^32 per CTA and launch)
-    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0u;
+    __shared__ unsigned s_cnt[5];                               // steps, esc, live, stores, freed slots  (< 2^32 per CTA and launch)
+    if (threadIdx.x < 5) s_cnt[threadIdx.x] = 0u;
     // fixed-point histograms are flushed by the CTA between tiles at least every fx_flush_trips loop trips (the host keeps
     // steps_per_launch below that), which bounds the number of deposits an entry can receive (set_fixed_point, mcb_api.cu)
     int since_flush = 0;
     // dense emission: free slots are only LISTED here; k_emit fills them between launches with full warps (emitting
-    // inside this kernel runs the long emission path for a few dead lanes per warp at ~5 % lane efficiency)
+    // inside this kernel runs the long emission path for a few dead lanes per warp at ~5 % lane efficiency).  Every CTA
+    // appends to its OWN segment of the list through a shared-memory cursor (a global cursor made every warp wait for a
+    // returning L2 atomic once per tile) and publishes its count at the end.
     const bool list_free = P.free_list != nullptr && P.ctr->next < P.n_end;
+    uint32_t* const my_free = P.free_list + (size_t)blockIdx.x * P.free_seg;
 
     // TMA state prefetch: a warp's 32 slots are one contiguous 2304-B group (StateView), bulk-copied into the warp's staging
     // buffer while the warp works on the group before it.  The buffer is free again as soon as the lanes have moved their
@@ -570,29 +577,8 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : (NDM == 1 ? (TM 
     __syncthreads();                                            // s_cnt is armed
 
     // tile = one group of 32 slots per warp: group g = (blockIdx + k gridDim) nwarps + warp; the trip count is CTA-uniform
+    const int nslots = (int)P.nslots;
     for (int g = (int)(blockIdx.x * nwarps + warp), gt = (int)(blockIdx.x * nwarps); gt < ngroups; g += gstride, gt += gstride) {
-        const long long i = (long long)g * 32 + lane;
-        const bool valid = i < P.nslots;
-        Particle ph; ph.mlo = 0; ph.nscat = 0; ph.ps = 0;
-        ph.px = ph.py = ph.pz = ph.dx = ph.dy = ph.dz = ph.sn = 0.0;
-        // the whole slot is loaded at once (one memory round trip, not meta first and the rest behind its branch); while
-        // the population is full nearly every slot is active, so nothing extra is read
-        if (staged) {
-            if (g < ngroups) {                                  // warp-uniform
-                uint64_t* bar_ = reinterpret_cast<uint64_t*>(smem + wbar);
-                while (!mbar_try_wait(bar_, wphase)) {}
-                wphase ^= 1u;
-                ph.load_shared(smem + wbuf, lane);
-                __syncwarp();
-                if (lane == 0 && g + gstride < ngroups) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the lanes' reads before the async write
-                    mbar_expect_tx(bar_, MCB_GROUP_BYTES);
-                    tma_bulk_g2s(smem + wbuf, P.st.base + (size_t)(g + gstride) * MCB_GROUP_BYTES, MCB_GROUP_BYTES, bar_);
-                }
-            }
-        } else if (valid) ph.load(P.st, i);
-        if (!valid || !ph.active()) ph.mlo = 0u; else ph.mlo &= ~(1u << 22);
-        const bool was_active = ph.active();
         if (FX && P.do_tally) {
             // between tiles (CTA-uniform): flush before an entry could have received more than fx_flush_trips rounds of deposits
             if (since_flush + P.steps_per_launch > P.fx_flush_trips) {
@@ -604,11 +590,33 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : (NDM == 1 ? (TM 
             }
             since_flush += P.steps_per_launch;
         }
+        if (g >= ngroups) continue;                             // warp-uniform: this warp has no group in the CTA's last tile
+        const int i = g * 32 + (int)lane;
+        const bool valid = i < nslots;
+        Particle ph;
+        // the whole slot is loaded at once (one memory round trip, not meta first and the rest behind its branch); while
+        // the population is full nearly every slot is active, so nothing extra is read.  Slots past nslots in the last group
+        // are zero-filled memory (inactive).
+        if (staged) {
+            uint64_t* bar_ = reinterpret_cast<uint64_t*>(smem + wbar);
+            while (!mbar_try_wait(bar_, wphase)) {}
+            wphase ^= 1u;
+            ph.load_shared(smem + wbuf, lane);
+            __syncwarp();
+            if (lane == 0 && g + gstride < ngroups) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the lanes' reads before the async write
+                mbar_expect_tx(bar_, MCB_GROUP_BYTES);
+                tma_bulk_g2s(smem + wbuf, P.st.base + (size_t)(g + gstride) * MCB_GROUP_BYTES, MCB_GROUP_BYTES, bar_);
+            }
+        } else ph.load(P.st, i);
+        if (!valid || !ph.active()) ph.mlo = 0u; else ph.mlo &= ~(1u << 22);
+        const bool was_active = ph.active();
+        unsigned tile_steps = 0;
         unsigned run_mask = __ballot_sync(0xFFFFFFFFu, was_active);
         for (int s = 0; s < P.steps_per_launch && run_mask != 0u; ++s) {
             // one loop trip (problem.cpp:401-435) in three phases; the tally phase is warp-synchronous
             const bool run = ph.active();
-            if (lane == 0) atomicAdd(&s_cnt[0], (unsigned)__popc(run_mask));
+            tile_steps += __popc(run_mask);
             Segment sg; sg.ok = false; sg.hit = -1; sg.d = 0.0; sg.nscat_before = 0;
             sg.bx = sg.by = sg.bz = sg.ex = sg.ey = sg.ez = 0.0;
             bool escaped = false;
@@ -667,20 +675,20 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : (NDM == 1 ? (TM 
             }
             if (sg.ok) escaped = collide<BOX>(P, T, ph, sg) != 0u;
             const unsigned em = __ballot_sync(0xFFFFFFFFu, escaped);           // rare: Progress::incrEsc problem.cpp:111-118
-            if (em && lane == 0) atomicAdd(&s_cnt[1], (unsigned)__popc(em));
+            if (em && lane == 0) red_shared_u32(&s_cnt[1], (unsigned)__popc(em));
             run_mask = __ballot_sync(0xFFFFFFFFu, ph.active());
         }
         if (was_active) ph.store(P.st, i);
         const unsigned st_mask = __ballot_sync(0xFFFFFFFFu, was_active);
-        if (lane == 0) { atomicAdd(&s_cnt[3], (unsigned)__popc(st_mask)); atomicAdd(&s_cnt[2], (unsigned)__popc(run_mask)); }
+        if (lane == 0) { red_shared_u32(&s_cnt[0], tile_steps); red_shared_u32(&s_cnt[2], (unsigned)__popc(run_mask)); red_shared_u32(&s_cnt[3], (unsigned)__popc(st_mask)); }
         if (list_free) {
             const unsigned fm = __ballot_sync(0xFFFFFFFFu, valid) & ~run_mask;  // valid slots that ended inactive
             if (fm) {
-                unsigned long long pos = 0;
+                unsigned pos = 0;
                 const int leader = __ffs(fm) - 1;
-                if ((int)lane == leader) pos = atomicAdd(&P.ctr->nfree, (unsigned long long)__popc(fm));
+                if ((int)lane == leader) pos = atomicAdd(&s_cnt[4], (unsigned)__popc(fm));
                 pos = __shfl_sync(0xFFFFFFFFu, pos, leader);
-                if ((fm >> lane) & 1u) P.free_list[pos + __popc(fm & ((1u << lane) - 1u))] = (uint32_t)i;
+                if ((fm >> lane) & 1u) my_free[pos + __popc(fm & ((1u << lane) - 1u))] = (uint32_t)i;
             }
         }
     }
@@ -692,6 +700,7 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : (NDM == 1 ? (TM 
         if (s_cnt[1]) atomicAdd(&P.ctr->esc, (unsigned long long)s_cnt[1]);
         if (s_cnt[2]) atomicAdd(&P.ctr->live, (unsigned long long)s_cnt[2]);
         if (s_cnt[3]) atomicAdd(&P.ctr->stores, (unsigned long long)s_cnt[3]);
+        if (P.free_cnt) P.free_cnt[blockIdx.x] = list_free ? s_cnt[4] : 0u;
     }
     // --- flush the shared-memory histogram(s): sum the copies, transpose row-major -> the field's column-major layout,
     //     one fp64 RED per non-zero entry
@@ -710,32 +719,56 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : (NDM == 1 ? (TM 
 
 #ifdef MCB_AUX_KERNELS      // the non-template kernels live in ONE translation unit (mcb_api.cu)
 // ------------------------------------------------------------------------------- k_emit
-// K1, dense: particle next+j is emitted into free slot free_list[j] (problem.cpp:386-399), all lanes busy.
-__global__ void __launch_bounds__(256) k_emit(const StepParams P) {
-    const unsigned long long next = P.ctr->next, nfree = P.ctr->nfree;
-    const unsigned long long room = P.n_end > next ? P.n_end - next : 0ull;
-    const unsigned long long n = nfree < room ? nfree : room;
+// K1, dense: particle next+j is emitted into the j-th free slot (problem.cpp:386-399), all lanes busy.  The free slots are
+// listed per k_step CTA (segment b of free_list holds free_cnt[b] entries); j is mapped to (segment, entry) through the
+// prefix sums of the counts, which every CTA of this kernel recomputes in shared memory (<= a few hundred entries).
+// nseg == 0: the first fill, every slot 0 .. nslots-1 is free.
+#define MCB_MAX_SEG 1024
+__device__ __forceinline__ unsigned long long emit_quota(const StepParams& P, unsigned long long nfree) {
+    const unsigned long long next = P.ctr->next, room = P.n_end > next ? P.n_end - next : 0ull;
+    return nfree < room ? nfree : room;
+}
+__global__ void __launch_bounds__(256) k_emit(const StepParams P, int nseg) {
+    __shared__ unsigned s_pre[MCB_MAX_SEG + 1];
+    unsigned long long nfree = (unsigned long long)P.nslots;
+    if (nseg > 0) {
+        if (threadIdx.x < 32) {                                   // one warp: inclusive scan of the counts, 32 at a time
+            unsigned carry = 0;
+            for (int b0 = 0; b0 < nseg; b0 += 32) {
+                const int b = b0 + (int)threadIdx.x;
+                unsigned v = b < nseg ? P.free_cnt[b] : 0u;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xFFFFFFFFu, v, o); if ((int)threadIdx.x >= o) v += t; }
+                if (b < nseg) s_pre[b + 1] = carry + v;
+                carry += __shfl_sync(0xFFFFFFFFu, v, 31);
+            }
+            if (threadIdx.x == 0) s_pre[0] = 0u;
+        }
+        __syncthreads();
+        nfree = s_pre[nseg];
+    }
+    const unsigned long long next = P.ctr->next, n = emit_quota(P, nfree);
     Tables T;
     T.lambda = reinterpret_cast<const double*>(P.mat_blob + P.mv.off_lambda);
     T.nw = P.mv.nw; T.np = P.mv.np; T.inv_bucket_w = P.mv.inv_bucket_w; T.inv_bucket_p = P.mv.inv_bucket_p;
     for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (unsigned long long)gridDim.x * blockDim.x) {
-        const long long i = (long long)P.free_list[j];
+        long long i = (long long)j;
+        if (nseg > 0) {
+            int lo = 0, hi = nseg;                                 // segment b with pre[b] <= j < pre[b+1]
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((unsigned)j >= s_pre[mid]) lo = mid; else hi = mid; }
+            i = (long long)P.free_list[(size_t)lo * P.free_seg + ((unsigned)j - s_pre[lo])];
+        }
         Particle ph;
         emit_particle(P, T, next + j, ph);
         ph.store(P.st, i);
     }
 }
-// after k_emit: advance the particle counter, empty the free list (one thread)
-__global__ void k_emit_commit(Counters* ctr, unsigned long long n_end) {
-    const unsigned long long room = n_end > ctr->next ? n_end - ctr->next : 0ull;
-    const unsigned long long n = ctr->nfree < room ? ctr->nfree : room;
-    ctr->next += n; ctr->emitted += n; ctr->nfree = 0;
-}
-// all slots free: free_list = 0..n-1
-__global__ void k_free_init(uint32_t* free_list, long long n, Counters* ctr) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) free_list[i] = (uint32_t)i;
-    if (i == 0) ctr->nfree = (unsigned long long)n;
+// after k_emit: advance the particle counter, empty the free lists (one thread)
+__global__ void k_emit_commit(const StepParams P, int nseg) {
+    unsigned long long nfree = (unsigned long long)P.nslots;
+    if (nseg > 0) { nfree = 0; for (int b = 0; b < nseg; ++b) { nfree += P.free_cnt[b]; P.free_cnt[b] = 0u; } }
+    const unsigned long long n = emit_quota(P, nfree);
+    P.ctr->next += n; P.ctr->emitted += n; P.ctr->live = 0ull;
 }
 
 // ------------------------------------------------------------------------------- k_traj
