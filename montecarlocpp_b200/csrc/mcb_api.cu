@@ -257,6 +257,8 @@ void fill_params(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, StepPa
     P->f_wprob = c->f_wprob.p; P->f_pprob = c->f_pprob.p; P->f_walias = c->f_walias.p; P->f_palias = c->f_palias.p;
     P->kind = prob->kind; P->rows = prob->rows; P->cols = (int32_t)c->cols; P->cum_step = prob->step > 0 ? prob->step : 1;
     P->maxscat = prob->maxscat; P->maxloop = prob->maxloop; P->seed = seed;
+    P->maxscat32 = (uint32_t)prob->maxscat; P->maxloop32 = (uint32_t)prob->maxloop;
+    for (int r = 0; r < 10; ++r) { P->rk[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u; P->rk[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u; }
     P->ctr = c->ctr.p; P->field_len = (long long)prob->rows * c->cols;
     P->so_mat = 16; P->so_geo = 16 + c->mv.bytes; P->so_hist = 16 + c->mv.bytes + c->gv.bytes;
     P->so_lambda = P->so_mat + c->mv.off_lambda; P->so_inv_vel = P->so_mat + c->mv.off_inv_vel; P->so_wprob = P->so_mat + c->mv.off_wprob;
@@ -350,9 +352,10 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
         // one segment per k_step CTA, long enough for every slot the CTA visits
         const long long tiles0 = (nslots + plan.block - 1) / plan.block;
         const long long grid0 = std::min<long long>(plan.grid, std::max<long long>(tiles0, 1));
-        if (grid0 > MCB_MAX_SEG) { c->err = "persistent grid too large for the free-list segments"; return MCB_ELIMIT; }
-        P.free_seg = (uint32_t)(((tiles0 + grid0 - 1) / grid0) * plan.block);
-        CUDA_TRY(c, c->free_list.alloc((size_t)grid0 * P.free_seg));
+        const long long nwarps0 = plan.block / 32;
+        if (grid0 * nwarps0 > MCB_MAX_SEG) { c->err = "persistent grid too large for the free-list segments"; return MCB_ELIMIT; }
+        P.free_seg = (uint32_t)(((tiles0 + grid0 - 1) / grid0) * 32);       // one segment per k_step WARP: 32 slots per tile
+        CUDA_TRY(c, c->free_list.alloc((size_t)(grid0 * nwarps0) * P.free_seg));
         CUDA_TRY(c, c->free_cnt.alloc(MCB_MAX_SEG));
         CUDA_TRY(c, cudaMemsetAsync(c->free_cnt.p, 0, MCB_MAX_SEG * sizeof(uint32_t), c->stream));
         P.free_list = c->free_list.p; P.free_cnt = c->free_cnt.p;
@@ -367,13 +370,13 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
         if (dense && !host_all_emitted) {
             // K1: fill the free slots listed by the previous k_step (all of them before the first), with full warps
             k_emit<<<(unsigned)(c->sm_count * 4), 256, 0, c->stream>>>(P, nseg);
-            k_emit_commit<<<1, 1, 0, c->stream>>>(P, nseg);         // also re-arms ctr->live
+            k_emit_commit<<<1, 256, 0, c->stream>>>(P, nseg);         // also re-arms ctr->live
             CUDA_TRY(c, cudaGetLastError());
             launches += 2;
         } else CUDA_TRY(c, cudaMemsetAsync(&c->ctr.p->live, 0, sizeof(unsigned long long), c->stream));   // rewritten by every launch
         const long long tiles = (nslots + plan.block - 1) / plan.block;
         const int grid = (int)std::min<long long>(plan.grid, std::max<long long>(tiles, 1));
-        nseg = grid;
+        nseg = grid * (plan.block / 32);
         CUDA_TRY(c, cudaEventRecord(c->evA[slot], c->stream));
         CUDA_TRY(c, launch_step(P, plan.tm, c->any_nd, c->all_box, plan.pad, grid, plan.block, plan.smem, c->stream));
         CUDA_TRY(c, cudaEventRecord(c->evB[slot], c->stream));
@@ -800,7 +803,7 @@ int mcb_trace(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
     if ((rc = upload_cdf(c, prob))) return rc;
     StepParams P; fill_params(c, prob, seed, &P);
     apply_plan(plan, prob, &P);
-    P.maxloop = std::min<long long>(prob->maxloop, nsteps);
+    P.maxloop = std::min<long long>(prob->maxloop, nsteps); P.maxloop32 = (uint32_t)P.maxloop;
     P.field = nullptr; P.do_tally = 0;
     P.steps_per_launch = (int)std::max<long long>(1, std::min<long long>(P.maxloop, 0x7FFFFFFF)); P.n_end = (unsigned long long)n_end;
     P.st = view_of(c, 0); P.nslots = n; P.free_list = nullptr; P.free_cnt = nullptr;
@@ -808,7 +811,7 @@ int mcb_trace(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
     CUDA_TRY(c, cudaMemcpyAsync(c->ctr.p, &init, sizeof init, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaMemsetAsync(c->state[0].p, 0, state_bytes(c->slots_alloc), c->stream));
     k_emit<<<(unsigned)(c->sm_count * 4), 256, 0, c->stream>>>(P, 0);     // first fill: particle n_begin + j into slot j
-    k_emit_commit<<<1, 1, 0, c->stream>>>(P, 0);
+    k_emit_commit<<<1, 256, 0, c->stream>>>(P, 0);
     CUDA_TRY(c, cudaGetLastError());
     if (P.maxloop > 0) CUDA_TRY(c, launch_step(P, plan.tm, c->any_nd, c->all_box, plan.pad, plan.grid, plan.block, plan.smem, c->stream));
     DevBuf<double> dpos, ddir, dsn; DevBuf<long long> dw, dp, dnscat, dsteps; DevBuf<int32_t> dsign, dalive, dsdom, dcell;
@@ -842,6 +845,8 @@ int mcb_traj(mcb_ctx* c, const mcb_traj_desc* t, uint64_t seed, mcb_traj_out* o)
     StepParams P; std::memset(&P, 0, sizeof P);
     P.mat_blob = c->mat_blob.p; P.mv = c->mv; P.geo_blob = c->geo_blob.p; P.gv = c->gv;
     P.emitters = c->emitters.p; P.nemitter = c->nemitter; P.seed = seed; P.maxscat = t->maxscat; P.maxloop = t->maxloop;
+    P.maxscat32 = (uint32_t)std::min<long long>(t->maxscat, 0x7FFFFFFFll); P.maxloop32 = (uint32_t)t->maxloop;
+    for (int r = 0; r < 10; ++r) { P.rk[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u; P.rk[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u; }
     DevBuf<double> dpts; DevBuf<int32_t> ds[5]; DevBuf<long long> dcnt;
     CUDA_TRY(c, dpts.alloc((size_t)o->max_points * 3)); CUDA_TRY(c, dcnt.alloc(3));
     for (int k = 0; k < 5; ++k) CUDA_TRY(c, ds[k].alloc((size_t)o->max_steps));

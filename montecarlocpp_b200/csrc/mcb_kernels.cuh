@@ -40,6 +40,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t phase) {
     return ok != 0;
 }
 
+// the same three operations on plain 32-bit shared-memory addresses (k_step's per-warp TMA state prefetch)
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s_a(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t phase) {
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(phase) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void lds2(uint32_t a, double& x, double& y) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a));
+}
+__device__ __forceinline__ void lds2(uint32_t a, double& x, unsigned long long& y) {
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=d"(x), "=l"(y) : "r"(a));
+}
+
 // streaming state access (warp-tiled layout, mcb_device.cuh: StateView): 128-bit accesses that do not allocate in L1
 __device__ __forceinline__ void ld_stream2(const void* p, double& a, double& b) {
     asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(p));
@@ -103,14 +124,19 @@ struct Particle {
         mlo = (uint32_t)m; nscat = (uint32_t)(m >> 32);
         return m;
     }
-    // the same slot out of a staged copy of its 2304-B group in shared memory (k_step's TMA prefetch)
-    __device__ __forceinline__ void load_shared(const unsigned char* buf, unsigned lane) {
-        const double2 a = *reinterpret_cast<const double2*>(buf + lane * 16), b = *reinterpret_cast<const double2*>(buf + 512 + lane * 16);
-        const double2 c = *reinterpret_cast<const double2*>(buf + 1024 + lane * 16);
-        const ulonglong2 d = *reinterpret_cast<const ulonglong2*>(buf + 1536 + lane * 16);
-        ps = *reinterpret_cast<const unsigned long long*>(buf + 2048 + lane * 8);
-        px = a.x; py = a.y; pz = b.x; dx = b.y; dy = c.x; dz = c.y; sn = __longlong_as_double((long long)d.x);
-        mlo = (uint32_t)d.y; nscat = (uint32_t)(d.y >> 32);
+    // the same slot out of a staged copy of its 2304-B group in shared memory (k_step's TMA prefetch): av = address of the
+    // lane's first vector (buffer + 16 lane), aw = address of its pid|step word (buffer + 2048 + 8 lane)
+    __device__ __forceinline__ void load_shared(uint32_t av, uint32_t aw) {
+        unsigned long long m;
+        lds2(av, px, py); lds2(av + 512u, pz, dx); lds2(av + 1024u, dy, dz); lds2(av + 1536u, sn, m);
+        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(ps) : "r"(aw));
+        mlo = (uint32_t)m; nscat = (uint32_t)(m >> 32);
+    }
+    // store to slot `lane` of group g
+    __device__ __forceinline__ void store_group(const StateView& st, int g, unsigned lane) const {
+        unsigned char* v = st.base + (size_t)g * MCB_GROUP_BYTES + lane * 16u;
+        st_stream2(v, px, py); st_stream2(v + 512, pz, dx); st_stream2(v + 1024, dy, dz); st_stream2(v + 1536, sn, meta());
+        st_stream1(v + 2048 - lane * 8u, ps);
     }
     __device__ __forceinline__ void store(const StateView& st, long long i) const {
         unsigned char* v = vec_ptr(st, i);
@@ -216,12 +242,14 @@ template <bool BOX>
 __device__ __forceinline__ bool is_inside(const Tables& T, const DSdom& sd, double x, double y, double z) {
     bool in = true;
     if (BOX || sd.aabb) {            // axis-aligned box: n_b.x is x[b]
-        const double p3[3] = {x, y, z};
+        // six signed distances against -eps, OR-ed in one predicate (setp.lt.or): no branches, no min/max detours
         const double neps = -sd.eps;
-        int out = 0;                                             // branch-free: six independent compares
-#pragma unroll
-        for (int b = 0; b < 3; ++b) out |= (int)(p3[b] + sd.offl[b] < neps) | (int)(sd.offh[b] - p3[b] < neps);
-        return out == 0;
+        const double s0 = x + sd.offl[0], s1 = sd.offh[0] - x, s2 = y + sd.offl[1], s3 = sd.offh[1] - y, s4 = z + sd.offl[2], s5 = sd.offh[2] - z;
+        uint32_t out;
+        asm("{\n .reg .pred p;\n setp.lt.f64 p, %1, %7;\n setp.lt.or.f64 p, %2, %7, p;\n setp.lt.or.f64 p, %3, %7, p;\n"
+            " setp.lt.or.f64 p, %4, %7, p;\n setp.lt.or.f64 p, %5, %7, p;\n setp.lt.or.f64 p, %6, %7, p;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(out) : "d"(s0), "d"(s1), "d"(s2), "d"(s3), "d"(s4), "d"(s5), "d"(neps));
+        return out == 0u;
     }
     if (sd.is_box) {                 // planes b and b+3 share n.pos up to sign: three dot products
 #pragma unroll
@@ -326,8 +354,8 @@ struct Draw {
 };
 __device__ __forceinline__ void draw_event(const StepParams& P, const Tables& T, uint32_t pid_lo, uint32_t pid_hi, uint32_t event, Draw& o) {
     uint32_t a[4], b[4];
-    philox4x32_10(pid_lo, pid_hi, event, 0u, (uint32_t)P.seed, (uint32_t)(P.seed >> 32), a);
-    philox4x32_10(pid_lo, pid_hi, event, 1u, (uint32_t)P.seed, (uint32_t)(P.seed >> 32), b);
+    philox4x32_10_rk(pid_lo, pid_hi, event, 0u, P.rk, a);
+    philox4x32_10_rk(pid_lo, pid_hi, event, 1u, P.rk, b);
     uint32_t r = (uint32_t)(((double)a[0] + 0.5) * T.inv_bucket_w);
     uint32_t q = (uint32_t)(((double)a[2] + 0.5) * T.inv_bucket_p);
     bool ok = r < (uint32_t)T.nw && q < (uint32_t)T.np;
@@ -340,8 +368,9 @@ __device__ __forceinline__ void draw_event(const StepParams& P, const Tables& T,
     double sp, cp; sincospi_unit(fma((double)b[1], c_k[26], -1.0), &sp, &cp);
     const double dist = T.lambda[wp] * neg_log1m_u32(b[2]);           // drawScatNext material.cpp:215-224
     o.ok = ok && !(dist < c_k[27]);
+    // (sth cp, sth sp, c) is unit to ~2e-16 by construction; Phonon::dir's normalisation (phonon.cpp:88-93) would move it by
+    // <= 1 ulp per component, which is the size of the other documented deviations: it is skipped
     o.wp = wp; o.dx = sth * cp; o.dy = sth * sp; o.dz = c; o.dist = dist;
-    renorm_drawn(o.dx, o.dy, o.dz);
 }
 
 // Second half of a loop trip (problem.cpp:418-434): Boundary::scatter or Material::scatter, then the stop test.
@@ -401,7 +430,7 @@ __device__ __forceinline__ uint32_t collide(const StepParams& P, const Tables& T
         }
         ph.nscat++;
     }
-    if ((long long)ph.nscat >= P.maxscat || (long long)ph.step() >= P.maxloop) ph.stop();     // :434, :401
+    if (ph.nscat >= P.maxscat32 || ph.step() >= P.maxloop32) ph.stop();                       // :434, :401
     return esc;
 }
 
@@ -543,38 +572,41 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : (NDM == 1 ? (TM 
     constexpr bool FX = MCB_TALLY_FX && TM == MCB_TM_WARP;        // fixed-point warp histograms (mcb_device.cuh: deposit)
     const uint32_t hi_off = 4u * (uint32_t)P.field_len;            // low-word plane, then high-word plane
 
-    // counters of this launch: warp-uniform values from ballots, added by lane 0 to four CTA-wide words in shared memory
-    // where they arise -- no per-thread counter registers live across the loop trip
-    __shared__ unsigned s_cnt[5];                               // steps, esc, live, stores, freed slots  (< 2^32 per CTA and launch)
-    if (threadIdx.x < 5) s_cnt[threadIdx.x] = 0u;
+    // counters of this launch: warp-uniform values from ballots, kept in a 16-byte slot per warp in shared memory that lane 0
+    // reads, bumps and writes back once per tile -- no per-thread counter registers live across the loop trip, no atomics
+    __shared__ uint4 s_wcnt[32];                                // per warp: steps, live, stores, freed slots  (< 2^32 per launch)
+    __shared__ unsigned s_esc;
+    if (lane == 0) s_wcnt[warp] = make_uint4(0u, 0u, 0u, 0u);
+    if (threadIdx.x == 0) s_esc = 0u;
     // fixed-point histograms are flushed by the CTA between tiles at least every fx_flush_trips loop trips (the host keeps
     // steps_per_launch below that), which bounds the number of deposits an entry can receive (set_fixed_point, mcb_api.cu)
     int since_flush = 0;
     // dense emission: free slots are only LISTED here; k_emit fills them between launches with full warps (emitting
-    // inside this kernel runs the long emission path for a few dead lanes per warp at ~5 % lane efficiency).  Every CTA
-    // appends to its OWN segment of the list through a shared-memory cursor (a global cursor made every warp wait for a
-    // returning L2 atomic once per tile) and publishes its count at the end.
+    // inside this kernel runs the long emission path for a few dead lanes per warp at ~5 % lane efficiency).  Every WARP
+    // appends to its own segment of the list (cursor = the warp's counter slot; a global cursor made every warp wait for
+    // a returning L2 atomic once per tile) and the CTA publishes the counts at the end.
     const bool list_free = P.free_list != nullptr && P.ctr->next < P.n_end;
-    uint32_t* const my_free = P.free_list + (size_t)blockIdx.x * P.free_seg;
+    uint32_t* const my_free = P.free_list + (size_t)(blockIdx.x * nwarps + warp) * P.free_seg;
 
     // TMA state prefetch: a warp's 32 slots are one contiguous 2304-B group (StateView), bulk-copied into the warp's staging
     // buffer while the warp works on the group before it.  The buffer is free again as soon as the lanes have moved their
     // slot into registers, so ONE buffer per warp keeps a full tile in flight.
     const bool staged = P.so_stage != 0u;
-    const uint32_t wbuf = P.so_stage + warp * MCB_GROUP_BYTES, wbar = P.so_wbar + warp * 8u;     // offsets into smem[]
+    const uint32_t a_buf = smem_u32(smem) + P.so_stage + warp * MCB_GROUP_BYTES;        // shared-memory addresses
+    const uint32_t a_bar = smem_u32(smem) + P.so_wbar + warp * 8u;
     const int ngroups = (int)((P.nslots + 31) >> 5);            // slots < 2^31 (plan_run)
     const int gstride = (int)(gridDim.x * nwarps);
     uint32_t wphase = 0;
     if (staged) {
         const int g0 = (int)(blockIdx.x * nwarps + warp);
-        if (lane == 0) { mbar_init(reinterpret_cast<uint64_t*>(smem + wbar), 1); fence_mbar_init(); }
+        if (lane == 0) { mbar_init(reinterpret_cast<uint64_t*>(smem + P.so_wbar) + warp, 1); fence_mbar_init(); }
         __syncwarp();
         if (lane == 0 && g0 < ngroups) {
-            mbar_expect_tx(reinterpret_cast<uint64_t*>(smem + wbar), MCB_GROUP_BYTES);
-            tma_bulk_g2s(smem + wbuf, P.st.base + (size_t)g0 * MCB_GROUP_BYTES, MCB_GROUP_BYTES, reinterpret_cast<uint64_t*>(smem + wbar));
+            mbar_expect_tx_a(a_bar, MCB_GROUP_BYTES);
+            tma_bulk_g2s_a(a_buf, P.st.base + (size_t)g0 * MCB_GROUP_BYTES, MCB_GROUP_BYTES, a_bar);
         }
     }
-    __syncthreads();                                            // s_cnt is armed
+    __syncthreads();                                            // the counter slots are armed
 
     // tile = one group of 32 slots per warp: group g = (blockIdx + k gridDim) nwarps + warp; the trip count is CTA-uniform
     const int nslots = (int)P.nslots;
@@ -592,27 +624,27 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : (NDM == 1 ? (TM 
         }
         if (g >= ngroups) continue;                             // warp-uniform: this warp has no group in the CTA's last tile
         const int i = g * 32 + (int)lane;
-        const bool valid = i < nslots;
         Particle ph;
         // the whole slot is loaded at once (one memory round trip, not meta first and the rest behind its branch); while
         // the population is full nearly every slot is active, so nothing extra is read.  Slots past nslots in the last group
         // are zero-filled memory (inactive).
         if (staged) {
-            uint64_t* bar_ = reinterpret_cast<uint64_t*>(smem + wbar);
-            while (!mbar_try_wait(bar_, wphase)) {}
+            while (!mbar_try_wait_a(a_bar, wphase)) {}
             wphase ^= 1u;
-            ph.load_shared(smem + wbuf, lane);
-            __syncwarp();
-            if (lane == 0 && g + gstride < ngroups) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the lanes' reads before the async write
-                mbar_expect_tx(bar_, MCB_GROUP_BYTES);
-                tma_bulk_g2s(smem + wbuf, P.st.base + (size_t)(g + gstride) * MCB_GROUP_BYTES, MCB_GROUP_BYTES, bar_);
-            }
+            ph.load_shared(a_buf + lane * 16u, a_buf + 2048u + lane * 8u);
         } else ph.load(P.st, i);
-        if (!valid || !ph.active()) ph.mlo = 0u; else ph.mlo &= ~(1u << 22);
+        if (i >= nslots || !ph.active()) ph.mlo = 0u; else ph.mlo &= ~(1u << 22);
         const bool was_active = ph.active();
         unsigned tile_steps = 0;
         unsigned run_mask = __ballot_sync(0xFFFFFFFFu, was_active);
+        if (staged && lane == 0 && g + gstride < ngroups) {
+            // Refill the staging buffer with the warp's next group.  The ballot above consumed every lane's last-loaded
+            // word, so all the lanes' shared-memory reads of the buffer have completed (loads of a warp complete in order);
+            // the bulk copy is ordered behind them by that dependency, like a consumer-release / producer-acquire pair --
+            // no proxy fence (its MEMBAR also waited for the previous tile's global stores: -5 %).
+            mbar_expect_tx_a(a_bar, MCB_GROUP_BYTES);
+            tma_bulk_g2s_a(a_buf, P.st.base + (size_t)(g + gstride) * MCB_GROUP_BYTES, MCB_GROUP_BYTES, a_bar);
+        }
         for (int s = 0; s < P.steps_per_launch && run_mask != 0u; ++s) {
             // one loop trip (problem.cpp:401-435) in three phases; the tally phase is warp-synchronous
             const bool run = ph.active();
@@ -674,33 +706,33 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : (NDM == 1 ? (TM 
                 }
             }
             if (sg.ok) escaped = collide<BOX>(P, T, ph, sg) != 0u;
-            const unsigned em = __ballot_sync(0xFFFFFFFFu, escaped);           // rare: Progress::incrEsc problem.cpp:111-118
-            if (em && lane == 0) red_shared_u32(&s_cnt[1], (unsigned)__popc(em));
+            if (escaped) red_shared_u32(&s_esc, 1u);                           // rare: Progress::incrEsc problem.cpp:111-118
             run_mask = __ballot_sync(0xFFFFFFFFu, ph.active());
         }
-        if (was_active) ph.store(P.st, i);
+        if (was_active) ph.store_group(P.st, g, lane);
+        // end of the tile: list the slots that ended inactive (every slot of the group exists in memory; k_emit only takes
+        // ids below nslots), bump the warp's counters
         const unsigned st_mask = __ballot_sync(0xFFFFFFFFu, was_active);
-        if (lane == 0) { red_shared_u32(&s_cnt[0], tile_steps); red_shared_u32(&s_cnt[2], (unsigned)__popc(run_mask)); red_shared_u32(&s_cnt[3], (unsigned)__popc(st_mask)); }
-        if (list_free) {
-            const unsigned fm = __ballot_sync(0xFFFFFFFFu, valid) & ~run_mask;  // valid slots that ended inactive
-            if (fm) {
-                unsigned pos = 0;
-                const int leader = __ffs(fm) - 1;
-                if ((int)lane == leader) pos = atomicAdd(&s_cnt[4], (unsigned)__popc(fm));
-                pos = __shfl_sync(0xFFFFFFFFu, pos, leader);
-                if ((fm >> lane) & 1u) my_free[pos + __popc(fm & ((1u << lane) - 1u))] = (uint32_t)i;
-            }
+        const unsigned fm = list_free ? __ballot_sync(0xFFFFFFFFu, i < nslots) & ~run_mask : 0u;
+        uint4 wc = s_wcnt[warp];                                // broadcast read; only lane 0 writes it back
+        if ((fm >> lane) & 1u) my_free[wc.w + __popc(fm & ((1u << lane) - 1u))] = (uint32_t)i;
+        if (lane == 0) {
+            wc.x += tile_steps; wc.y += __popc(run_mask); wc.z += __popc(st_mask); wc.w += __popc(fm);
+            s_wcnt[warp] = wc;
         }
+        __syncwarp();
     }
 
-    // --- the CTA's counters: one global atomic each
+    // --- the CTA's counters: one global atomic each; the warps' free-list counts
     __syncthreads();
+    if (threadIdx.x < nwarps && P.free_cnt) P.free_cnt[blockIdx.x * nwarps + threadIdx.x] = list_free ? s_wcnt[threadIdx.x].w : 0u;
     if (threadIdx.x == 0) {
-        if (s_cnt[0]) atomicAdd(&P.ctr->steps, (unsigned long long)s_cnt[0]);
-        if (s_cnt[1]) atomicAdd(&P.ctr->esc, (unsigned long long)s_cnt[1]);
-        if (s_cnt[2]) atomicAdd(&P.ctr->live, (unsigned long long)s_cnt[2]);
-        if (s_cnt[3]) atomicAdd(&P.ctr->stores, (unsigned long long)s_cnt[3]);
-        if (P.free_cnt) P.free_cnt[blockIdx.x] = list_free ? s_cnt[4] : 0u;
+        unsigned long long st = 0, lv = 0, so = 0;
+        for (unsigned w = 0; w < nwarps; ++w) { st += s_wcnt[w].x; lv += s_wcnt[w].y; so += s_wcnt[w].z; }
+        if (st) atomicAdd(&P.ctr->steps, st);
+        if (s_esc) atomicAdd(&P.ctr->esc, (unsigned long long)s_esc);
+        if (lv) atomicAdd(&P.ctr->live, lv);
+        if (so) atomicAdd(&P.ctr->stores, so);
     }
     // --- flush the shared-memory histogram(s): sum the copies, transpose row-major -> the field's column-major layout,
     //     one fp64 RED per non-zero entry
@@ -723,7 +755,7 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : (NDM == 1 ? (TM 
 // listed per k_step CTA (segment b of free_list holds free_cnt[b] entries); j is mapped to (segment, entry) through the
 // prefix sums of the counts, which every CTA of this kernel recomputes in shared memory (<= a few hundred entries).
 // nseg == 0: the first fill, every slot 0 .. nslots-1 is free.
-#define MCB_MAX_SEG 1024
+#define MCB_MAX_SEG 8192          /* k_step warps: 148 CTAs x <= 32 warps (x ctas_per_sm) */
 __device__ __forceinline__ unsigned long long emit_quota(const StepParams& P, unsigned long long nfree) {
     const unsigned long long next = P.ctr->next, room = P.n_end > next ? P.n_end - next : 0ull;
     return nfree < room ? nfree : room;
@@ -732,11 +764,13 @@ __global__ void __launch_bounds__(256) k_emit(const StepParams P, int nseg) {
     __shared__ unsigned s_pre[MCB_MAX_SEG + 1];
     unsigned long long nfree = (unsigned long long)P.nslots;
     if (nseg > 0) {
+        for (int b = (int)threadIdx.x; b < nseg; b += (int)blockDim.x) s_pre[b + 1] = P.free_cnt[b];      // coalesced, in flight together
+        __syncthreads();
         if (threadIdx.x < 32) {                                   // one warp: inclusive scan of the counts, 32 at a time
             unsigned carry = 0;
             for (int b0 = 0; b0 < nseg; b0 += 32) {
                 const int b = b0 + (int)threadIdx.x;
-                unsigned v = b < nseg ? P.free_cnt[b] : 0u;
+                unsigned v = b < nseg ? s_pre[b + 1] : 0u;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xFFFFFFFFu, v, o); if ((int)threadIdx.x >= o) v += t; }
                 if (b < nseg) s_pre[b + 1] = carry + v;
@@ -763,12 +797,20 @@ __global__ void __launch_bounds__(256) k_emit(const StepParams P, int nseg) {
         ph.store(P.st, i);
     }
 }
-// after k_emit: advance the particle counter, empty the free lists (one thread)
-__global__ void k_emit_commit(const StepParams P, int nseg) {
-    unsigned long long nfree = (unsigned long long)P.nslots;
-    if (nseg > 0) { nfree = 0; for (int b = 0; b < nseg; ++b) { nfree += P.free_cnt[b]; P.free_cnt[b] = 0u; } }
-    const unsigned long long n = emit_quota(P, nfree);
-    P.ctr->next += n; P.ctr->emitted += n; P.ctr->live = 0ull;
+// after k_emit: advance the particle counter, empty the free lists (one CTA)
+__global__ void __launch_bounds__(256) k_emit_commit(const StepParams P, int nseg) {
+    __shared__ unsigned long long s_sum;
+    if (threadIdx.x == 0) s_sum = 0ull;
+    __syncthreads();
+    unsigned mine = 0;
+    for (int b = (int)threadIdx.x; b < nseg; b += (int)blockDim.x) { mine += P.free_cnt[b]; P.free_cnt[b] = 0u; }
+    mine = __reduce_add_sync(0xFFFFFFFFu, mine);
+    if ((threadIdx.x & 31u) == 0u && mine) atomicAdd(&s_sum, (unsigned long long)mine);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long n = emit_quota(P, nseg > 0 ? s_sum : (unsigned long long)P.nslots);
+        P.ctr->next += n; P.ctr->emitted += n; P.ctr->live = 0ull;
+    }
 }
 
 // ------------------------------------------------------------------------------- k_traj
