@@ -171,6 +171,7 @@ struct RunPlan {
     // 1-D difference-array histograms (tm == MCB_TM_WARP, no N-D grid): padded columns (0 = run-time stride), plane stride,
     // warps per histogram group, flush interval in loop trips, offset of the flush scratch
     int t1d, pad, trips; uint32_t ps, inst_bytes, scratch_off, stage_off, wbar_off;
+    uint32_t cstride;                   // MCB_TM_BLOCK: bytes per histogram column
 };
 
 #define MCB_FX_FLUSH_TRIPS 16
@@ -183,69 +184,65 @@ struct RunPlan {
 
 int plan_run(mcb_ctx* c, const mcb_problem_desc* prob, long long nparticles, RunPlan* r) {
     const mcb_options& o = c->opt;
-    // the N-D kernels are built for fewer, fatter threads; the serial N-D walk with warp-private histograms wants 128 registers
-    // (512 threads), with the CTA histogram / the global field 80 (768 threads): try the warp-histogram shape first
     const int per_sm = o.ctas_per_sm > 0 ? o.ctas_per_sm : 1;
     const size_t base = 16 + (size_t)c->mv.bytes + (size_t)c->gv.bytes;
-    const size_t hist = (size_t)prob->rows * (size_t)c->cols * sizeof(double);
     const size_t budget = c->smem_optin / (size_t)per_sm > 1024 ? c->smem_optin / (size_t)per_sm - 1024 : 0;
-    int block_max = c->any_nd == 2 ? MCB_BLOCK_MAX_ND : (c->any_nd == 1 ? MCB_BLOCK_MAX_ND1 : MCB_BLOCK_MAX);
-    if (c->any_nd == 1 && o.tally_mode != 2 && o.tally_mode != 3) {
-        const int bw = o.block > 0 ? std::min(o.block, MCB_BLOCK_MAX_ND1W) : MCB_BLOCK_MAX_ND1W;
-        if (o.tally_mode == 1 || base + hist * (size_t)(bw / 32) <= budget) block_max = MCB_BLOCK_MAX_ND1W;
-    }
+    // CTA shapes (__launch_bounds__ of the k_step instances): 1-D tallies 768 threads x 80 registers; the N-D walks are built for
+    // fewer, fatter threads
+    const int block_max = c->any_nd == 2 ? MCB_BLOCK_MAX_ND : (c->any_nd == 1 ? MCB_BLOCK_MAX_ND1 : MCB_BLOCK_MAX);
     r->block = o.block > 0 ? std::min(o.block, block_max) : block_max;
-    if (r->block % 32 != 0 || o.block > MCB_BLOCK_MAX) { c->err = "block must be a multiple of 32, <= " + std::to_string(MCB_BLOCK_MAX); return MCB_EINVAL; }
+    if (r->block % 32 != 0 || o.block > 1024) { c->err = "block must be a multiple of 32, <= 1024"; return MCB_EINVAL; }
     r->S = o.steps_per_launch > 0 ? o.steps_per_launch : 16;
-    long long slots = o.slots > 0 ? o.slots : (long long)c->sm_count * r->block * 32;   // ~2.4 M resident phonons
+    long long slots = o.slots > 0 ? o.slots : (long long)c->sm_count * r->block * 32;   // ~3.6 M resident phonons
     slots = std::min(slots, std::max<long long>(nparticles, 1));
     if (slots > 0x7FFFFF00ll) { c->err = "too many resident slots (< 2^31)"; return MCB_ELIMIT; }
     r->slots = slots;
     const long long tiles = (slots + r->block - 1) / r->block;
     r->grid = (int)std::min<long long>((long long)c->sm_count * per_sm, std::max<long long>(tiles, 1));
     const size_t nwarps = (size_t)r->block / 32;
-    r->t1d = 0; r->pad = 0; r->trips = MCB_FX_FLUSH_TRIPS; r->ps = 0; r->inst_bytes = 0; r->scratch_off = 0; r->stage_off = 0; r->wbar_off = 0; r->copies = 1;
-    // 1-D / single-cell tallies: difference-array histograms (mcb_device.cuh: deposit_fx).  An instance holds
+    r->t1d = 0; r->pad = 0; r->trips = MCB_FX_FLUSH_TRIPS; r->ps = 0; r->inst_bytes = 0; r->scratch_off = 0; r->stage_off = 0; r->wbar_off = 0;
+    r->copies = 1; r->cstride = 0; r->tm = MCB_TM_GLOBAL;
+    const size_t stage = nwarps * (MCB_GROUP_BYTES + 8) + 128;       // per-warp staging buffers of the TMA state prefetch + mbarriers
+    auto place_stage = [&](size_t end) {                               // staging area behind everything else, if it fits
+        if (end + stage > budget) return end;
+        r->stage_off = (uint32_t)((end + 127) / 128 * 128); r->wbar_off = r->stage_off + (uint32_t)(nwarps * MCB_GROUP_BYTES);
+        return (size_t)r->wbar_off + nwarps * 8;
+    };
+    const long long fdep = c->any_nd == 2 ? 3 : 1;                     // deposits of one flight into one entry (cooperative N-D walk: <= 3)
+    // (1) 1-D / single-cell tallies: difference-array histograms (mcb_device.cuh: deposit_fx).  An instance holds
     // [direct | difference][row][limb 0 | 1 | 2] planes of `ps` bytes and is shared by the whole CTA; up to 4 copies (picked by
-    // lane id) thin out same-word hits inside a warp instruction.  The per-warp staging buffers of the TMA state prefetch
-    // come first; copies take what is left.
+    // lane id) thin out same-word hits inside a warp instruction.  The state staging buffers come first, copies take the rest.
     if (c->any_nd == 0 && c->t1_ok && o.tally_mode != 2 && o.tally_mode != 3) {
         const int pad = c->cols <= 32 ? 32 : (c->cols <= 128 ? 128 : (c->cols <= 512 ? 512 : 0));
         const uint32_t ps = 4u * (uint32_t)(pad > 0 ? pad : (int)((c->cols + 31) / 32 * 32));
         const size_t inst = (size_t)prob->rows * 2u * MCB_T1D_LIMBS * ps;
         const size_t scratch = ((size_t)prob->rows * (size_t)c->cols * 2 + (size_t)prob->rows * (size_t)((c->cols + 31) / 32)) * 8 + 16;
-        const size_t stage = nwarps * (MCB_GROUP_BYTES + 8);
         for (int st = 1; st >= 0 && !r->t1d; --st)
             for (int cp = 4; cp >= 1; cp >>= 1)
-                if (base + inst * (size_t)cp + scratch + (st ? stage + 128 : 0) <= budget) {
+                if (base + inst * (size_t)cp + scratch + (st ? stage : 0) <= budget) {
                     r->t1d = 1; r->pad = c->all_box ? pad : 0; r->copies = cp; r->ps = ps; r->inst_bytes = (uint32_t)inst;
-                    // an entry receives at most (threads sharing the copy) deposits per loop trip; 2^16 between two flushes
-                    r->trips = (int)std::min<long long>(256, 65536ll / std::max(1, r->block / cp));
                     r->tm = MCB_TM_WARP;
                     r->scratch_off = (uint32_t)((base + inst * (size_t)cp + 15) / 16 * 16);
-                    size_t end = r->scratch_off + scratch;
-                    if (st) { r->stage_off = (uint32_t)((end + 127) / 128 * 128); r->wbar_off = r->stage_off + (uint32_t)(nwarps * MCB_GROUP_BYTES); end = r->wbar_off + nwarps * 8; }
-                    r->smem = end;
+                    r->smem = place_stage(r->scratch_off + scratch);
                     break;
                 }
-        if (r->t1d) return MCB_OK;
-        if (o.tally_mode == 1) { c->err = "tally_mode=1 (shared-memory histograms) does not fit in shared memory"; return MCB_ELIMIT; }
     }
-    // tally placement: warp-private histograms when they fit, else one per CTA, else the global field in L2
-    int tm = MCB_TM_GLOBAL;
-    if (c->any_nd != 0 && base + hist * nwarps <= budget) tm = MCB_TM_WARP;
-    else if (base + hist <= budget) tm = MCB_TM_BLOCK;
-    if (o.tally_mode == 1) {
-        if (c->any_nd == 0) { c->err = "tally_mode=1 needs unit-stride 1-D tally grids"; return MCB_ELIMIT; }
-        tm = MCB_TM_WARP; if (base + hist * nwarps > c->smem_optin) { c->err = "tally_mode=1 (warp histograms) does not fit in shared memory"; return MCB_ELIMIT; }
+    // (2) any grid: one three-limb histogram per CTA (mcb_device.cuh: deposit), walked cell by cell; up to 4 copies by lane id
+    if (!r->t1d && o.tally_mode != 2) {
+        const uint32_t cstride = 4u * (uint32_t)((3 * prob->rows) | 1);
+        const size_t inst = (size_t)c->cols * cstride;
+        for (int cp = 4; cp >= 1; cp >>= 1)
+            if (base + inst * (size_t)cp <= budget && inst < 0xFFFFFFFFull) {
+                r->tm = MCB_TM_BLOCK; r->copies = cp; r->cstride = cstride; r->inst_bytes = (uint32_t)inst;
+                r->smem = place_stage(base + inst * (size_t)cp);
+                break;
+            }
+        if (r->tm != MCB_TM_BLOCK && (o.tally_mode == 1 || o.tally_mode == 3)) { c->err = "tally_mode: the shared-memory histogram does not fit"; return MCB_ELIMIT; }
     }
-    if (o.tally_mode == 3) { tm = MCB_TM_BLOCK; if (base + hist > c->smem_optin) { c->err = "tally_mode=3 (CTA histogram) does not fit in shared memory"; return MCB_ELIMIT; } }
-    if (o.tally_mode == 2) tm = MCB_TM_GLOBAL;
-    // a kernel built for 512 threads must not be launched with more: the warp-histogram N-D kernel is only reachable with block <= 512
-    if (c->any_nd == 1 && tm == MCB_TM_WARP && r->block > MCB_BLOCK_MAX_ND1W) { c->err = "internal: warp-histogram N-D kernel launched too wide"; return MCB_EINVAL; }
-    r->tm = tm; r->copies = 1;
-    if (tm == MCB_TM_WARP) for (int cp = 4; cp > 1; cp >>= 1) if (base + hist * nwarps * cp <= budget) { r->copies = cp; break; }
-    r->smem = base + (tm == MCB_TM_WARP ? hist * nwarps * r->copies : (tm == MCB_TM_BLOCK ? hist : 0));
+    // (3) the global field in L2 (fp64 RED)
+    if (r->tm == MCB_TM_GLOBAL) r->smem = place_stage(base);
+    if (r->tm != MCB_TM_GLOBAL)          // an entry receives at most (threads sharing the copy) x fdep deposits per loop trip; 2^16 between two flushes
+        r->trips = (int)std::max<long long>(1, std::min<long long>(256, 65536ll / (std::max(1, r->block / r->copies) * fdep)));
     if (r->smem > c->smem_optin) { c->err = "material + geometry tables exceed the shared-memory staging area"; return MCB_ELIMIT; }
     return MCB_OK;
 }
@@ -269,24 +266,21 @@ void fill_params(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, StepPa
 void apply_plan(const RunPlan& plan, const mcb_problem_desc* prob, StepParams* P) {
     P->tally_smem = plan.tm; P->hist_copies = plan.copies;
     P->fx_ps = plan.ps; P->fx_diff_off = (uint32_t)prob->rows * MCB_T1D_LIMBS * plan.ps; P->hist_bytes = plan.inst_bytes; P->so_scratch = plan.scratch_off;
-    P->so_stage = plan.stage_off; P->so_wbar = plan.wbar_off;
+    P->so_stage = plan.stage_off; P->so_wbar = plan.wbar_off; P->fx_cstride = plan.cstride;
 }
 
-// Fixed-point scale of the shared-memory tallies.  Payload component k of a flight is accepted up to fx_max = 2^E >
-// flight_max (* the 99.9 % slowness for the dt row; anything larger takes the exact fp64 path) and deposited as
-// q = rint(v 2^(Q-1-E)), |q| <= 2^(Q-1).  A histogram is flushed at least every `trips` loop trips (k_step flushes between
-// tiles and the schedule keeps steps_per_launch <= trips), so an entry receives at most N <= 2^n deposits between flushes.
-//  * N-D walks, warp-private two-limb histograms (mcb_device.cuh: deposit): N = f x 32 lanes x 16 trips, f = 1 deposit per
-//    flight and cell (3 for the cooperative N-D walk, whose pieces can share a cell); low limb B = 32 - n bits, Q = 63 - 2n
-//    (n = 9: B = 23, Q = 45).
-//  * 1-D difference-array histograms, three limbs shared by the CTA (deposit_fx): N = (threads per copy) x trips <= 2^16,
-//    Q = 64 - n capped at 50 (the rounding trick holds |q| < 2^51): quantum 2^-47 .. 2^-49 of fx_max.
+// Fixed-point scale of the shared-memory tallies (mcb_device.cuh: deposit, deposit_fx).  Payload component k of a flight is
+// accepted up to fx_max = 2^E > flight_max (* the 99.9 % slowness for the dt row; anything larger takes the exact fp64 path)
+// and deposited as q = rint(v 2^(Q-1-E)), |q| <= 2^(Q-1), in three carry-free limbs.  A histogram is flushed at least every
+// `trips` loop trips (k_step flushes between tiles and the schedule keeps steps_per_launch <= trips), so an entry receives at
+// most N = (threads sharing the copy) x trips x f <= 2^n <= 2^16 deposits between flushes (f = 1 deposit per flight and cell;
+// 3 for the cooperative N-D walk, whose pieces can share a cell): the 16-bit limb fields sum below 2^32 and the top limb
+// stays inside int32 for Q = 64 - n, capped at 50 (the rounding trick holds |q| < 2^51): quantum 2^-47 .. 2^-49 of fx_max.
 void set_fixed_point(mcb_ctx* c, const mcb_problem_desc* prob, const RunPlan& plan, StepParams* P) {
-    const long long bound = plan.t1d ? (long long)std::max(1, plan.block / plan.copies) * plan.trips
-                                     : (c->any_nd == 2 ? 3ll : 1ll) * 32ll * plan.trips;
-    int n = 0; while ((1ll << n) < bound) ++n;                                             // bound <= 2^n
-    const int B = 32 - n, QB = plan.t1d ? std::min(50, 64 - n) : std::min(50, 63 - 2 * n);
-    P->fx_limb_bits = B;
+    const long long bound = (long long)std::max(1, plan.block / plan.copies) * plan.trips * (c->any_nd == 2 ? 3 : 1);
+    int n = 0; while ((1ll << n) < bound) ++n;                                             // bound <= 2^n <= 2^16
+    const int QB = std::min(50, 64 - n);
+    P->fx_limb_bits = 16;
     for (int k = 0; k < 4; ++k) {
         const bool is_dt = (prob->kind == MCB_PROB_TEMP || prob->kind == MCB_PROB_CUMTEMP || prob->kind == MCB_PROB_MULTI) && k == 0;
         const double amax = c->flight_max * (is_dt ? c->inv_vel_fx : 1.0);
@@ -365,7 +359,7 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
     if (total > 0) for (long long it = 0;; ++it) {
         const int slot = (int)(it & 1);
         // fixed-point histograms are flushed between tiles: keep a tile's loop trips within the flush interval
-        if (MCB_TALLY_FX && plan.tm == MCB_TM_WARP) S_cur = std::min(S_cur, plan.trips);
+        if (plan.tm != MCB_TM_GLOBAL) S_cur = std::min(S_cur, plan.trips);
         P.st = view_of(c, cur); P.nslots = nslots; P.steps_per_launch = S_cur;
         if (dense && !host_all_emitted) {
             // K1: fill the free slots listed by the previous k_step (all of them before the first), with full warps

@@ -434,23 +434,25 @@ __device__ __forceinline__ uint32_t collide(const StepParams& P, const Tables& T
     return esc;
 }
 
-// Flush `ncopy` fixed-point histogram copies (two 32-bit limb planes each, mcb_device.cuh: deposit) into the global fp64
-// field: every copy's entry is recombined as (int32 high limb << B) + low limb, the copies are summed as 64-bit integers
-// (exact, order-free), converted once, transposed from the histograms' row-major layout to the field's column-major one,
-// and re-armed with zeros.  `tid`/`nthr` = the cooperating threads (the CTA, between tiles and at the end of a launch).
+// sum(q) of one histogram entry from its three limbs (mcb_device.cuh: deposit / deposit_fx)
+__device__ __forceinline__ long long limbs_value(uint32_t p0, uint32_t p1, uint32_t p2) {
+    const uint32_t sb = p1 - (p2 << 16), sa = p0 - (sb << 16);
+    return (long long)(int32_t)p2 * 4294967296ll + (long long)sb * 65536ll + (long long)sa;
+}
+// Flush the CTA's `ncopy` three-limb histograms (MCB_TM_BLOCK) into the global fp64 field: per entry the copies are recombined
+// and summed as 64-bit integers (exact, order-free), converted once and added with one fp64 RED; the limbs are re-armed
+// with zeros.  Entries are taken in the field's own column-major order.
 template <int NCOMP>
-__device__ __forceinline__ void flush_fixed_point(uint32_t* words, unsigned ncopy, const StepParams& P, unsigned tid, unsigned nthr) {
-    for (long long i = tid; i < P.field_len; i += nthr) {                         // i = r*cols + c in the histograms
+__device__ __forceinline__ void flush_block_fx(unsigned char* hist, unsigned ncopy, const StepParams& P, unsigned tid, unsigned nthr) {
+    for (long long e = tid; e < P.field_len; e += nthr) {
+        const long long c = e / P.rows; const int r = (int)(e - c * P.rows);
         long long acc = 0;
         for (unsigned w = 0; w < ncopy; ++w) {
-            uint32_t* h = words + 2ll * w * P.field_len;
-            acc += (long long)(int32_t)h[P.field_len + i] * (1ll << P.fx_limb_bits) + (long long)h[i];
-            h[i] = 0u; h[P.field_len + i] = 0u;
+            uint32_t* q = reinterpret_cast<uint32_t*>(hist + (size_t)w * P.hist_bytes + (size_t)c * P.fx_cstride) + 3 * r;
+            acc += limbs_value(q[0], q[1], q[2]);
+            q[0] = 0u; q[1] = 0u; q[2] = 0u;
         }
-        if (acc != 0) {
-            const long long r = i / P.cols, c = i - r * P.cols;
-            atomicAdd(P.field + c * P.rows + r, (double)acc * P.fx_inv[(int)(r % NCOMP)]);
-        }
+        if (acc != 0) atomicAdd(P.field + e, (double)acc * P.fx_inv[r % NCOMP]);
     }
 }
 // Flush the 1-D difference-array histograms (mcb_device.cuh: deposit_fx) with the whole CTA, in three phases:
@@ -461,10 +463,6 @@ __device__ __forceinline__ void flush_fixed_point(uint32_t* words, unsigned ncop
 //     to the global field (column-major, fp64 RED).
 // Callers place a __syncthreads() before (all deposits done); the next deposits only touch the instances, which are zero
 // after phase 1.
-__device__ __forceinline__ long long limbs_value(uint32_t p0, uint32_t p1, uint32_t p2) {
-    const uint32_t sb = p1 - (p2 << 16), sa = p0 - (sb << 16);
-    return (long long)(int32_t)p2 * 4294967296ll + (long long)sb * 65536ll + (long long)sa;
-}
 template <int NCOMP>
 __device__ __forceinline__ void flush_tally1d(unsigned char* hist, unsigned ninst, long long* scratch, const StepParams& P,
                                               unsigned warp, unsigned nwarps, unsigned lane) {
@@ -517,16 +515,13 @@ __device__ __forceinline__ void flush_tally1d(unsigned char* hist, unsigned nins
 #define MCB_BLOCK_MAX 768         // 1-D / single-cell tallies: 80 registers x 24 warps (round 2, with the TMA state prefetch: 896 x 72 -11 %, 640 x 96 -1 %)
 #endif
 #ifndef MCB_BLOCK_MAX_ND1
-#define MCB_BLOCK_MAX_ND1 768     // serial N-D walk, CTA histogram / global tally: 80 registers (measured: 640 +-1 %, 512 -15 % on C3)
-#endif
-#ifndef MCB_BLOCK_MAX_ND1W
-#define MCB_BLOCK_MAX_ND1W 512    // serial N-D walk with warp histograms: 128 registers, no spills (measured on C4: 768 -> 512 = +45 %)
+#define MCB_BLOCK_MAX_ND1 512     // serial N-D walk: 128 registers, no spills (round 2, three-limb CTA histogram: 768 x 80 regs spills 600 B, -27 %; 640 -32 %)
 #endif
 #ifndef MCB_BLOCK_MAX_ND
 #define MCB_BLOCK_MAX_ND 512      // the cooperative N-D walk keeps two crossing iterators live: give it 128 registers
 #endif
 template <int NCOMP, int TM, int NDM, bool BOX, int PAD>
-__global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : (NDM == 1 ? (TM == MCB_TM_WARP ? MCB_BLOCK_MAX_ND1W : MCB_BLOCK_MAX_ND1) : MCB_BLOCK_MAX), 1) k_step(const StepParams P) {
+__global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : (NDM == 1 ? MCB_BLOCK_MAX_ND1 : MCB_BLOCK_MAX), 1) k_step(const StepParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
     unsigned char* s_mat = smem + P.so_mat;
@@ -535,8 +530,7 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : (NDM == 1 ? (TM 
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     constexpr bool T1D = NDM == 0 && TM == MCB_TM_WARP && MCB_TALLY_FX;          // 1-D difference-array histograms
     const unsigned ninst = T1D ? (unsigned)P.hist_copies : 0u;
-    const long long hist_words = T1D ? (long long)ninst * (P.hist_bytes / 4u)
-                                     : 2ll * (TM == MCB_TM_WARP ? P.field_len * nwarps * P.hist_copies : (TM == MCB_TM_BLOCK ? P.field_len : 0));
+    const long long hist_words = TM == MCB_TM_GLOBAL ? 0ll : (long long)P.hist_copies * (P.hist_bytes / 4u);
 
     // --- stage tables: one elected thread arms the mbarrier and issues the TMA bulk copies
     if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
@@ -563,14 +557,13 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : (NDM == 1 ? (TM 
     T.sdom = reinterpret_cast<const DSdom*>(smem + P.so_sdom);
     T.pairs = reinterpret_cast<const int32_t*>(smem + P.so_pairs);
     T.nw = P.mv.nw; T.np = P.mv.np; T.inv_bucket_w = P.mv.inv_bucket_w; T.inv_bucket_p = P.mv.inv_bucket_p;
-    // warp-private histograms, `hist_copies` interleaved copies per warp (by lane) to thin out same-cell collisions
-    T.hist = TM == MCB_TM_WARP ? s_hist + ((long long)warp * P.hist_copies + (lane & (unsigned)(P.hist_copies - 1))) * P.field_len
-                               : (TM == MCB_TM_BLOCK ? s_hist : P.field);
+    // CTA histogram: `hist_copies` interleaved copies (a lane picks its copy by lane id) thin out same-word hits
+    T.hist = TM == MCB_TM_BLOCK ? reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(s_hist) + (lane & (unsigned)(P.hist_copies - 1)) * P.hist_bytes)
+                                : P.field;
     // 1-D difference-array histograms: shared by the CTA, a lane picks its copy by lane id
     const uint32_t my_hist = T1D ? smem_u32(s_hist) + (lane & (unsigned)(P.hist_copies - 1)) * P.hist_bytes : 0u;
     const bool cum = P.kind == MCB_PROB_CUMTEMP || P.kind == MCB_PROB_CUMFLUX;
-    constexpr bool FX = MCB_TALLY_FX && TM == MCB_TM_WARP;        // fixed-point warp histograms (mcb_device.cuh: deposit)
-    const uint32_t hi_off = 4u * (uint32_t)P.field_len;            // low-word plane, then high-word plane
+    constexpr bool FX = TM != MCB_TM_GLOBAL;                      // fixed-point shared-memory histograms (mcb_device.cuh: deposit)
 
     // counters of this launch: warp-uniform values from ballots, kept in a 16-byte slot per warp in shared memory that lane 0
     // reads, bumps and writes back once per tile -- no per-thread counter registers live across the loop trip, no atomics
@@ -616,7 +609,7 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : (NDM == 1 ? (TM 
             if (since_flush + P.steps_per_launch > P.fx_flush_trips) {
                 __syncthreads();
                 if (T1D) flush_tally1d<NCOMP>(reinterpret_cast<unsigned char*>(s_hist), ninst, reinterpret_cast<long long*>(smem + P.so_scratch), P, warp, nwarps, lane);
-                else flush_fixed_point<NCOMP>(reinterpret_cast<uint32_t*>(s_hist), nwarps * (unsigned)P.hist_copies, P, threadIdx.x, blockDim.x);
+                else flush_block_fx<NCOMP>(reinterpret_cast<unsigned char*>(s_hist), (unsigned)P.hist_copies, P, threadIdx.x, blockDim.x);
                 __syncthreads();
                 since_flush = 0;
             }
@@ -693,7 +686,7 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : (NDM == 1 ? (TM 
                     if (NCOMP == 1) amt[0] = sg_ * (sg.d * T.inv_vel[ph.wp()]);
                     else if (NCOMP == 4) { amt[0] = sg_ * (sg.d * T.inv_vel[ph.wp()]); amt[1 % NCOMP] = sg_ * (sg.ex - sg.bx); amt[2 % NCOMP] = sg_ * (sg.ey - sg.by); amt[3 % NCOMP] = sg_ * (sg.ez - sg.bz); }
                     else { amt[0] = sg_ * (sg.ex - sg.bx); amt[1 % NCOMP] = sg_ * (sg.ey - sg.by); amt[2 % NCOMP] = sg_ * (sg.ez - sg.bz); }
-                    FxArgs fx{hi_off, (uint32_t)P.fx_limb_bits, (1u << P.fx_limb_bits) - 1u, false, &P};
+                    FxArgs fx{P.fx_cstride, false, &P};
                     if (FX) {
                         // fixed-point histograms: scale by the launch's power of two (exact); a payload beyond the chosen range
                         // (rare: a long flight of a very slow mode) is deposited exactly through the global fp64 path instead
@@ -737,15 +730,8 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : (NDM == 1 ? (TM 
     // --- flush the shared-memory histogram(s): sum the copies, transpose row-major -> the field's column-major layout,
     //     one fp64 RED per non-zero entry
     if (TM != MCB_TM_GLOBAL && P.do_tally) {
-        const unsigned ncopy = TM == MCB_TM_WARP ? nwarps * (unsigned)P.hist_copies : 1u;
         if (T1D) flush_tally1d<NCOMP>(reinterpret_cast<unsigned char*>(s_hist), ninst, reinterpret_cast<long long*>(smem + P.so_scratch), P, warp, nwarps, lane);
-        else if (FX) flush_fixed_point<NCOMP>(reinterpret_cast<uint32_t*>(s_hist), ncopy, P, threadIdx.x, blockDim.x);
-        else for (long long i = threadIdx.x; i < P.field_len; i += blockDim.x) {   // i = r*cols + c in the histograms
-            double v = 0.0;
-            for (unsigned w = 0; w < ncopy; ++w) v += s_hist[(long long)w * P.field_len + i];
-            const long long r = i / P.cols, c = i - r * P.cols;
-            if (v != 0.0) atomicAdd(P.field + c * P.rows + r, v);
-        }
+        else flush_block_fx<NCOMP>(reinterpret_cast<unsigned char*>(s_hist), (unsigned)P.hist_copies, P, threadIdx.x, blockDim.x);
     }
 }
 

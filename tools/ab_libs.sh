@@ -3,6 +3,6 @@
 wl="$1"; shift
 for round in 1 2; do
   for kv in "$@"; do
-    AB_TAG="${kv%%=*}" AB_BLOCK="$(echo ${kv%%=*} | grep -oE "b[0-9]+$" | tr -d b || true)" MCB_LIBMCB="$(pwd)/${kv#*=}" timeout 300 python tools/ab_run.py $wl 2>&1 | grep -v "^$"
+    AB_TAG="${kv%%=*}" AB_BLOCK=768 MCB_LIBMCB="$(pwd)/${kv#*=}" timeout 300 python tools/ab_run.py $wl 2>&1 | grep -v "^$"
   done
 done

@@ -11,7 +11,7 @@ args=""; for t in "$@"; do args="$args $t=abv/libmcb_$t.so"; done
 bash tools/ab_libs.sh "$wl" $args 2>&1 | tee gpurun_out/ab_b.log
 for t in "$@"; do
   for w in $wl; do
-  AB_BLOCK="$(echo $t | grep -oE "b[0-9]+$" | tr -d b || true)" MCB_LIBMCB="$(pwd)/abv/libmcb_$t.so" timeout 300 ncu --metrics smsp__inst_executed.sum,gpu__time_duration.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio,smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio,smsp__average_warps_issue_stalled_wait_per_issue_active.ratio,smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio,launch__grid_size,launch__block_size \
+  AB_BLOCK=768 MCB_LIBMCB="$(pwd)/abv/libmcb_$t.so" timeout 300 ncu --metrics smsp__inst_executed.sum,gpu__time_duration.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio,smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio,smsp__average_warps_issue_stalled_wait_per_issue_active.ratio,smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio,launch__grid_size,launch__block_size \
     --clock-control none -k regex:k_step -s 20 -c 1 --csv --log-file gpurun_out/inst_${t}_$w.csv python tools/ab_run.py $w > gpurun_out/ncu_inst_$t.log 2>&1
   python - <<PY
 import csv
