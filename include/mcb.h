@@ -260,6 +260,17 @@ int  mcb_finalize_dev(mcb_ctx* ctx, const mcb_problem_desc* prob, double* field_
 /* The stream the library launches on (a cudaStream_t), for event timing by callers. */
 int  mcb_stream(const mcb_ctx* ctx, void** stream);
 
+/* ---- several GPUs in one process (C++ callers; replaces the thread fan-out + `omp critical` sum of main.cpp:155-166).
+ * Phonons are independent histories: context g (one per device) solves its particle range with mcb_solve_raw, which
+ * leaves the RAW tally in the context's own device buffer; mcb_allreduce sums those buffers in place over NVLink
+ * (ncclAllReduce, ncclDouble, ncclSum on the contexts' streams; NCCL is bound with dlopen at the first call); mcb_finalize
+ * normalises (problem.cpp:439-444) one context's buffer and copies it to the host.  The Philox key is the global particle
+ * id, so the result does not depend on the number of devices up to fp summation order. */
+int  mcb_device_count(int* count);                 /* leading sm_100 devices visible to this process */
+int  mcb_solve_raw(mcb_ctx* ctx, const mcb_problem_desc* prob, uint64_t seed, int64_t n_begin, int64_t n_end, mcb_stats* stats);
+int  mcb_allreduce(mcb_ctx* const* ctxs, int n, const mcb_problem_desc* prob);
+int  mcb_finalize(mcb_ctx* ctx, const mcb_problem_desc* prob, double* out_field);
+
 /* ---------------------------------------------------------------- diagnostics ---
  * Per-particle state after emission and `nsteps` loop trips, for particles
  * [n_begin, n_end): the integer-parity probe of SURVEY §8c KA6.  Arrays are length

@@ -17,7 +17,7 @@ SYMBOLS = [
     "mcb_create", "mcb_destroy", "mcb_last_error", "mcb_abi_version", "mcb_build_info", "mcb_set_options", "mcb_get_options",
     "mcb_upload_material", "mcb_upload_domain", "mcb_field_cols", "mcb_solve", "mcb_solve_raw_dev",
     "mcb_finalize_dev", "mcb_stream", "mcb_trace", "mcb_cell_index", "mcb_accumulate", "mcb_get_alias",
-    "mcb_philox_words", "mcb_traj",
+    "mcb_philox_words", "mcb_traj", "mcb_device_count", "mcb_solve_raw", "mcb_allreduce", "mcb_finalize",
 ]
 
 _lib = None

@@ -7,6 +7,9 @@
 #include "mcb_kernels.cuh"
 
 #include <algorithm>
+#include <dlfcn.h>
+#include <map>
+#include <mutex>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -754,6 +757,105 @@ int mcb_finalize_dev(mcb_ctx* c, const mcb_problem_desc* prob, double* field_dev
         CUDA_TRY(c, cudaGetLastError());
     }
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return MCB_OK;
+}
+
+// ---------------------------------------------------------------- several devices in one process (C++ callers, no torch)
+int mcb_device_count(int* count) {
+    if (!count) return MCB_EINVAL;
+    int n = 0, ok = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) n = 0;
+    for (int d = 0; d < n; ++d) { cudaDeviceProp p; if (cudaGetDeviceProperties(&p, d) == cudaSuccess && p.major == 10) ++ok; else break; }
+    *count = ok;
+    return MCB_OK;
+}
+
+int mcb_solve_raw(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n_begin, int64_t n_end, mcb_stats* stats) {
+    if (!c) return MCB_EINVAL;
+    int rc = check_problem(c, prob);
+    if (rc) return rc;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const size_t len = (size_t)prob->rows * (size_t)c->cols;
+    CUDA_TRY(c, c->field.alloc(len));
+    CUDA_TRY(c, cudaMemsetAsync(c->field.p, 0, std::max<size_t>(len, 1) * sizeof(double), c->stream));
+    return run_solve(c, prob, seed, n_begin, n_end, c->field.p, stats);
+}
+
+int mcb_finalize(mcb_ctx* c, const mcb_problem_desc* prob, double* out_field) {
+    if (!c) return MCB_EINVAL;
+    if (!out_field) { c->err = "null output field"; return MCB_EINVAL; }
+    int rc = check_problem(c, prob);
+    if (rc) return rc;
+    const size_t len = (size_t)prob->rows * (size_t)c->cols;
+    if (!c->field.p || c->field.n < len) { c->err = "mcb_finalize before mcb_solve_raw"; return MCB_ESTATE; }
+    rc = mcb_finalize_dev(c, prob, c->field.p);
+    if (rc) return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(out_field, c->field.p, len * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return MCB_OK;
+}
+
+namespace {
+// NCCL is bound at run time (dlopen), not at link time: a process that already carries another libnccl.so.2 (torch ships
+// its own) keeps using that one, and single-GPU users need no NCCL at all.
+struct Nccl {
+    typedef struct ncclComm* comm_t;
+    int (*CommInitAll)(comm_t*, int, const int*) = nullptr;
+    int (*CommDestroy)(comm_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false; std::string err;
+    Nccl() {
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+        if (!h) { err = std::string("libnccl.so.2 not found: ") + dlerror(); return; }
+        CommInitAll = (int (*)(comm_t*, int, const int*))dlsym(h, "ncclCommInitAll");
+        CommDestroy = (int (*)(comm_t))dlsym(h, "ncclCommDestroy");
+        AllReduce = (int (*)(const void*, void*, size_t, int, int, comm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
+        GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
+        GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
+        GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+        ok = CommInitAll && CommDestroy && AllReduce && GroupStart && GroupEnd && GetErrorString;
+        if (!ok) err = "libnccl.so.2 lacks the expected symbols";
+    }
+};
+std::mutex g_nccl_mu;
+std::map<std::vector<int>, std::vector<Nccl::comm_t>> g_comms;      // one communicator clique per device list
+}
+
+// replaces the omp-critical `sol += partial` of main.cpp:162-165 when the particle range is sharded over GPUs
+int mcb_allreduce(mcb_ctx* const* ctxs, int n, const mcb_problem_desc* prob) {
+    if (!ctxs || n <= 0 || !ctxs[0]) return MCB_EINVAL;
+    mcb_ctx* c0 = ctxs[0];
+    int rc = check_problem(c0, prob);
+    if (rc) return rc;
+    if (n == 1) return MCB_OK;
+    const size_t len = (size_t)prob->rows * (size_t)c0->cols;
+    std::vector<int> devs;
+    for (int i = 0; i < n; ++i) {
+        if (!ctxs[i] || ctxs[i]->cols != c0->cols || !ctxs[i]->field.p || ctxs[i]->field.n < len) { c0->err = "mcb_allreduce: contexts do not hold the same raw field (mcb_solve_raw first)"; return MCB_ESTATE; }
+        devs.push_back(ctxs[i]->device);
+    }
+    for (int i = 0; i < n; ++i) for (int j = i + 1; j < n; ++j) if (devs[i] == devs[j]) { c0->err = "mcb_allreduce: one context per device"; return MCB_EINVAL; }
+    std::lock_guard<std::mutex> lock(g_nccl_mu);
+    static Nccl nccl;
+    if (!nccl.ok) { c0->err = nccl.err; return MCB_ECUDA; }
+    std::vector<Nccl::comm_t>& comms = g_comms[devs];
+    if (comms.empty()) {
+        comms.resize(n);
+        const int r = nccl.CommInitAll(comms.data(), n, devs.data());
+        if (r != 0) { c0->err = std::string("ncclCommInitAll: ") + nccl.GetErrorString(r); g_comms.erase(devs); return MCB_ECUDA; }
+    }
+    int r = nccl.GroupStart();
+    for (int i = 0; i < n && r == 0; ++i) {
+        CUDA_TRY(c0, cudaSetDevice(ctxs[i]->device));
+        r = nccl.AllReduce(ctxs[i]->field.p, ctxs[i]->field.p, len, /*ncclDouble*/ 8, /*ncclSum*/ 0, comms[i], ctxs[i]->stream);
+    }
+    const int r2 = nccl.GroupEnd();
+    if (r != 0 || r2 != 0) { c0->err = std::string("ncclAllReduce: ") + nccl.GetErrorString(r != 0 ? r : r2); return MCB_ECUDA; }
+    for (int i = 0; i < n; ++i) { CUDA_TRY(c0, cudaSetDevice(ctxs[i]->device)); CUDA_TRY(c0, cudaStreamSynchronize(ctxs[i]->stream)); }
     return MCB_OK;
 }
 

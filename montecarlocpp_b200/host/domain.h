@@ -19,6 +19,7 @@ protected:
 private:
     Subdomain::Pointers sdomPtrs_;
     Emitter::Pointers emitPtrs_;
+    unsigned long uid_ = mcNextUid();
     virtual std::string info() const = 0;
 public:
     Domain() {}
@@ -31,6 +32,7 @@ public:
     const Subdomain* locate(const Vector3d& pos) const;
     const Subdomain::Pointers& sdomPtrs() const { return sdomPtrs_; }
     const Emitter::Pointers& emitPtrs() const { return emitPtrs_; }
+    unsigned long uid() const { return uid_; }
 
     virtual Matrix3Xd checkpoints() const = 0;
     virtual ArrayXXd average(const ArrayXXd& data) const { return data; }     // domain.cpp:78-81

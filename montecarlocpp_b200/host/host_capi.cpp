@@ -2,6 +2,9 @@
 // can drive the SAME objects a C++ caller would: Material, the Domain classes, the FieldProblem family.
 // Not part of the reference API; every call maps 1:1 to a constructor or method of the mirror.
 #include <cstring>
+#include <omp.h>
+#include <stdexcept>
+#include <vector>
 #include <memory>
 #include <string>
 #include "domain.h"
@@ -13,6 +16,36 @@ namespace { thread_local std::string g_err; }
 
 struct mcbh_domain { std::unique_ptr<Domain> dom; FlatDomain flat; };
 struct mcbh_problem { std::unique_ptr<FieldProblem> prob; };
+
+static int solve_like_the_reference(const mcbh_problem* p, uint32_t mt_seed, int nthreads, double* out, mcb_stats* stats, int64_t* progress_count) {
+    try {
+        ArrayXXd sol = p->prob->initSolution();
+        Progress prog = p->prob->initProgress();
+        std::string err; mcb_stats st = mcb_stats();
+#pragma omp parallel num_threads(nthreads > 0 ? nthreads : 1)
+        {
+            ArrayXXd partial;
+            bool ok = true;
+            try {
+                Rng gen(mt_seed + (uint32_t)omp_get_thread_num());
+                partial = p->prob->solve(gen, &prog);
+            } catch (const std::exception& e) {
+                ok = false;
+#pragma omp critical(mcbh_err)
+                { err = e.what(); }
+            }
+#pragma omp critical(mcbh_sum)
+            {
+                if (ok) { sol += partial; if (omp_get_thread_num() == 0) st = FieldProblem::lastStats(); }
+            }
+        }
+        if (!err.empty()) throw std::runtime_error(err);
+        std::memcpy(out, sol.data(), sizeof(double) * (size_t)sol.size());
+        if (stats) *stats = st;
+        if (progress_count) *progress_count = prog.count();
+        return MCB_OK;
+    } catch (const std::exception& e) { g_err = e.what(); return MCB_EINVAL; }
+}
 
 extern "C" {
 
@@ -92,6 +125,19 @@ int mcbh_problem_solve_seeded(const mcbh_problem* p, int device, uint64_t seed, 
         if (stats) *stats = FieldProblem::lastStats();
         return MCB_OK;
     , MCB_EINVAL)
+}
+
+// process-wide device selection (n = 0: every visible sm_100 device); returns the number selected
+int mcbh_set_devices(const int* ordinals, int n) {
+    MCBH_TRY(
+        FieldProblem::devices(std::vector<int>(ordinals, ordinals + (n > 0 ? n : 0)));
+        return (int)FieldProblem::devices().size();
+    , -1)
+}
+// The reference's calling pattern (main.cpp:155-166): solve() entered by every thread of an OpenMP region with its own
+// generator (mt19937(mt_seed + thread)), the partial fields summed under `omp critical`.  Must equal ONE solve.
+int mcbh_problem_solve_omp(const mcbh_problem* p, uint32_t mt_seed, int nthreads, double* out, mcb_stats* stats, int64_t* progress_count) {
+    return solve_like_the_reference(p, mt_seed, nthreads, out, stats, progress_count);
 }
 
 // TriangularPrismImpl::cellVol (cell = MCB_CELL_TRIPRISM) / TetrahedronImpl::cellVol (MCB_CELL_TETRAHEDRON)

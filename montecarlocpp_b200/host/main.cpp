@@ -9,10 +9,13 @@
 //   temp|flux|multi nemit maxscat maxloop nsim | cumtemp|cumflux nemit size maxscat maxloop nsim
 //   check r00 r01 r02 r10 r11 r12 r20 r21 r22 | traj px py pz dx dy dz maxscat maxloop
 //
-// Differences from the reference driver: the solve runs on the GPU and is called once per repetition from
-// the main thread (the reference opens an OpenMP region and sums per-thread partials); the 42-subdomain octet
-// domain is not built.
+// Differences from the reference driver: FieldProblem::solve runs on the GPU(s).  It is still called the reference's way --
+// from every thread of an OpenMP region, partial fields summed (main.cpp:155-166) -- and sums to exactly one solve (thread 0
+// brings it, see problem.cpp).  The environment variable MCB_DEVICES selects the GPUs: "all" (default: every visible
+// sm_100 device; the particle range is sharded over them and the tallies summed with NCCL) or a comma-separated list.
 #include <unistd.h>
+#include <cstdlib>
+#include <memory>
 #include <iomanip>
 #include <iostream>
 #include <sstream>
@@ -26,10 +29,25 @@
 typedef Dev::result_type Seed;
 
 #ifdef DEBUG
-static Seed getSeed() { static Seed s(0); return s++; }
+static Seed getSeed() { static Seed s(0); Seed r;
+#pragma omp critical
+    { r = s++; }
+    return r; }
 #else
-static Seed getSeed() { static Dev urandom; return urandom(); }
+static Seed getSeed() { static Dev urandom; Seed r;
+#pragma omp critical(mc_seed)
+    { r = urandom(); }
+    return r; }
 #endif
+static void printSeed(Seed s) {                                                   // main.cpp:50-65
+#pragma omp single
+    { std::cout << "  seeds: "; }
+#pragma omp critical
+    { std::cout << s << ' '; }
+#pragma omp barrier
+#pragma omp single
+    { std::cout << std::endl; }
+}
 
 static void printSolution(const ArrayXXd& sol) {
     std::ios_base::fmtflags mask = std::cout.flags();
@@ -83,12 +101,18 @@ static ArrayXXd checkDomain(const Material* mat, const Domain* dom, const Matrix
 static ArrayXXd solveField(const FieldProblem* prob, const Clock& clk) {
     static long n = 0;
     std::cout << "Solution " << n++ << std::endl;
+    ArrayXXd sol = prob->initSolution();
     Progress prog = prob->initProgress();
     prog.clock(clk);
-    Seed s = getSeed();
-    std::cout << "  seeds: " << s << ' ' << std::endl;
-    Rng gen(s);
-    ArrayXXd sol = prob->solve(gen, &prog);
+#pragma omp parallel
+    {
+        Seed s = getSeed();
+        printSeed(s);
+        Rng gen(s);
+        ArrayXXd partial = prob->solve(gen, &prog);
+#pragma omp critical
+        { sol += partial; }
+    }
     std::cout << "Output" << std::endl;
     printSolution(sol);
     ArrayXXd avg = prob->dom()->average(sol);
@@ -117,6 +141,12 @@ int main(int argc, const char* argv[]) {
 #endif
     std::cout << argss.str() << std::endl << std::endl;
     try {
+        {   // MCB_DEVICES: "all" (default) | "0,2,3"
+            std::vector<int> devs;
+            const char* e = std::getenv("MCB_DEVICES");
+            if (e && std::string(e) != "all") { std::stringstream ds(e); std::string tok; while (std::getline(ds, tok, ',')) if (!tok.empty()) devs.push_back(std::atoi(tok.c_str())); }
+            FieldProblem::devices(devs);
+        }
         std::string prefix; argss >> prefix;
         MC_ASSERT_MSG(chdir(prefix.c_str()) == 0, "Invalid directory");
 

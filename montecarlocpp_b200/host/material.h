@@ -10,6 +10,8 @@
 #include <vector>
 #include "../../include/mcb.h"
 
+#include "mc_types.h"
+
 class Material {
     static const int nscat_ = 2;
     long np_, nw_;
@@ -18,6 +20,7 @@ class Material {
     std::vector<double> energyPdf_, fluxPdf_, scatPdf_;
     double energySum_, fluxSum_, scatSum_;
     std::string disp_, relax_;
+    unsigned long uid_ = mcNextUid();                      // a copy shares the id: same tables
     std::string info() const;
 public:
     Material();
@@ -27,6 +30,7 @@ public:
     double cond() const { return k_; }
     long nw() const { return nw_; }
     long np() const { return np_; }
+    unsigned long uid() const { return uid_; }
     double tau(long w, long p) const { return tau_.at((size_t)(w + nw_ * p)); }
     double vel(long w, long p) const { return vel_.at((size_t)(w + nw_ * p)); }
     double energySum() const { return energySum_; }

@@ -133,4 +133,9 @@ private:
 // default seeding), so the signature `solve(Rng& gen, ...)` keeps its meaning.
 typedef std::mt19937 Rng;
 
+// identity of a table-bearing object (Material, Domain) for the device-side table cache: heap addresses are reused after
+// delete, a counter is not
+#include <atomic>
+inline unsigned long mcNextUid() { static std::atomic<unsigned long> next(1); return next.fetch_add(1); }
+
 #endif

@@ -9,6 +9,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <thread>
 #include <sstream>
 #ifdef _OPENMP
 #include <omp.h>
@@ -127,43 +128,58 @@ FlatDomain flattenDomain(const Domain* dom) {
     return f;
 }
 
-//---------------------------------------- device contexts (one per device, tables cached by object identity)
+//---------------------------------------- device contexts (one per device, tables cached by object uid)
 namespace {
 struct DeviceContext {
-    mcb_ctx* ctx = 0; const Material* mat = 0; const Domain* dom = 0; long cols = 0;
+    mcb_ctx* ctx = 0; unsigned long mat = 0, dom = 0; long cols = 0;
+    std::mutex mu;                                  // one GPU stream per device: calls from several host threads are serialised
     ~DeviceContext() { if (ctx) mcb_destroy(ctx); }
 };
-std::mutex g_mu;
+std::mutex g_mu;                                    // guards the map and the device selection
 std::map<int, std::unique_ptr<DeviceContext>> g_ctx;
-thread_local int t_device = 0;
+std::vector<int> g_devices(1, 0);                   // process-wide (an OpenMP worker sees what the main thread selected)
 thread_local mcb_stats t_stats = mcb_stats();
 
 void check(mcb_ctx* c, int rc, const char* what) {
     if (rc != MCB_OK) throw std::runtime_error(std::string(what) + ": " + mcb_last_error(c));
 }
 }
-void FieldProblem::device(int ordinal) { t_device = ordinal; }
+int FieldProblem::deviceCount() { int n = 0; mcb_device_count(&n); return n; }
+void FieldProblem::device(int ordinal) { devices(std::vector<int>(1, ordinal)); }
+void FieldProblem::devices(const std::vector<int>& ordinals) {
+    std::vector<int> d = ordinals;
+    if (d.empty()) { const int n = deviceCount(); for (int i = 0; i < n; ++i) d.push_back(i); if (d.empty()) d.push_back(0); }
+    std::lock_guard<std::mutex> lock(g_mu);
+    g_devices = d;
+}
+std::vector<int> FieldProblem::devices() { std::lock_guard<std::mutex> lock(g_mu); return g_devices; }
 mcb_stats FieldProblem::lastStats() { return t_stats; }
 
 namespace {
-// Runs f(ctx) with the device context of the calling thread's device, after making sure the tables of (mat, dom) are
-// resident.  One GPU stream per device: calls from several host threads are serialised.
+// Runs f(ctx) with the context of device `dev`, after making sure the tables of (mat, dom) are resident there.  The cache is
+// keyed on the objects' uids (a freed Domain's address is routinely reused by the next one; its uid is not).
 template <typename F>
-void withDevice(const Material* mat, const Domain* dom, F f) {
-    std::lock_guard<std::mutex> lock(g_mu);
-    std::unique_ptr<DeviceContext>& dc = g_ctx[t_device];
-    if (!dc) {
-        dc.reset(new DeviceContext);
-        int rc = mcb_create(t_device, &dc->ctx);
-        if (rc != MCB_OK) { std::string msg = mcb_last_error(0); dc.reset(); g_ctx.erase(t_device); throw std::runtime_error("mcb_create: " + msg); }
+void withDevice(int dev, const Material* mat, const Domain* dom, F f) {
+    DeviceContext* dc = 0;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        std::unique_ptr<DeviceContext>& slot = g_ctx[dev];
+        if (!slot) {
+            slot.reset(new DeviceContext);
+            int rc = mcb_create(dev, &slot->ctx);
+            if (rc != MCB_OK) { std::string msg = mcb_last_error(0); slot.reset(); g_ctx.erase(dev); throw std::runtime_error("mcb_create: " + msg); }
+        }
+        dc = slot.get();
     }
-    if (dc->mat != mat) { mcb_material_desc md = mat->desc(); check(dc->ctx, mcb_upload_material(dc->ctx, &md), "mcb_upload_material"); dc->mat = mat; }
-    if (dc->dom != dom) {
+    std::lock_guard<std::mutex> lock(dc->mu);
+    if (dc->mat != mat->uid()) { mcb_material_desc md = mat->desc(); check(dc->ctx, mcb_upload_material(dc->ctx, &md), "mcb_upload_material"); dc->mat = mat->uid(); }
+    if (dc->dom != dom->uid()) {
         FlatDomain fd = flattenDomain(dom); mcb_domain_desc dd = fd.desc();
-        check(dc->ctx, mcb_upload_domain(dc->ctx, &dd), "mcb_upload_domain"); dc->dom = dom; dc->cols = fd.cols;
+        check(dc->ctx, mcb_upload_domain(dc->ctx, &dd), "mcb_upload_domain"); dc->dom = dom->uid(); dc->cols = fd.cols;
     }
     f(dc->ctx);
 }
+int firstDevice() { std::lock_guard<std::mutex> lock(g_mu); return g_devices.front(); }
 }
 
 
@@ -216,7 +232,7 @@ ArrayXXd TrajProblem::solve(Rng& gen, Progress* prog) const {
     mcb_traj_out o = mcb_traj_out();
     o.max_points = 2 * nmax + 1; o.points = pts.data(); o.max_steps = nmax;
     o.step_sdom = ssd.data(); o.step_in = sin_.data(); o.step_in_kind = sink.data(); o.step_out = sout.data(); o.step_out_kind = soutk.data();
-    withDevice(mat(), dom(), [&](mcb_ctx* ctx) { check(ctx, mcb_traj(ctx, &t, seed, &o), "mcb_traj"); });
+    withDevice(firstDevice(), mat(), dom(), [&](mcb_ctx* ctx) { check(ctx, mcb_traj(ctx, &t, seed, &o), "mcb_traj"); });
 
     // the per-trip lines of problem.cpp:260-275
     auto typeOf = [&](int s, int k) { return k >= 0 ? sp.at((size_t)s)->bdryPtrs().at((size_t)k)->type() : std::string("Null"); };
@@ -286,39 +302,64 @@ mcb_problem_desc FieldProblem::desc() const {
 
 ArrayXXd FieldProblem::solveSeeded(unsigned long long seed, long n_begin, long n_end, Progress* prog) const {
     ArrayXXd out = initSolution();
+    const std::vector<int> devs = devices();
+    const long G = (long)devs.size();
     mcb_stats st = mcb_stats();
-    withDevice(mat(), dom(), [&](mcb_ctx* ctx) {
+    if (G <= 1) {
+        withDevice(devs.front(), mat(), dom(), [&](mcb_ctx* ctx) {
+            mcb_problem_desc pd = desc();
+            check(ctx, mcb_solve(ctx, &pd, seed, n_begin, n_end, out.data(), &st), "mcb_solve");
+        });
+    } else {
+        // Phonons are independent histories: device g takes a contiguous share of [n_begin, n_end) (the static partition the
+        // reference gives its OpenMP threads, problem.cpp:383-384) on its own host thread; the raw tallies are summed over
+        // NVLink (ncclAllReduce inside mcb_allreduce: the `sol += partial` of main.cpp:162-165) and normalised once.
+        const long n = n_end - n_begin, q = n / G, r = n % G;
+        std::vector<mcb_stats> sts((size_t)G, mcb_stats());
+        std::vector<mcb_ctx*> ctxs((size_t)G, (mcb_ctx*)0);
+        std::vector<std::string> errs((size_t)G);
         mcb_problem_desc pd = desc();
-        check(ctx, mcb_solve(ctx, &pd, seed, n_begin, n_end, out.data(), &st), "mcb_solve");
-    });
+        std::vector<std::thread> workers;
+        for (long g = 0; g < G; ++g)
+            workers.emplace_back([&, g]() {
+                const long b = n_begin + g * q + std::min(g, r), e = b + q + (g < r ? 1 : 0);
+                try {
+                    withDevice(devs[(size_t)g], mat(), dom(), [&](mcb_ctx* ctx) {
+                        ctxs[(size_t)g] = ctx;
+                        check(ctx, mcb_solve_raw(ctx, &pd, seed, b, e, &sts[(size_t)g]), "mcb_solve_raw");
+                    });
+                } catch (const std::exception& ex) { errs[(size_t)g] = ex.what(); }
+            });
+        for (std::thread& w : workers) w.join();
+        for (const std::string& e : errs) if (!e.empty()) throw std::runtime_error(e);
+        check(ctxs[0], mcb_allreduce(ctxs.data(), (int)G, &pd), "mcb_allreduce");
+        check(ctxs[0], mcb_finalize(ctxs[0], &pd, out.data()), "mcb_finalize");
+        for (const mcb_stats& s : sts) {
+            st.emitted += s.emitted; st.steps += s.steps; st.esc += s.esc; st.launches += s.launches; st.step_launches += s.step_launches;
+            st.slot_steps += s.slot_steps; st.state_stores += s.state_stores; st.steady_launches += s.steady_launches;
+            st.steady_steps += s.steady_steps; st.steady_stores += s.steady_stores;
+            st.device_ms = std::max(st.device_ms, s.device_ms); st.step_ms = std::max(st.step_ms, s.step_ms); st.steady_ms = std::max(st.steady_ms, s.steady_ms);
+        }
+        st.cols = sts[0].cols; st.launches += 1;
+    }
     t_stats = st;
     if (prog) prog->advance((long)st.emitted, (long)st.esc);
     return out;
 }
 
-// Reference signature (problem.cpp:370).  `gen` only supplies the 64-bit Philox seed.  Called from inside
-// `#pragma omp parallel` (main.cpp:155) every thread takes the static chunk the reference's orphaned
-// `omp for schedule(static)` (problem.cpp:383) would give it, so the partials still add up to one solve.
+// Reference signature (problem.cpp:370).  `gen` only supplies the 64-bit Philox seed.  The reference calls solve() from EVERY
+// thread of `#pragma omp parallel` (main.cpp:155) and splits the particle loop with an orphaned `omp for` (problem.cpp:383);
+// the caller then sums the threads' partial fields.  Here OpenMP thread 0 runs the whole range on the device(s) and the other
+// threads return a zero partial, so the caller's sum is still exactly ONE solve, whatever the thread count (a GPU solve
+// entered T times without this would count every phonon T times).  Every thread draws its two words, so the callers'
+// engines stay in step with a serial run.
 ArrayXXd FieldProblem::solve(Rng& gen, Progress* prog) const {
     unsigned long long hi = gen(), lo = gen();
-    unsigned long long seed = (hi << 32) | lo;
-    long n_begin = 0, n_end = nemit_;
+    const unsigned long long seed = (hi << 32) | lo;
 #ifdef _OPENMP
-    if (omp_in_parallel()) {
-        // all threads must agree on the stream: take thread 0's seed
-        static unsigned long long shared_seed;
-#pragma omp barrier
-#pragma omp master
-        { shared_seed = seed; }
-#pragma omp barrier
-        seed = shared_seed;
-        const long T = omp_get_num_threads(), t = omp_get_thread_num();
-        const long q = nemit_ / T, r = nemit_ % T;                          // static schedule: first r chunks get q+1
-        n_begin = t * q + std::min(t, r);
-        n_end = n_begin + q + (t < r ? 1 : 0);
-    }
+    if (omp_in_parallel() && omp_get_thread_num() != 0) return initSolution();
 #endif
-    return solveSeeded(seed, n_begin, n_end, prog);
+    return solveSeeded(seed, 0, nemit_, prog);
 }
 
 //---------------------------------------- the five tallies

@@ -113,8 +113,13 @@ public:
     double power() const { return power_; }
     const VectorXl& emitPdf() const { return emitPdf_; }
     mcb_problem_desc desc() const;                      // pointers valid for this object's lifetime
-    // device selection / counters of the latest solve on this thread (not in the reference)
-    static void device(int ordinal);
+    // device selection / counters of the latest solve on this thread (not in the reference).  The selection is
+    // process-wide: solve() shards the particle range over every selected device (one host thread + one mcb context per
+    // device), sums the raw tallies with NCCL (mcb_allreduce) and normalises once.
+    static void device(int ordinal);                              // one device
+    static void devices(const std::vector<int>& ordinals);        // several; empty = every visible sm_100 device
+    static std::vector<int> devices();
+    static int deviceCount();
     static mcb_stats lastStats();
     ArrayXXd solveSeeded(unsigned long long seed, long n_begin, long n_end, Progress* prog) const;
 

@@ -41,6 +41,8 @@ def lib():
         L.mcbh_problem_desc.argtypes = [vp, C.POINTER(abi.ProblemDesc)]
         L.mcbh_problem_solve.argtypes = [vp, C.c_int, C.c_uint32, dp, C.POINTER(abi.Stats)]
         L.mcbh_problem_solve_seeded.argtypes = [vp, C.c_int, C.c_uint64, C.c_int64, C.c_int64, dp, C.POINTER(abi.Stats)]
+        L.mcbh_problem_solve_omp.argtypes = [vp, C.c_uint32, C.c_int, dp, C.POINTER(abi.Stats), lp]
+        L.mcbh_set_devices.argtypes = [C.POINTER(C.c_int), C.c_int]
         L.mcbh_simplex_cell_vol.restype = C.c_double
         L.mcbh_simplex_cell_vol.argtypes = [C.c_int, lp, lp, C.c_double]
         _lib = L
@@ -124,9 +126,33 @@ class FieldProblem:
             raise RuntimeError(_err())
         return out.reshape(self.dom.cols, self.rows).T.copy(), st.asdict()
 
+    def solve_omp(self, mt_seed=0, nthreads=1):
+        """The reference's calling pattern (main.cpp:155-166): solve() from every thread of an OpenMP region, partials summed.
+        Returns (field, stats, Progress::count())."""
+        out = np.zeros(self.rows * self.dom.cols); st = abi.Stats(); cnt = C.c_int64()
+        if lib().mcbh_problem_solve_omp(self.h, mt_seed, nthreads, out.ctypes.data_as(abi.c_double_p), C.byref(st), C.byref(cnt)) != 0:
+            raise RuntimeError(_err())
+        return out.reshape(self.dom.cols, self.rows).T.copy(), st.asdict(), cnt.value
+
     def __del__(self):
         if getattr(self, "h", None):
             lib().mcbh_problem_free(self.h); self.h = None
+
+
+def set_devices(ordinals=()):
+    """Process-wide device selection of FieldProblem::solve (empty: every visible sm_100 device).  With several devices the
+    particle range is sharded over them and the raw tallies are summed with NCCL (mcb_allreduce)."""
+    arr = (C.c_int * max(1, len(ordinals)))(*ordinals)
+    n = lib().mcbh_set_devices(arr, len(ordinals))
+    if n < 0:
+        raise RuntimeError(_err())
+    return n
+
+
+def device_count():
+    n = C.c_int()
+    capi.lib().mcb_device_count(C.byref(n))
+    return n.value
 
 
 def simplex_cell_vol(cell, index, shape, vol):
