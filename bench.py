@@ -222,7 +222,7 @@ class Runner:
         # the library's own stream: the zeroing, the all-reduce and the finalize are issued on it, so the NCCL kernel is
         # ordered after the solve's last flush and before k_finalize (a collective on torch's stream was not)
         self.lib_stream = torch.cuda.ExternalStream(ctx.stream())
-        self.ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        self.ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         self.coll_ms = self.zero_ms = self.fin_ms = 0.0
         self.arrive = []
         torch.cuda.synchronize()
@@ -241,10 +241,12 @@ class Runner:
             if self.world > 1:
                 dist.all_reduce(self.raw, op=dist.ReduceOp.SUM)      # the per-solve field reduction (main.cpp:162-165) over NCCL
             self.ev[3].record()
-        t_fin = time.perf_counter()
         ctx.finalize_dev(self.prob.desc, self.raw.data_ptr())          # k_finalize on the same stream, then a stream sync
+        with torch.cuda.stream(self.lib_stream):
+            self.ev[4].record()
+        self.ev[4].synchronize()
         if timed:
-            self.fin_ms += 1e3 * (time.perf_counter() - t_fin) - self.ev[2].elapsed_time(self.ev[3])
+            self.fin_ms += self.ev[3].elapsed_time(self.ev[4])
             self.zero_ms += self.ev[0].elapsed_time(self.ev[1])
             self.coll_ms += self.ev[2].elapsed_time(self.ev[3])
             self.arrive.append(t_arrive)

@@ -1,7 +1,7 @@
 // domain.h — host mirror of Domain and the box-celled domains the reference ships (domain.h:38-296,
 // domain.cpp:28-570): Bulk, Film, Jct, Tee, Tube.  SlabDomain and WireDomain are NOT in the reference;
 // they are the two box variants BASELINE.json's configs need (isothermal walls; diffuse wire) and use
-// only reference building blocks.  HexDomain / PyrDomain (non-box cells) are built; the 42-subdomain OctetDomain is not.
+// only reference building blocks.  HexDomain / PyrDomain (non-box cells) and the 42-subdomain OctetDomain are built.
 #ifndef MCB_HOST_DOMAIN_H
 #define MCB_HOST_DOMAIN_H
 #include <iosfwd>
@@ -160,5 +160,23 @@ private:
 public:
     TubeDomain(const VectorXd& dim, const VectorXl& div, double dT);    // 4 dims, 4 divs
     Matrix3Xd checkpoints() const;
+};
+// Octet-truss unit cell (domain.h:299-385, domain.cpp:576-1280): 42 convex subdomains -- prisms, pyramids, triangular prisms
+// and parallelepipeds -- joined by 71 Inter pairs and 5 mirror-periodic pairs; the ten strut subdomains (16..25) carry the
+// temperature gradient and the tally grids.  dim = (s, d1, d2, t), div = (div0..div3).  The geometry table (origins and edge
+// vectors as linear forms of s, a, t; boundary classes; pair lists) is octet_table.inc, derived from outputs of the reference
+// by tools/derive_octet_table.py and pinned against the reference's own objects in tests/test_reference_pin.py.
+class OctetDomain : public Domain {
+public:
+    typedef PeriBoundary<Polygon<4> > Peri4;
+private:
+    VectorXd dim_; VectorXl div_; double dT_;
+    std::vector<std::unique_ptr<EmitSubdomain> > cells_;
+    std::string info() const;
+public:
+    OctetDomain(const VectorXd& dim, const VectorXl& div, double dT);
+    Matrix3Xd checkpoints() const;                  // one interior point per subdomain (the reference hand-picks 52)
+    ArrayXXd average(const ArrayXXd& data) const;   // domain.cpp:1252-1280: cell-volume weighted mean over the k = 0 layer of the strut grids
+    std::vector<double> averageWeights() const;     // the per-column weights of that mean (OctetDomain::WeightF)
 };
 #endif

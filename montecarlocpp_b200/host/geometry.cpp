@@ -350,3 +350,113 @@ PyrDomain::PyrDomain(const Vector3d& dim, double dT)
 }
 std::string PyrDomain::info() const { return describe("PyrDomain", static_cast<const Domain*>(this), vec(dim_), VectorXl(), dT_); }
 Matrix3Xd PyrDomain::checkpoints() const { return points({0.5 * dim_}); }
+
+//---------------------------------------- OctetDomain (domain.cpp:576-1280)
+namespace {
+#include "octet_table.inc"
+typedef SpecBoundary Spec; typedef DiffBoundary Diff; typedef InterBoundary Inter;
+typedef PeriBoundary<Parallelogram> PeriP; typedef PeriBoundary<Polygon<4> > Peri4;
+typedef std::tuple<MCB_OCTET_CELL_TYPES> OctetTypes;
+static_assert(std::tuple_size<OctetTypes>::value == 42, "octet table");
+
+double evalForm(const OctetForm& f, double s, double a, double t) {
+    const double r2 = std::sqrt(2.);
+    return ((f.ps + f.qs * r2) * s + (f.pa + f.qa * r2) * a + (f.pt + f.qt * r2) * t) / 16.;
+}
+// the two constructor shapes: (o, 3 x 3 matrix, div vector, gradT) for parallelepipeds / triangular prisms,
+// (o, N columns, one div, gradT) for prisms / pyramids
+template <class T> std::unique_ptr<EmitSubdomain> makeCell(const Vector3d& o, const std::vector<Vector3d>& cols, const Vector3l& div, const Vector3d& grad) {
+    if constexpr (std::is_constructible<T, const Vector3d&, const Matrix3d&, const Vector3l&, const Vector3d&>::value)
+        return std::unique_ptr<EmitSubdomain>(new T(o, Matrix3d::Columns(cols.at(0), cols.at(1), cols.at(2)), div, grad));
+    else
+        return std::unique_ptr<EmitSubdomain>(new T(o, cols, div(0), grad));
+}
+template <size_t... I>
+std::unique_ptr<EmitSubdomain> makeCellAt(size_t i, const Vector3d& o, const std::vector<Vector3d>& cols, const Vector3l& div, const Vector3d& grad,
+                                           std::index_sequence<I...>) {
+    typedef std::unique_ptr<EmitSubdomain> (*Fn)(const Vector3d&, const std::vector<Vector3d>&, const Vector3l&, const Vector3d&);
+    static const Fn table[] = {&makeCell<typename std::tuple_element<I, OctetTypes>::type>...};
+    return table[i](o, cols, div, grad);
+}
+Boundary* bdryOf(const std::vector<std::unique_ptr<EmitSubdomain> >& cells, int cell, int b) {
+    return const_cast<Boundary*>(cells.at((size_t)cell)->bdryPtrs().at((size_t)b));
+}
+}
+
+OctetDomain::OctetDomain(const VectorXd& dim, const VectorXl& div, double dT)
+    : dim_(checked(dim, 4, "OctetDomain needs 4 dimensions")), div_(checked(div, 4, "OctetDomain needs 4 divisions")), dT_(dT) {
+    const double r2 = std::sqrt(2.);
+    const double s = dim_[0], t = dim_[3];
+    const double a = PI / 5. * (dim_[1] + dim_[2]) - (4. - PI) / 5. * t, b = a / 4.;
+    MC_ASSERT_MSG(b > t, "Invalid dimensions");                                  // domain.cpp:702-704
+    MC_ASSERT_MSG(a > (r2 + 1.) * (b + t), "Invalid dimensions");
+    MC_ASSERT_MSG(s / 2. > a + (r2 + 1.) * (b + t) + t, "Invalid dimensions");
+    // the gradient runs along the strut, from the top node to the bottom node of the cell
+    const double g = dT / (s - 2. * a - 2. * (r2 + 1.) * b - 2. * (2. + r2) * t);
+    const Vector3d gradT(g, 0., -g), noGrad;
+    for (size_t i = 0; i < 42; ++i) {
+        const OctetCell& c = kOctetCells[i];
+        const Vector3d o(evalForm(c.o[0], s, a, t), evalForm(c.o[1], s, a, t), evalForm(c.o[2], s, a, t));
+        std::vector<Vector3d> cols;
+        for (int k = 0; k < c.ncol; ++k) cols.push_back(Vector3d(evalForm(c.col[k][0], s, a, t), evalForm(c.col[k][1], s, a, t), evalForm(c.col[k][2], s, a, t)));
+        Vector3l dv;
+        for (int k = 0; k < 3; ++k) dv(k) = c.div[k] < 0 ? -1 : div_[(size_t)c.div[k]];
+        cells_.push_back(makeCellAt(i, o, cols, dv, c.grad ? gradT : noGrad, std::make_index_sequence<42>()));
+    }
+    for (const auto& pr : kOctetInter) {
+        InterBoundary* x = dynamic_cast<InterBoundary*>(bdryOf(cells_, pr[0], pr[1]));
+        InterBoundary* y = dynamic_cast<InterBoundary*>(bdryOf(cells_, pr[2], pr[3]));
+        MC_ASSERT_MSG(x && y, "octet table: Inter pair on a boundary of another class");
+        makePair(*x, *y);
+    }
+    const Vector3d transl(s / 2., 0., -s / 2.);
+    const Matrix3d rot = Matrix3d::Diagonal(-1., 1., 1.);
+    for (const auto& pr : kOctetPeri) {
+        Boundary* x = bdryOf(cells_, pr[0], pr[1]); Boundary* y = bdryOf(cells_, pr[2], pr[3]);
+        if (Peri4* p4 = dynamic_cast<Peri4*>(x)) { Peri4* q4 = dynamic_cast<Peri4*>(y); MC_ASSERT_MSG(q4, "octet table: periodic pair of two shapes"); makePair(*p4, *q4, transl, rot); }
+        else { PeriP* pp = dynamic_cast<PeriP*>(x); PeriP* qp = dynamic_cast<PeriP*>(y); MC_ASSERT_MSG(pp && qp, "octet table: periodic pair of two shapes"); makePair(*pp, *qp, transl, rot); }
+    }
+    for (const auto& c : cells_) addSdom(c.get());
+}
+std::string OctetDomain::info() const { return describe("OctetDomain", static_cast<const Domain*>(this), dim_, div_, dT_); }
+
+Matrix3Xd OctetDomain::checkpoints() const {
+    std::vector<Vector3d> pts;
+    const double s = dim_[0], t = dim_[3], a = PI / 5. * (dim_[1] + dim_[2]) - (4. - PI) / 5. * t;
+    for (size_t i = 0; i < 42; ++i) {
+        const OctetCell& c = kOctetCells[i];
+        Vector3d o(evalForm(c.o[0], s, a, t), evalForm(c.o[1], s, a, t), evalForm(c.o[2], s, a, t));
+        std::vector<Vector3d> col;
+        for (int k = 0; k < c.ncol; ++k) col.push_back(Vector3d(evalForm(c.col[k][0], s, a, t), evalForm(c.col[k][1], s, a, t), evalForm(c.col[k][2], s, a, t)));
+        Vector3d p = o;
+        if (c.kind == MCB_CELL_PARALLELEPIPED) p = o + 0.5 * (col[0] + col[1] + col[2]);
+        else if (c.kind == MCB_CELL_TRIPRISM) p = o + (1. / 3.) * (col[0] + col[1]) + 0.5 * col[2];
+        else {                                                      // base polygon o, o + col 1 .. o + col N-1; col 0 = axis / apex
+            Vector3d base; for (int k = 1; k < c.ncol; ++k) base = base + col[(size_t)k];
+            base = (1. / c.ncol) * base;
+            p = c.kind == MCB_CELL_PRISM ? o + base + 0.5 * col[0] : o + 0.75 * base + 0.25 * col[0];
+        }
+        pts.push_back(p);
+    }
+    Matrix3Xd m; m.c = pts;
+    return m;
+}
+
+std::vector<double> OctetDomain::averageWeights() const {
+    std::vector<double> w;
+    for (size_t i = 0; i < cells_.size(); ++i) {
+        const Subdomain* sd = cells_[i].get();
+        const Vector3l shp = sd->shape();
+        for (long k = 0; k < shp(2); ++k) for (long j = 0; j < shp(1); ++j) for (long ii = 0; ii < shp(0); ++ii)
+            w.push_back((i >= 16 && i < 26 && k == 0) ? sd->cellVol(Vector3l(ii, j, k)) : 0.);      // WeightF, domain.cpp:1259-1280
+    }
+    return w;
+}
+ArrayXXd OctetDomain::average(const ArrayXXd& data) const {
+    const std::vector<double> w = averageWeights();
+    MC_ASSERT_MSG((long)w.size() == data.cols(), "average: column count");
+    double wsum = 0.; for (double x : w) wsum += x;
+    ArrayXXd avg(data.rows(), 1);
+    for (long r = 0; r < data.rows(); ++r) { double acc = 0.; for (long c = 0; c < data.cols(); ++c) acc += data(r, c) * w[(size_t)c]; avg(r, 0) = acc / wsum; }
+    return avg;
+}

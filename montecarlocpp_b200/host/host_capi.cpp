@@ -75,6 +75,7 @@ mcbh_domain* mcbh_domain_create(const char* kind, const double* dim, int ndim, c
         } else if (k == "jct") { need(4, 4); h->dom.reset(new JctDomain(d, v, dT)); }
         else if (k == "tee") { need(5, 5); h->dom.reset(new TeeDomain(d, v, dT)); }
         else if (k == "tube") { need(4, 4); h->dom.reset(new TubeDomain(d, v, dT)); }
+        else if (k == "octet") { need(4, 4); h->dom.reset(new OctetDomain(d, v, dT)); }
         else if (k == "hex") { need(4, 0); h->dom.reset(new HexDomain(d, dT)); }
         else if (k == "pyr") { need(3, 0); h->dom.reset(new PyrDomain(Vector3d(d[0], d[1], d[2]), dT)); }
         else MC_ASSERT_MSG(false, "Invalid domain");
@@ -85,6 +86,17 @@ mcbh_domain* mcbh_domain_create(const char* kind, const double* dim, int ndim, c
 void mcbh_domain_free(mcbh_domain* d) { delete d; }
 int mcbh_domain_desc(const mcbh_domain* d, mcb_domain_desc* out) { if (!d || !out) return MCB_EINVAL; *out = d->flat.desc(); return MCB_OK; }
 int64_t mcbh_domain_cols(const mcbh_domain* d) { return d->flat.cols; }
+// Domain::average applied to a rows x cols solution (column-major): returns the number of columns of the result
+// (cols for every shipped domain but OctetDomain, whose average is rows x 1, domain.cpp:1252-1257)
+int64_t mcbh_domain_average(const mcbh_domain* d, const double* sol, int64_t rows, double* out) {
+    MCBH_TRY(
+        ArrayXXd in(rows, d->flat.cols);
+        std::memcpy(in.data(), sol, sizeof(double) * (size_t)in.size());
+        ArrayXXd avg = d->dom->average(in);
+        std::memcpy(out, avg.data(), sizeof(double) * (size_t)avg.size());
+        return (int64_t)avg.cols();
+    , -1)
+}
 
 mcbh_problem* mcbh_problem_create(const Material* mat, const mcbh_domain* dom, int kind, int64_t nemit, int64_t size,
                                   int64_t maxscat, int64_t maxloop) {

@@ -5,6 +5,7 @@
 //
 //   grey|silicon [T] | custom [T] disp relax
 //   bulk dim div0 | film dim0 dim1 div1 | hex dim0 dim1 | pyr dim0 dim1 | jct dim0 dim3 | tee dim0 dim4 div0 | tube dim0 dim1 dim3 div1 div3
+//   octet dim0 dim1 dim2 dim3 div0 div1 div2 div3 dT
 //   slab dim0 dim1 div0 dT | wire dim0 dim1 div1        (not in the reference; see domain.h)
 //   temp|flux|multi nemit maxscat maxloop nsim | cumtemp|cumflux nemit size maxscat maxloop nsim
 //   check r00 r01 r02 r10 r11 r12 r20 r21 r22 | traj px py pz dx dy dz maxscat maxloop
@@ -189,6 +190,10 @@ int main(int argc, const char* argv[]) {
         } else if (domStr == "tube") {
             double d0, d1, d3; long v1, v3; argss >> d0 >> d1 >> d3 >> v1 >> v3;
             dom.reset(new TubeDomain(VectorXd{d0, d1, d1, d3}, VectorXl{0, v1, v1, v3}, 1e6 * d0));
+        } else if (domStr == "octet") {                                  // main.cpp:376-387
+            double d0, d1, d2, d3, dT; long v0, v1, v2, v3; argss >> d0 >> d1 >> d2 >> d3 >> v0 >> v1 >> v2 >> v3 >> dT;
+            MC_ASSERT_MSG(argss.fail() || (d0 > 0. && d1 > 0. && d2 > 0. && d3 > 0.), "Dimensions must be positive");
+            if (!argss.fail()) dom.reset(new OctetDomain(VectorXd{d0, d1, d2, d3}, VectorXl{v0, v1, v2, v3}, dT));
         } else MC_ASSERT_MSG(false, "Invalid domain");
         MC_ASSERT_MSG(!argss.fail(), "Invalid domain arguments");
         std::cout << *dom << std::endl << std::endl;

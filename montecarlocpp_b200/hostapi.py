@@ -35,6 +35,8 @@ def lib():
         L.mcbh_domain_desc.argtypes = [vp, C.POINTER(abi.DomainDesc)]
         L.mcbh_domain_cols.restype = C.c_int64
         L.mcbh_domain_cols.argtypes = [vp]
+        L.mcbh_domain_average.restype = C.c_int64
+        L.mcbh_domain_average.argtypes = [vp, dp, C.c_int64, dp]
         L.mcbh_problem_create.restype = vp
         L.mcbh_problem_create.argtypes = [vp, vp, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64]
         L.mcbh_problem_free.argtypes = [vp]
@@ -86,6 +88,16 @@ class Domain:
         self.desc = abi.DomainDesc()
         lib().mcbh_domain_desc(self.h, C.byref(self.desc))
         self.cols = lib().mcbh_domain_cols(self.h)
+
+    def average(self, sol):
+        """Domain::average (domain.cpp:78-81; OctetDomain: rows x 1 weighted mean, domain.cpp:1252-1257)."""
+        sol = np.asarray(sol, np.float64)
+        flat = np.ascontiguousarray(sol.T).ravel()               # column-major like ArrayXXd
+        out = np.zeros(flat.size)
+        n = lib().mcbh_domain_average(self.h, flat.ctypes.data_as(abi.c_double_p), sol.shape[0], out.ctypes.data_as(abi.c_double_p))
+        if n < 0:
+            raise RuntimeError(_err())
+        return out[:sol.shape[0] * n].reshape(n, sol.shape[0]).T.copy()
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -265,6 +265,36 @@ def test_octet_domain_through_the_reference_binding(gpu_ctx, matfiles, div):
     assert (np.abs(ag.mean(0) - ar.mean(0)) <= 3.5 * sa).all(), (ag.mean(0), ar.mean(0), sa)
 
 
+@pytest.mark.parametrize("div", [[0, 0, 0, 0], [2, 2, 2, 1]], ids=["cells", "grid"])
+def test_octet_domain_of_the_host_mirror(matfiles, div):
+    """The PRODUCT's OctetDomain (host mirror, geometry table of octet_table.inc) through FieldProblem::solve, against the
+    reference's CPU solve of its own OctetDomain: zero escapes, per-cell 4.5 sigma, Domain::average within 3.5 sigma."""
+    from oracle import refbin
+    if not refbin.driver_available():
+        pytest.skip("oracle/_ref/ref_driver not built (make -C oracle ref in the dev container)")
+    from montecarlocpp_b200 import hostapi
+    disp, relax = matfiles["silicon_small"]
+    dim, dT, nemit, maxscat, B = [1e-6, 1e-7, 1e-7, 1e-8], 1.0, 60000, 50, 6
+    mat = hostapi.Material(disp, relax, 300.0)
+    dom = hostapi.Domain("octet", dim, div, dT)
+    prob = hostapi.FieldProblem(mat, dom, "multi", nemit, maxscat)
+    hostapi.set_devices([0])
+    g, esc = [], 0
+    for b in range(B):
+        sol, st = prob.solve_seeded(SEED + 700 + b)
+        g.append(sol); esc += st["esc"]
+    r = [refbin.drive(disp, relax, 300.0, "octet", dim, div, dT, "multi", nemit, maxscat, seed=7000 + 16 * b, threads=4) for b in range(B)]
+    assert esc == 0 and sum(x["esc"] for x in r) == 0
+    g, r = np.stack(g), np.stack([x["output"] for x in r])
+    assert g.shape == r.shape and np.isfinite(g).all()
+    se = np.sqrt(g.var(0, ddof=1) / B + r.var(0, ddof=1) / B)
+    z = np.abs(g.mean(0) - r.mean(0)) / np.where(se > 0, se, 1.0)
+    assert (z < 4.5).all() and (z < 3.0).mean() > 0.9, z.max()
+    ag = np.stack([dom.average(x)[:, 0] for x in g]); ar = np.stack([dom.average(x)[:, 0] for x in r])
+    sa = np.sqrt(ag.var(0, ddof=1) / B + ar.var(0, ddof=1) / B)
+    assert (np.abs(ag.mean(0) - ar.mean(0)) <= 3.5 * sa).all(), (ag.mean(0), ar.mean(0), sa)
+
+
 def test_bulk_conductivity_within_one_percent(gpu_ctx, omats):
     """KA1: <q_x>/|grad T| -> Material::cond() (material.cpp:160-161)."""
     # grey pins the 1 % bar; the synthetic silicon's heavy-tailed free paths need the looser bound even at 1.6e7
@@ -337,8 +367,16 @@ def test_cli_driver_keeps_the_reference_stdout_blocks(matfiles, tmp_path):
     assert len(block) == 4 and all(len(row.split()) == 10 for row in block)
     vals = np.array([[float(x) for x in row.split()] for row in block])
     assert (vals[1] > 0).all()                      # heat flows down the gradient in every cell
-    bad = subprocess.run([exe, str(tmp_path), "grey", "300", "octet", "1"], capture_output=True, text=True)
+    bad = subprocess.run([exe, str(tmp_path), "grey", "300", "icosahedron", "1"], capture_output=True, text=True)
     assert bad.returncode != 0 and "Invalid domain" in bad.stderr
+    # the octet truss (main.cpp:376-387): gridded struts -> Output (4 x 32 columns) and the Averaged block (4 x 1) of Domain::average
+    r = subprocess.run([exe, str(tmp_path), "grey", "300", "octet", "1e-6", "1e-7", "1e-7", "1e-8", "2", "2", "2", "1", "1.0",
+                        "multi", "40000", "20", "0", "1"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    for token in ("OctetDomain ", "  div: [2 2 2 1]", "Output", "Averaged", "esc: 0"):
+        assert token in r.stdout, token
+    avg = r.stdout.split("Averaged\n")[1].split("\n\n")[0].strip().split("\n")
+    assert len(avg) == 4 and all(len(row.split()) == 1 for row in avg)
 
 
 TRAJ_CASES = [("grey", "tube", dict(pos=[5e-7, 6e-8, 1e-8], dir=[1, 0.3, 0.2]), 40), ("silicon", "jct", dict(pos=[1e-7, 5e-8, 2.5e-8]), 30),

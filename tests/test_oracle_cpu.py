@@ -282,6 +282,8 @@ def test_host_mirror_error_behaviour(matfiles):
     with pytest.raises(RuntimeError, match="Error opening dispersion file"):
         hostapi.Material("/nonexistent_disp.txt", matfiles["grey"][1])
     with pytest.raises(RuntimeError, match="Invalid domain"):
+        hostapi.Domain("icosahedron", [1.0] * 4, [1] * 4, 1.0)
+    with pytest.raises(RuntimeError, match="Invalid dimensions"):          # domain.cpp:702-704
         hostapi.Domain("octet", [1.0] * 4, [1] * 4, 1.0)
     with pytest.raises(RuntimeError, match="Volume too small"):
         hostapi.Domain("bulk", [1e-6, -1e-6, 1e-6], [1, 0, 0], 1.0)
