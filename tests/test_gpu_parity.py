@@ -297,8 +297,9 @@ def test_octet_domain_of_the_host_mirror(matfiles, div):
 
 def test_bulk_conductivity_within_one_percent(gpu_ctx, omats):
     """KA1: <q_x>/|grad T| -> Material::cond() (material.cpp:160-161)."""
-    # grey pins the 1 % bar; the synthetic silicon's heavy-tailed free paths need the looser bound even at 1.6e7
-    for mname, tol in (("grey", 0.01), ("silicon", 0.02)):
+    # grey at 1.6e7 phonons; the synthetic silicon's heavy-tailed free paths need ~1e9 for the same 1 % bar:
+    # tests/test_gpu_configs.py::test_bulk_conductivity_within_one_percent_both_materials
+    for mname, tol in (("grey", 0.01),):
         mat, dom = omats[mname], cases.bulk()
         cases.upload(gpu_ctx, mat, dom)
         # maxscat = 1: only the first flight carries signal (later flights are isotropic, zero-mean noise)
