@@ -11,6 +11,7 @@
 #include "../../include/mcb.h"
 
 #include "mc_types.h"
+#include "phonon.h"
 
 class Material {
     static const int nscat_ = 2;
@@ -33,6 +34,8 @@ public:
     unsigned long uid() const { return uid_; }
     double tau(long w, long p) const { return tau_.at((size_t)(w + nw_ * p)); }
     double vel(long w, long p) const { return vel_.at((size_t)(w + nw_ * p)); }
+    double tau(const Phonon& phn) const { return tau(phn.prop().w(), phn.prop().p()); }      // material.cpp:174-184
+    double vel(const Phonon& phn) const { return vel(phn.prop().w(), phn.prop().p()); }
     double energySum() const { return energySum_; }
     double fluxSum() const { return fluxSum_; }
     double scatSum() const { return scatSum_; }

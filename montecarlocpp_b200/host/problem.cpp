@@ -15,6 +15,7 @@
 #include <omp.h>
 #endif
 #include "domain.h"
+#include "field.h"
 #include "material.h"
 
 //---------------------------------------- Clock / Progress
@@ -182,6 +183,38 @@ void withDevice(int dev, const Material* mat, const Domain* dom, F f) {
 int firstDevice() { std::lock_guard<std::mutex> lock(g_mu); return g_devices.front(); }
 }
 
+
+//---------------------------------------- Field::accumulate / CellVolF
+VectorXd CellVolF::operator()(const Subdomain* sdom, const Vector3l& index) const { return VectorXd(1, sdom->cellVol(index)); }
+
+Field& Field::accumulate(const Subdomain* sdom, const Vector3d& ipos, const Vector3d& fpos, const VectorXd& amount) {
+    MC_ASSERT_MSG(dom_, "Field has no domain");
+    MC_ASSERT_MSG((long)amount.size() == data_.rows(), "Amount has the wrong number of rows");
+    int32_t index = -1;
+    const Subdomain::Pointers& sp = dom_->sdomPtrs();
+    for (size_t i = 0; i < sp.size(); ++i) if (sp[i] == sdom) index = (int32_t)i;
+    MC_ASSERT_MSG(index >= 0, "Subdomain not in domain");
+    const double b[3] = {ipos(0), ipos(1), ipos(2)}, e[3] = {fpos(0), fpos(1), fpos(2)};
+    // the tally walk lives on the device (k_accumulate behind mcb_accumulate); only the geometry tables are needed
+    DeviceContext* dc = 0;
+    const int dev = firstDevice();
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        std::unique_ptr<DeviceContext>& slot = g_ctx[dev];
+        if (!slot) {
+            slot.reset(new DeviceContext);
+            if (mcb_create(dev, &slot->ctx) != MCB_OK) { std::string msg = mcb_last_error(0); slot.reset(); g_ctx.erase(dev); throw std::runtime_error("mcb_create: " + msg); }
+        }
+        dc = slot.get();
+    }
+    std::lock_guard<std::mutex> lock(dc->mu);
+    if (dc->dom != dom_->uid()) {
+        FlatDomain fd = flattenDomain(dom_); mcb_domain_desc dd = fd.desc();
+        check(dc->ctx, mcb_upload_domain(dc->ctx, &dd), "mcb_upload_domain"); dc->dom = dom_->uid(); dc->cols = fd.cols;
+    }
+    check(dc->ctx, mcb_accumulate(dc->ctx, (int32_t)data_.rows(), 1, &index, b, e, amount.data(), data_.data()), "mcb_accumulate");
+    return *this;
+}
 
 //---------------------------------------- TrajProblem
 TrajProblem::TrajProblem() : maxscat_(0), maxloop_(0) {}

@@ -131,6 +131,13 @@ private:
     mutable std::vector<int64_t> emit64_;
 };
 
+// Field(1, dom, CellVolF()): the cell volumes the normalisation divides by (problem.h:151-155, problem.cpp:302-306, 441-442)
+class Subdomain;
+class CellVolF {
+public:
+    VectorXd operator()(const Subdomain* sdom, const Vector3l& index) const;
+};
+
 #define MCB_DECLARE_FIELD_PROBLEM(Name)                                                              \
     class Name : public FieldProblem {                                                              \
         std::string info() const;                                                                   \
