@@ -111,6 +111,7 @@ struct mcb_ctx {
     // geometry
     bool has_dom = false; GeometryView gv{}; DevBuf<unsigned char> geo_blob;
     std::vector<DSdom> h_sdom; int nemitter = 0; int any_nd = 0;      // 0 / 1 / 2: see k_step's NDM
+    int nd_mark_words = 0;       // warp-balanced N-D tally: 32-bit mark words a warp needs = max items of one flight (1 + sum of max_)
     int all_box = 0;             // every subdomain is an axis-aligned box (k_step's BOX)
     int t1_ok = 0;               // every 1-D tally grid has unit column stride (the difference-array histograms apply)
     DevBuf<DEmitter> emitters; DevBuf<double> cell_vol; long long cols = 0;
@@ -171,6 +172,8 @@ int ensure_slots(mcb_ctx* c, long long slots) {
 
 struct RunPlan {
     long long slots; int S, block, grid; int tm, copies; size_t smem;
+    int ndm;                            // k_step's NDM: 0 no N-D grid, 1 serial walk, 2 + cooperative pieces, 3 warp-balanced items
+    uint32_t nd_off, nd_warp_bytes;     // NDM 3: the per-warp record areas
     // 1-D difference-array histograms (tm == MCB_TM_WARP, no N-D grid): padded columns (0 = run-time stride), plane stride,
     // warps per histogram group, flush interval in loop trips, offset of the flush scratch
     int t1d, pad, trips; uint32_t ps, inst_bytes, scratch_off, stage_off, wbar_off;
@@ -181,6 +184,15 @@ struct RunPlan {
 #ifndef MCB_COOP_ND_CELLS
 #define MCB_COOP_ND_CELLS 64      // grids at least this fine along an axis take the warp-cooperative N-D walk
 #endif
+#ifndef MCB_ND_BALANCED
+#define MCB_ND_BALANCED 1      // N-D tally grids: the warp-balanced item walk (k_step NDM 3) instead of the per-lane serial walk
+#endif
+#ifndef MCB_EMIT_FUSED
+#define MCB_EMIT_FUSED 1       // steady phase: k_step refills its own free slots (no k_emit / k_emit_commit launches between the steps)
+#endif
+#ifndef MCB_DECAY_S
+#define MCB_DECAY_S 16         // loop trips per launch once nothing is left to emit
+#endif
 #ifndef MCB_COMPACT_PCT
 #define MCB_COMPACT_PCT 90
 #endif
@@ -188,11 +200,19 @@ struct RunPlan {
 int plan_run(mcb_ctx* c, const mcb_problem_desc* prob, long long nparticles, RunPlan* r) {
     const mcb_options& o = c->opt;
     const int per_sm = o.ctas_per_sm > 0 ? o.ctas_per_sm : 1;
-    const size_t base = 16 + (size_t)c->mv.bytes + (size_t)c->gv.bytes;
+    size_t base = 16 + (size_t)c->mv.bytes + (size_t)c->gv.bytes;
     const size_t budget = c->smem_optin / (size_t)per_sm > 1024 ? c->smem_optin / (size_t)per_sm - 1024 : 0;
     // CTA shapes (__launch_bounds__ of the k_step instances): 1-D tallies 768 threads x 80 registers; the N-D walks are built for
     // fewer, fatter threads
-    const int block_max = c->any_nd == 2 ? MCB_BLOCK_MAX_ND : (c->any_nd == 1 ? MCB_BLOCK_MAX_ND1 : MCB_BLOCK_MAX);
+    r->ndm = c->any_nd; r->nd_off = 0; r->nd_warp_bytes = 0;
+#if MCB_ND_BALANCED
+    if (c->any_nd) {                    // the per-warp record areas must leave room for the tables (very fine grids need many mark words)
+        const size_t wb = (size_t)(MCB_NDB_FIXED + 4 * (c->nd_mark_words + 2) + 15) / 16 * 16;
+        const int blk = o.block > 0 ? std::min(o.block, MCB_BLOCK_MAX_ND3) : MCB_BLOCK_MAX_ND3;
+        if (base + 16 + (size_t)(blk / 32) * wb <= budget) { r->ndm = 3; r->nd_warp_bytes = (uint32_t)wb; }
+    }
+#endif
+    const int block_max = r->ndm == 3 ? MCB_BLOCK_MAX_ND3 : (c->any_nd == 2 ? MCB_BLOCK_MAX_ND : (c->any_nd == 1 ? MCB_BLOCK_MAX_ND1 : MCB_BLOCK_MAX));
     r->block = o.block > 0 ? std::min(o.block, block_max) : block_max;
     if (r->block % 32 != 0 || o.block > 1024) { c->err = "block must be a multiple of 32, <= 1024"; return MCB_EINVAL; }
     r->S = o.steps_per_launch > 0 ? o.steps_per_launch : 16;
@@ -203,6 +223,10 @@ int plan_run(mcb_ctx* c, const mcb_problem_desc* prob, long long nparticles, Run
     const long long tiles = (slots + r->block - 1) / r->block;
     r->grid = (int)std::min<long long>((long long)c->sm_count * per_sm, std::max<long long>(tiles, 1));
     const size_t nwarps = (size_t)r->block / 32;
+    if (r->ndm == 3) {                  // the record areas sit between the tables and the histogram
+        r->nd_off = (uint32_t)((base + 15) / 16 * 16);
+        base = r->nd_off + nwarps * r->nd_warp_bytes;
+    }
     r->t1d = 0; r->pad = 0; r->trips = MCB_FX_FLUSH_TRIPS; r->ps = 0; r->inst_bytes = 0; r->scratch_off = 0; r->stage_off = 0; r->wbar_off = 0;
     r->copies = 1; r->cstride = 0; r->tm = MCB_TM_GLOBAL;
     const size_t stage = nwarps * (MCB_GROUP_BYTES + 8) + 128;       // per-warp staging buffers of the TMA state prefetch + mbarriers
@@ -211,7 +235,7 @@ int plan_run(mcb_ctx* c, const mcb_problem_desc* prob, long long nparticles, Run
         r->stage_off = (uint32_t)((end + 127) / 128 * 128); r->wbar_off = r->stage_off + (uint32_t)(nwarps * MCB_GROUP_BYTES);
         return (size_t)r->wbar_off + nwarps * 8;
     };
-    const long long fdep = c->any_nd == 2 ? 3 : 1;                     // deposits of one flight into one entry (cooperative N-D walk: <= 3)
+    const long long fdep = r->ndm == 2 ? 3 : 1;                     // deposits of one flight into one entry (cooperative N-D walk: <= 3)
     // (1) 1-D / single-cell tallies: difference-array histograms (mcb_device.cuh: deposit_fx).  An instance holds
     // [direct | difference][row][limb 0 | 1 | 2] planes of `ps` bytes and is shared by the whole CTA; up to 4 copies (picked by
     // lane id) thin out same-word hits inside a warp instruction.  The state staging buffers come first, copies take the rest.
@@ -270,6 +294,8 @@ void apply_plan(const RunPlan& plan, const mcb_problem_desc* prob, StepParams* P
     P->tally_smem = plan.tm; P->hist_copies = plan.copies;
     P->fx_ps = plan.ps; P->fx_diff_off = (uint32_t)prob->rows * MCB_T1D_LIMBS * plan.ps; P->hist_bytes = plan.inst_bytes; P->so_scratch = plan.scratch_off;
     P->so_stage = plan.stage_off; P->so_wbar = plan.wbar_off; P->fx_cstride = plan.cstride;
+    P->so_nd = plan.nd_off; P->nd_warp_bytes = plan.nd_warp_bytes;
+    if (plan.ndm == 3) P->so_hist = (uint32_t)(plan.nd_off + (size_t)(plan.block / 32) * plan.nd_warp_bytes);
 }
 
 // Fixed-point scale of the shared-memory tallies (mcb_device.cuh: deposit, deposit_fx).  Payload component k of a flight is
@@ -280,7 +306,7 @@ void apply_plan(const RunPlan& plan, const mcb_problem_desc* prob, StepParams* P
 // 3 for the cooperative N-D walk, whose pieces can share a cell): the 16-bit limb fields sum below 2^32 and the top limb
 // stays inside int32 for Q = 64 - n, capped at 50 (the rounding trick holds |q| < 2^51): quantum 2^-47 .. 2^-49 of fx_max.
 void set_fixed_point(mcb_ctx* c, const mcb_problem_desc* prob, const RunPlan& plan, StepParams* P) {
-    const long long bound = (long long)std::max(1, plan.block / plan.copies) * plan.trips * (c->any_nd == 2 ? 3 : 1);
+    const long long bound = (long long)std::max(1, plan.block / plan.copies) * plan.trips * (plan.ndm == 2 ? 3 : 1);
     int n = 0; while ((1ll << n) < bound) ++n;                                             // bound <= 2^n <= 2^16
     const int QB = std::min(50, 64 - n);
     P->fx_limb_bits = 16;
@@ -326,7 +352,7 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
     apply_plan(plan, prob, &P);
     set_fixed_point(c, prob, plan, &P);
 
-    Counters init{}; init.next = (unsigned long long)n_begin;
+    Counters init{}; init.next[0] = init.next[1] = (unsigned long long)n_begin;
     CUDA_TRY(c, cudaMemcpyAsync(c->ctr.p, &init, sizeof init, cudaMemcpyHostToDevice, c->stream));
     int cur = 0; long long nslots = plan.slots;
     CUDA_TRY(c, cudaMemsetAsync(c->state[cur].p, 0, state_bytes(nslots), c->stream));        // every slot inactive
@@ -353,8 +379,8 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
         if (grid0 * nwarps0 > MCB_MAX_SEG) { c->err = "persistent grid too large for the free-list segments"; return MCB_ELIMIT; }
         P.free_seg = (uint32_t)(((tiles0 + grid0 - 1) / grid0) * 32);       // one segment per k_step WARP: 32 slots per tile
         CUDA_TRY(c, c->free_list.alloc((size_t)(grid0 * nwarps0) * P.free_seg));
-        CUDA_TRY(c, c->free_cnt.alloc(MCB_MAX_SEG));
-        CUDA_TRY(c, cudaMemsetAsync(c->free_cnt.p, 0, MCB_MAX_SEG * sizeof(uint32_t), c->stream));
+        CUDA_TRY(c, c->free_cnt.alloc(2 * MCB_MAX_SEG));                    // double-buffered by launch parity
+        CUDA_TRY(c, cudaMemsetAsync(c->free_cnt.p, 0, 2 * MCB_MAX_SEG * sizeof(uint32_t), c->stream));
         P.free_list = c->free_list.p; P.free_cnt = c->free_cnt.p;
     } else P.free_list = nullptr;
     long long steady_launches = 0; float steady_ms = 0.f;
@@ -363,19 +389,24 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
         const int slot = (int)(it & 1);
         // fixed-point histograms are flushed between tiles: keep a tile's loop trips within the flush interval
         if (plan.tm != MCB_TM_GLOBAL) S_cur = std::min(S_cur, plan.trips);
-        P.st = view_of(c, cur); P.nslots = nslots; P.steps_per_launch = S_cur;
-        if (dense && !host_all_emitted) {
-            // K1: fill the free slots listed by the previous k_step (all of them before the first), with full warps
-            k_emit<<<(unsigned)(c->sm_count * 4), 256, 0, c->stream>>>(P, nseg);
-            k_emit_commit<<<1, 256, 0, c->stream>>>(P, nseg);         // also re-arms ctr->live
-            CUDA_TRY(c, cudaGetLastError());
-            launches += 2;
-        } else CUDA_TRY(c, cudaMemsetAsync(&c->ctr.p->live, 0, sizeof(unsigned long long), c->stream));   // rewritten by every launch
+        P.st = view_of(c, cur); P.nslots = nslots; P.steps_per_launch = S_cur; P.parity = slot;
         const long long tiles = (nslots + plan.block - 1) / plan.block;
         const int grid = (int)std::min<long long>(plan.grid, std::max<long long>(tiles, 1));
+        // K1: the first fill (every slot free) is its own dense kernel; afterwards every k_step warp refills, at the start of
+        // the launch, the slots it listed as free in the launch before (same grid, same slots: nothing is compacted while
+        // particles are left to emit).  MCB_EMIT_FUSED=0 keeps the two emission kernels between the k_step launches.
+        P.emit_fused = 0;
+        if (dense && !host_all_emitted) {
+            if (it == 0 || !MCB_EMIT_FUSED || grid * (plan.block / 32) != nseg) {
+                k_emit<<<(unsigned)(c->sm_count * 4), 256, 0, c->stream>>>(P, nseg);
+                k_emit_commit<<<1, 256, 0, c->stream>>>(P, nseg);
+                CUDA_TRY(c, cudaGetLastError());
+                launches += 2;
+            } else P.emit_fused = 1;
+        }
         nseg = grid * (plan.block / 32);
         CUDA_TRY(c, cudaEventRecord(c->evA[slot], c->stream));
-        CUDA_TRY(c, launch_step(P, plan.tm, c->any_nd, c->all_box, plan.pad, grid, plan.block, plan.smem, c->stream));
+        CUDA_TRY(c, launch_step(P, plan.tm, plan.ndm, c->all_box, plan.pad, grid, plan.block, plan.smem, c->stream));
         CUDA_TRY(c, cudaEventRecord(c->evB[slot], c->stream));
         CUDA_TRY(c, cudaMemcpyAsync(&c->h_ctr[slot], c->ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(c, cudaEventRecord(c->evC[slot], c->stream));
@@ -384,7 +415,7 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
         const int prev = slot ^ 1;
         CUDA_TRY(c, cudaEventSynchronize(c->evC[prev]));
         float ms = 0.f; cudaEventElapsedTime(&ms, c->evA[prev], c->evB[prev]); step_ms_total += ms;
-        const unsigned long long live = c->h_ctr[prev].live, next = c->h_ctr[prev].next;
+        const unsigned long long live = c->h_ctr[prev].live[prev], next = c->h_ctr[prev].next[prev ^ 1];     // launch it-1 had parity `prev`
         const bool all_emitted = next >= (unsigned long long)n_end;
         host_all_emitted = all_emitted;
         if (!all_emitted) {          // launch it-1 ran with a full population: steady-phase accounting
@@ -413,7 +444,7 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
         // decay phase (nothing left to emit): launches are no longer full, so amortise them over >= 16 loop trips;
         // once the survivors fit one tile per CTA let every thread run its phonon to termination
         if (all_emitted && c->opt.decay_mode != 1) {
-            S_cur = std::max(plan.S, 16);
+            S_cur = std::max(plan.S, MCB_DECAY_S);
             if ((long long)live <= tail_slots) S_cur = (int)std::min<long long>(std::max<long long>(prob->maxloop, 1), 1 << 22);
         }
     }
@@ -602,7 +633,7 @@ int mcb_upload_domain(mcb_ctx* c, const mcb_domain_desc* d) {
     for (int i = 0; i < d->npair; ++i) if (d->pairs[i] < 0 || d->pairs[i] >= d->nplane) { c->err = "pair id out of range"; return MCB_EINVAL; }
     std::vector<DSdom> sd(d->nsdom); std::vector<double> cell_vol; int any_nd = 0; double flight_max = 0.0;
     int all_box = 1, t1_ok = 1;
-    long long cols = 0;
+    long long cols = 0, nd_mark_words = 0;
     for (int s = 0; s < d->nsdom; ++s) {
         const mcb_sdom_desc& S = d->sdoms[s]; DSdom& D = sd[s]; std::memset(&D, 0, sizeof D);
         if (S.plane_count <= 0 || S.plane_begin < 0 || S.plane_begin + S.plane_count > d->nplane) { c->err = "sdom plane range out of bounds"; return MCB_EINVAL; }
@@ -644,6 +675,11 @@ int mcb_upload_domain(mcb_ctx* c, const mcb_domain_desc* d) {
                 diam = std::min(diam, best * (1.0 + 1e-12));
             }
             flight_max = std::max(flight_max, diam + 4.0 * std::fabs(S.eps));
+        }
+        if (S.accum >= 3) {
+            nd_mark_words = std::max<long long>(nd_mark_words, 1 + S.max[0] + S.max[1] + S.max[2]);
+            // BOX kernels take coord() as div * (inv_dd * (p_d - o_d)): every off-diagonal entry of inv_ must be an exact zero
+            if (D.aabb) for (int r = 0; r < 3; ++r) for (int k = 0; k < 3; ++k) if (r != k && S.inv[r + 3 * k] != 0.0) all_box = 0;
         }
         if (S.accum >= 3) any_nd = std::max(any_nd, (S.shape[0] >= MCB_COOP_ND_CELLS || S.shape[1] >= MCB_COOP_ND_CELLS || S.shape[2] >= MCB_COOP_ND_CELLS) ? 2 : 1);
         const long long sp = S.shape[0] * S.shape[1] * S.shape[2];
@@ -728,7 +764,7 @@ int mcb_upload_domain(mcb_ctx* c, const mcb_domain_desc* d) {
     CUDA_TRY(c, cudaMemcpy(c->emitters.p, em.data(), em.size() * sizeof(DEmitter), cudaMemcpyHostToDevice));
     CUDA_TRY(c, c->cell_vol.alloc(cell_vol.size()));
     if (!cell_vol.empty()) CUDA_TRY(c, cudaMemcpy(c->cell_vol.p, cell_vol.data(), cell_vol.size() * 8, cudaMemcpyHostToDevice));
-    c->gv = v; c->h_sdom = sd; c->nemitter = d->nemitter; c->cols = cols; c->any_nd = any_nd; c->flight_max = flight_max; c->has_dom = true;
+    c->gv = v; c->h_sdom = sd; c->nemitter = d->nemitter; c->cols = cols; c->any_nd = any_nd; c->nd_mark_words = (int)std::min<long long>(nd_mark_words, 1 << 20); c->flight_max = flight_max; c->has_dom = true;
     c->all_box = all_box; c->t1_ok = t1_ok;
     return MCB_OK;
 }
@@ -903,13 +939,13 @@ int mcb_trace(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
     P.field = nullptr; P.do_tally = 0;
     P.steps_per_launch = (int)std::max<long long>(1, std::min<long long>(P.maxloop, 0x7FFFFFFF)); P.n_end = (unsigned long long)n_end;
     P.st = view_of(c, 0); P.nslots = n; P.free_list = nullptr; P.free_cnt = nullptr;
-    Counters init{}; init.next = (unsigned long long)n_begin;
+    Counters init{}; init.next[0] = init.next[1] = (unsigned long long)n_begin;
     CUDA_TRY(c, cudaMemcpyAsync(c->ctr.p, &init, sizeof init, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaMemsetAsync(c->state[0].p, 0, state_bytes(c->slots_alloc), c->stream));
-    k_emit<<<(unsigned)(c->sm_count * 4), 256, 0, c->stream>>>(P, 0);     // first fill: particle n_begin + j into slot j
+    k_emit<<<(unsigned)(c->sm_count * 8), 256, 0, c->stream>>>(P, 0);     // first fill: particle n_begin + j into slot j
     k_emit_commit<<<1, 256, 0, c->stream>>>(P, 0);
     CUDA_TRY(c, cudaGetLastError());
-    if (P.maxloop > 0) CUDA_TRY(c, launch_step(P, plan.tm, c->any_nd, c->all_box, plan.pad, plan.grid, plan.block, plan.smem, c->stream));
+    if (P.maxloop > 0) CUDA_TRY(c, launch_step(P, plan.tm, plan.ndm, c->all_box, plan.pad, plan.grid, plan.block, plan.smem, c->stream));
     DevBuf<double> dpos, ddir, dsn; DevBuf<long long> dw, dp, dnscat, dsteps; DevBuf<int32_t> dsign, dalive, dsdom, dcell;
     CUDA_TRY(c, dpos.alloc(3 * n)); CUDA_TRY(c, ddir.alloc(3 * n)); CUDA_TRY(c, dsn.alloc(n));
     CUDA_TRY(c, dw.alloc(n)); CUDA_TRY(c, dp.alloc(n)); CUDA_TRY(c, dnscat.alloc(n)); CUDA_TRY(c, dsteps.alloc(n));

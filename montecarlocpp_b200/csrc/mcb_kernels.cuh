@@ -224,17 +224,32 @@ __device__ __forceinline__ void emit_from(const DEmitter& E, Rng& g, Particle& p
     ph.init(0u, sign != 0u, false, (uint32_t)E.sdom, 0ull);           // the caller sets wp, active and the particle id
 }
 
-// problem.cpp:386-399 for particle `pid`: pick emitter, drawFluxProp, Emitter::emit, drawScatNext
-static __device__ __noinline__ void emit_particle(const StepParams& P, const Tables& T, unsigned long long pid, Particle& ph) {
+// problem.cpp:386-399 for particle `pid`: pick emitter, drawFluxProp, Emitter::emit, drawScatNext.  Out of line (it is long and
+// runs once per particle); its inputs travel BY VALUE: a reference to the kernel parameter struct would force every thread to
+// copy the whole struct into local memory.
+struct EmitArgs {
+    const DEmitter* emitters; const long long* emit_cdf; const double* f_wprob; const double* f_pprob;
+    const int32_t* f_walias; const int32_t* f_palias; const double* lambda;
+    unsigned long long seed; double inv_bucket_w, inv_bucket_p; int32_t nemitter, nw, np, active;
+};
+static __device__ __noinline__ void emit_particle_impl(const EmitArgs a, unsigned long long pid, Particle& ph) {
     // emitter = upper_bound(emitCdf, n)  (problem.cpp:386-387)
-    int lo = 0, hi = P.nemitter;
-    while (lo < hi) { int mid = (lo + hi) >> 1; if ((long long)pid < P.emit_cdf[mid]) hi = mid; else lo = mid + 1; }
-    const DEmitter& E = P.emitters[lo];
-    Rng g; g.begin(P.seed, pid, 0u);
-    const uint32_t wp = draw_prop(g, T, P.f_wprob, P.f_walias, P.f_pprob, P.f_palias);
+    int lo = 0, hi = a.nemitter;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if ((long long)pid < a.emit_cdf[mid]) hi = mid; else lo = mid + 1; }
+    const DEmitter& E = a.emitters[lo];
+    Rng g; g.begin(a.seed, pid, 0u);
+    Tables T; T.nw = a.nw; T.np = a.np; T.inv_bucket_w = a.inv_bucket_w; T.inv_bucket_p = a.inv_bucket_p;
+    const uint32_t wp = draw_prop(g, T, a.f_wprob, a.f_walias, a.f_pprob, a.f_palias);
     emit_from(E, g, ph);
-    ph.init(wp, ph.sign(), P.maxloop > 0, ph.sdom(), pid);
-    ph.sn = draw_scat_next(g, T.lambda[wp]);
+    ph.init(wp, ph.sign(), a.active != 0, ph.sdom(), pid);
+    ph.sn = draw_scat_next(g, a.lambda[wp]);
+}
+__device__ __forceinline__ void emit_particle(const StepParams& P, const Tables& T, unsigned long long pid, Particle& ph) {
+    EmitArgs a;
+    a.emitters = P.emitters; a.emit_cdf = P.emit_cdf; a.f_wprob = P.f_wprob; a.f_pprob = P.f_pprob; a.f_walias = P.f_walias; a.f_palias = P.f_palias;
+    a.lambda = T.lambda; a.seed = P.seed; a.inv_bucket_w = T.inv_bucket_w; a.inv_bucket_p = T.inv_bucket_p;
+    a.nemitter = P.nemitter; a.nw = T.nw; a.np = T.np; a.active = P.maxloop > 0 ? 1 : 0;
+    emit_particle_impl(a, pid, ph);
 }
 
 // Subdomain::isInside subdomain.cpp:108-116.  BOX: every subdomain of the domain is an axis-aligned box (the host checks).
@@ -344,6 +359,68 @@ __device__ __forceinline__ uint32_t advect_move(const Tables& T, Particle& ph, S
     return 0u;
 }
 
+// The random events of a loop trip -- Material::scatter (material.cpp:226-231) and DiffBoundary::scatter (boundary.cpp:308-312)
+// -- are drawn TOGETHER: both start the event's word sequence with Philox block 0 and both end in "two uniforms -> sqrt ->
+// sincos(pi r) -> unit vector" (drawIso / drawAniso, random.cpp:16-44), so the lanes of a warp that scatter intrinsically and
+// the lanes that hit a diffuse wall share one pass through the Philox rounds and the sincos kernel instead of taking two
+// divergent ones (wire / film: the two events split a warp about evenly).
+//  * intrinsic: seven words (w int, w real, p int, p real, iso mu, iso phi, free path) at fixed positions of blocks 0 and 1,
+//    valid when no draw is rejected (probability ~ nw / 2^32); a rejection (or a 1-entry table, whose uniform_int draws no
+//    word) replays the event through the sequential generator, so the consumed stream is always the CPU oracle's;
+//  * diffuse wall: words 0 and 1 of block 0 (aniso r, phi), then the wall's rotation.
+// (Drawing the event ahead of the flight, to interleave its dependency chain with advect / tally, was measured:
+// -4 ... -14 %, the extra live registers cost more than the overlap gains.)
+template <bool BOX>
+__device__ __forceinline__ void scatter_draw(const StepParams& P, const Tables& T, Particle& ph, bool intr, const DPlaneCold* cb) {
+    uint32_t a[4];
+    philox4x32_10_rk(ph.pid_lo(), ph.pid_hi(), ph.step(), 0u, P.rk, a);
+    uint32_t w1 = a[0], w2 = a[1];                 // the two words of the direction draw
+    bool ok = true;
+    uint32_t wp = 0; double dist = 0.0;
+    if (intr) {
+        ok = T.nw > 1 && T.np > 1;
+        if (ok) {
+            uint32_t b[4];
+            philox4x32_10_rk(ph.pid_lo(), ph.pid_hi(), ph.step(), 1u, P.rk, b);
+            uint32_t r = (uint32_t)(((double)a[0] + 0.5) * T.inv_bucket_w);
+            uint32_t q = (uint32_t)(((double)a[2] + 0.5) * T.inv_bucket_p);
+            ok = r < (uint32_t)T.nw && q < (uint32_t)T.np;
+            r = min(r, (uint32_t)T.nw - 1u); q = min(q, (uint32_t)T.np - 1u);
+            const uint32_t w = (double)a[1] * c_k[25] < T.wprob[r] ? r : (uint32_t)T.walias[r];
+            const uint32_t k = w * (uint32_t)T.np + q;
+            wp = (double)a[3] * c_k[25] < T.pprob[k] ? k : w * (uint32_t)T.np + (uint32_t)T.palias[k];
+            dist = T.lambda[wp] * neg_log1m_u32(b[2]);                 // drawScatNext material.cpp:215-224
+            ok = ok && !(dist < c_k[27]);
+            w1 = b[0]; w2 = b[1];
+        }
+    }
+    if (ok) {
+        const double u = fma((double)w1, c_k[26], -1.0);              // uniform_real(-1, 1), exact
+        double sp, cp; sincospi_unit(fma((double)w2, c_k[26], -1.0), &sp, &cp);
+        // drawIso: z = u, sin = sqrt(1 - u^2) ; drawAniso(false): sin^2 = |u|, z = sqrt(1 - |u|)
+        const double au = fabs(u);
+        const double sth = sqrt(intr ? fma(-u, u, 1.0) : au);
+        double z = u;
+        if (!intr) z = sqrt(1.0 - au);
+        const double lx = sth * cp, ly = sth * sp;
+        if (intr) {
+            // (sth cp, sth sp, u) is unit to ~2e-16 by construction; Phonon::dir's normalisation (phonon.cpp:88-93) would move it
+            // by <= 1 ulp per component, which is the size of the other documented deviations: it is skipped
+            ph.set_wp(wp); ph.dx = lx; ph.dy = ly; ph.dz = z; ph.sn = dist;
+        } else {
+            matvec(cb->m, lx, ly, z, ph.dx, ph.dy, ph.dz);
+            renorm_unit(ph.dx, ph.dy, ph.dz);
+        }
+    } else {                                                           // intrinsic, replayed word by word
+        Rng g; g.begin(P.seed, ph.pid(), ph.step());
+        ph.set_wp(draw_prop(g, T, T.wprob, T.walias, T.pprob, T.palias));
+        draw_iso(g, ph.dx, ph.dy, ph.dz);
+        ph.sn = draw_scat_next(g, T.lambda[ph.wp()]);
+        renorm_unit(ph.dx, ph.dy, ph.dz);
+    }
+    ph.nscat++;
+}
+
 // The random part of Material::scatter (material.cpp:226-231): its seven words (w int, w real, p int, p real, iso mu,
 // iso phi, free path) sit at fixed positions of two Philox blocks, valid when no draw is rejected (probability ~ nw / 2^32);
 // a rejection (ok = false) replays the event through the sequential generator in collide(), so the consumed stream is
@@ -374,12 +451,16 @@ __device__ __forceinline__ void draw_event(const StepParams& P, const Tables& T,
 }
 
 // Second half of a loop trip (problem.cpp:418-434): Boundary::scatter or Material::scatter, then the stop test.
-template <bool BOX>
+// UNI: intrinsic and diffuse-wall events share one pass through scatter_draw (kernels of domains with N-D tally grids: +2 ... +4 %;
+// the 1-D kernels keep the separate paths: their 80-register budget spills with it, C2 slab -1.7 %).
+template <bool BOX, bool UNI>
 __device__ __forceinline__ uint32_t collide(const StepParams& P, const Tables& T, Particle& ph, Segment& sg) {
     uint32_t esc = 0;
     const int hit = sg.hit;
     sg.next_plane = hit;
-    if (hit >= 0) {                                                            // problem.cpp:418-429
+    if (UNI && (hit < 0 || T.cold[hit].kind == MCB_BDRY_DIFF)) {                // material.cpp:226-231 | boundary.cpp:308-312
+        scatter_draw<BOX>(P, T, ph, hit < 0, hit >= 0 ? &T.cold[hit] : nullptr);
+    } else if (hit >= 0) {                                                     // problem.cpp:418-429
         const DPlaneCold& cb = T.cold[hit];
         const int kind = cb.kind;
         if (kind == MCB_BDRY_SPEC) {                                           // boundary.cpp:283-287
@@ -511,6 +592,9 @@ __device__ __forceinline__ void flush_tally1d(unsigned char* hist, unsigned nins
 // PAD  : NDM == 0 with TM == MCB_TM_WARP uses the 1-D difference-array histograms (mcb_device.cuh: tally_1d); PAD > 0 is
 //        the compile-time padded column count of a histogram plane (cols <= PAD), 0 = run-time plane stride
 // Dynamic shared memory: [mbarrier 16 B][material blob][geometry blob][histogram(s)]
+#ifndef MCB_L2_PREFETCH
+#define MCB_L2_PREFETCH 1
+#endif
 #ifndef MCB_BLOCK_MAX
 #define MCB_BLOCK_MAX 768         // 1-D / single-cell tallies: 80 registers x 24 warps (round 2, with the TMA state prefetch: 896 x 72 -11 %, 640 x 96 -1 %)
 #endif
@@ -520,8 +604,11 @@ __device__ __forceinline__ void flush_tally1d(unsigned char* hist, unsigned nins
 #ifndef MCB_BLOCK_MAX_ND
 #define MCB_BLOCK_MAX_ND 512      // the cooperative N-D walk keeps two crossing iterators live: give it 128 registers
 #endif
+#ifndef MCB_BLOCK_MAX_ND3
+#define MCB_BLOCK_MAX_ND3 512     // warp-balanced N-D tally (mcb_device.cuh: tally_nd_balanced): ~5 KB of shared memory per warp
+#endif
 template <int NCOMP, int TM, int NDM, bool BOX, int PAD>
-__global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : (NDM == 1 ? MCB_BLOCK_MAX_ND1 : MCB_BLOCK_MAX), 1) k_step(const StepParams P) {
+__global__ void __launch_bounds__(NDM == 3 ? MCB_BLOCK_MAX_ND3 : (NDM == 2 ? MCB_BLOCK_MAX_ND : (NDM == 1 ? MCB_BLOCK_MAX_ND1 : MCB_BLOCK_MAX)), 1) k_step(const StepParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
     unsigned char* s_mat = smem + P.so_mat;
@@ -578,8 +665,48 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : (NDM == 1 ? MCB_
     // inside this kernel runs the long emission path for a few dead lanes per warp at ~5 % lane efficiency).  Every WARP
     // appends to its own segment of the list (cursor = the warp's counter slot; a global cursor made every warp wait for
     // a returning L2 atomic once per tile) and the CTA publishes the counts at the end.
-    const bool list_free = P.free_list != nullptr && P.ctr->next < P.n_end;
     uint32_t* const my_free = P.free_list + (size_t)(blockIdx.x * nwarps + warp) * P.free_seg;
+    const unsigned long long next0 = P.ctr->next[P.parity];
+    unsigned long long emit_now = 0;                            // particles this launch emits (all CTAs compute the same value)
+    // K1 fused into the launch (steady phase): the slots a warp listed as free in the previous launch are the slots it
+    // visits again now (same grid, same slot count), so the warp refills them itself before its first tile -- particle
+    // next + (free slots listed by the warps before it) + j into its j-th free slot, problem.cpp:386-399, 32 at a time --
+    // and the two emission launches per loop trip (k_emit, k_emit_commit: ~25-45 us of every iteration) disappear.  Every
+    // CTA sums the previous launch's per-warp counts itself (a few thousand words from L2).
+    if (P.emit_fused && P.free_list != nullptr && next0 < P.n_end) {
+        __shared__ unsigned s_red[64];
+        const uint32_t* cnt = P.free_cnt + (size_t)P.parity * MCB_MAX_SEG;
+        const int nseg = (int)(gridDim.x * nwarps), first = (int)(blockIdx.x * nwarps);
+        unsigned before = 0, all = 0;
+        for (int b = (int)threadIdx.x; b < nseg; b += (int)blockDim.x) { const unsigned v = cnt[b]; all += v; if (b < first) before += v; }
+        before = __reduce_add_sync(0xFFFFFFFFu, before); all = __reduce_add_sync(0xFFFFFFFFu, all);
+        if (lane == 0) { s_red[warp] = before; s_red[32 + warp] = all; }
+        __syncthreads();
+        before = 0; all = 0;
+        for (unsigned w = 0; w < nwarps; ++w) { before += s_red[w]; all += s_red[32 + w]; }
+        const unsigned mine = lane < nwarps ? cnt[first + (int)lane] : 0u;       // this CTA's warps
+        unsigned incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((int)lane >= o) incl += v; }
+        const unsigned n_w = __shfl_sync(0xFFFFFFFFu, mine, (int)warp), base = before + __shfl_sync(0xFFFFFFFFu, incl - mine, (int)warp);
+        const unsigned long long room = P.n_end - next0;
+        emit_now = (unsigned long long)all < room ? (unsigned long long)all : room;
+#pragma unroll 1
+        for (unsigned j = lane; j < n_w; j += 32u) {
+            if ((unsigned long long)(base + j) < room) {
+                Particle np_;
+                emit_particle(P, T, next0 + base + j, np_);
+                np_.store(P.st, (long long)my_free[j]);
+            }
+        }
+        __syncwarp();
+        asm volatile("fence.proxy.async;" ::: "memory");       // the refilled slots are read back through the TMA prefetch
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        P.ctr->next[P.parity ^ 1] = next0 + emit_now; P.ctr->live[P.parity ^ 1] = 0ull;
+        if (emit_now) atomicAdd(&P.ctr->emitted, emit_now);
+    }
+    const bool list_free = P.free_list != nullptr && next0 + emit_now < P.n_end;
 
     // TMA state prefetch: a warp's 32 slots are one contiguous 2304-B group (StateView), bulk-copied into the warp's staging
     // buffer while the warp works on the group before it.  The buffer is free again as soon as the lanes have moved their
@@ -599,6 +726,9 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : (NDM == 1 ? MCB_
             tma_bulk_g2s_a(a_buf, P.st.base + (size_t)g0 * MCB_GROUP_BYTES, MCB_GROUP_BYTES, a_bar);
         }
     }
+    // warp-balanced N-D tally: this warp's record area; its mark words start at zero and are re-armed after every trip
+    const uint32_t nd_base = NDM == 3 ? smem_u32(smem) + P.so_nd + warp * P.nd_warp_bytes : 0u;
+    if (NDM == 3) for (uint32_t i = lane; i < (P.nd_warp_bytes - MCB_NDB_FIXED) / 4u; i += 32u) sts_s32(nd_base + MCB_NDB_FIXED + 4u * i, 0);
     __syncthreads();                                            // the counter slots are armed
 
     // tile = one group of 32 slots per warp: group g = (blockIdx + k gridDim) nwarps + warp; the trip count is CTA-uniform
@@ -630,6 +760,11 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : (NDM == 1 ? MCB_
         const bool was_active = ph.active();
         unsigned tile_steps = 0;
         unsigned run_mask = __ballot_sync(0xFFFFFFFFu, was_active);
+#if MCB_L2_PREFETCH
+        // no room for the staging buffers (N-D kernels: the record areas take it): at least pull the warp's next group into L2
+        if (!staged && lane == 0 && g + gstride < ngroups)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.st.base + (size_t)(g + gstride) * MCB_GROUP_BYTES), "r"(MCB_GROUP_BYTES) : "memory");
+#endif
         if (staged && lane == 0 && g + gstride < ngroups) {
             // Refill the staging buffer with the warp's next group.  The ballot above consumed every lane's last-loaded
             // word, so all the lanes' shared-memory reads of the buffer have completed (loads of a warp complete in order);
@@ -687,18 +822,31 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : (NDM == 1 ? MCB_
                     else if (NCOMP == 4) { amt[0] = sg_ * (sg.d * T.inv_vel[ph.wp()]); amt[1 % NCOMP] = sg_ * (sg.ex - sg.bx); amt[2 % NCOMP] = sg_ * (sg.ey - sg.by); amt[3 % NCOMP] = sg_ * (sg.ez - sg.bz); }
                     else { amt[0] = sg_ * (sg.ex - sg.bx); amt[1 % NCOMP] = sg_ * (sg.ey - sg.by); amt[2 % NCOMP] = sg_ * (sg.ez - sg.bz); }
                     FxArgs fx{P.fx_cstride, false, &P};
+                    double raw[NDM == 3 ? NCOMP : 1];
                     if (FX) {
                         // fixed-point histograms: scale by the launch's power of two (exact); a payload beyond the chosen range
                         // (rare: a long flight of a very slow mode) is deposited exactly through the global fp64 path instead
                         bool fits = true;
 #pragma unroll
-                        for (int k = 0; k < NCOMP; ++k) { fits = fits && fabs(amt[k]) <= P.fx_max[k]; amt[k] *= P.fx_scale[k]; }
+                        for (int k = 0; k < NCOMP; ++k) { fits = fits && fabs(amt[k]) <= P.fx_max[k]; if (NDM == 3) raw[k] = amt[k]; amt[k] *= P.fx_scale[k]; }
                         fx.slow = !fits;
                     }
+                    if (NDM == 3) {
+                        // N-D grids: one work item per crossed cell, dealt out over the warp; the 1-D and single-cell grids of
+                        // a mixed domain keep the serial iterator
+                        const bool nd_seg = sg.ok && sd.accum >= 3, flat_seg = sg.ok && sd.accum < 3;
+                        if (__any_sync(0xFFFFFFFFu, flat_seg))
+                            tally_segments<NCOMP, TM, false, true, false>(sd, T.hist, P.rows, P.cols, rbase, flat_seg, sg.bx, sg.by, sg.bz, sg.ex, sg.ey, sg.ez, amt, lane, fx);
+                        if (FX && fx.slow) {
+#pragma unroll
+                            for (int k = 0; k < NCOMP; ++k) amt[k] = raw[k];
+                        }
+                        tally_nd_balanced<NCOMP, TM, BOX>(nd_base, sd, T.hist, P.rows, P.cols, rbase, nd_seg, FX && fx.slow, sg.bx, sg.by, sg.bz, sg.ex, sg.ey, sg.ez, amt, lane, fx);
+                    } else
                     tally_segments<NCOMP, TM, (NDM > 0), true, (NDM == 2)>(sd, T.hist, P.rows, P.cols, rbase, sg.ok, sg.bx, sg.by, sg.bz, sg.ex, sg.ey, sg.ez, amt, lane, fx);
                 }
             }
-            if (sg.ok) escaped = collide<BOX>(P, T, ph, sg) != 0u;
+            if (sg.ok) escaped = collide<BOX, (NDM > 0)>(P, T, ph, sg) != 0u;
             if (escaped) red_shared_u32(&s_esc, 1u);                           // rare: Progress::incrEsc problem.cpp:111-118
             run_mask = __ballot_sync(0xFFFFFFFFu, ph.active());
         }
@@ -718,13 +866,13 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : (NDM == 1 ? MCB_
 
     // --- the CTA's counters: one global atomic each; the warps' free-list counts
     __syncthreads();
-    if (threadIdx.x < nwarps && P.free_cnt) P.free_cnt[blockIdx.x * nwarps + threadIdx.x] = list_free ? s_wcnt[threadIdx.x].w : 0u;
+    if (threadIdx.x < nwarps && P.free_cnt) P.free_cnt[(size_t)(P.parity ^ 1) * MCB_MAX_SEG + blockIdx.x * nwarps + threadIdx.x] = list_free ? s_wcnt[threadIdx.x].w : 0u;
     if (threadIdx.x == 0) {
         unsigned long long st = 0, lv = 0, so = 0;
         for (unsigned w = 0; w < nwarps; ++w) { st += s_wcnt[w].x; lv += s_wcnt[w].y; so += s_wcnt[w].z; }
         if (st) atomicAdd(&P.ctr->steps, st);
         if (s_esc) atomicAdd(&P.ctr->esc, (unsigned long long)s_esc);
-        if (lv) atomicAdd(&P.ctr->live, lv);
+        if (lv) atomicAdd(&P.ctr->live[P.parity], lv);
         if (so) atomicAdd(&P.ctr->stores, so);
     }
     // --- flush the shared-memory histogram(s): sum the copies, transpose row-major -> the field's column-major layout,
@@ -741,16 +889,15 @@ __global__ void __launch_bounds__(NDM == 2 ? MCB_BLOCK_MAX_ND : (NDM == 1 ? MCB_
 // listed per k_step CTA (segment b of free_list holds free_cnt[b] entries); j is mapped to (segment, entry) through the
 // prefix sums of the counts, which every CTA of this kernel recomputes in shared memory (<= a few hundred entries).
 // nseg == 0: the first fill, every slot 0 .. nslots-1 is free.
-#define MCB_MAX_SEG 8192          /* k_step warps: 148 CTAs x <= 32 warps (x ctas_per_sm) */
 __device__ __forceinline__ unsigned long long emit_quota(const StepParams& P, unsigned long long nfree) {
-    const unsigned long long next = P.ctr->next, room = P.n_end > next ? P.n_end - next : 0ull;
+    const unsigned long long next = P.ctr->next[P.parity], room = P.n_end > next ? P.n_end - next : 0ull;
     return nfree < room ? nfree : room;
 }
 __global__ void __launch_bounds__(256) k_emit(const StepParams P, int nseg) {
     __shared__ unsigned s_pre[MCB_MAX_SEG + 1];
     unsigned long long nfree = (unsigned long long)P.nslots;
     if (nseg > 0) {
-        for (int b = (int)threadIdx.x; b < nseg; b += (int)blockDim.x) s_pre[b + 1] = P.free_cnt[b];      // coalesced, in flight together
+        for (int b = (int)threadIdx.x; b < nseg; b += (int)blockDim.x) s_pre[b + 1] = P.free_cnt[(size_t)P.parity * MCB_MAX_SEG + b];      // coalesced, in flight together
         __syncthreads();
         if (threadIdx.x < 32) {                                   // one warp: inclusive scan of the counts, 32 at a time
             unsigned carry = 0;
@@ -767,7 +914,7 @@ __global__ void __launch_bounds__(256) k_emit(const StepParams P, int nseg) {
         __syncthreads();
         nfree = s_pre[nseg];
     }
-    const unsigned long long next = P.ctr->next, n = emit_quota(P, nfree);
+    const unsigned long long next = P.ctr->next[P.parity], n = emit_quota(P, nfree);
     Tables T;
     T.lambda = reinterpret_cast<const double*>(P.mat_blob + P.mv.off_lambda);
     T.nw = P.mv.nw; T.np = P.mv.np; T.inv_bucket_w = P.mv.inv_bucket_w; T.inv_bucket_p = P.mv.inv_bucket_p;
@@ -789,13 +936,13 @@ __global__ void __launch_bounds__(256) k_emit_commit(const StepParams P, int nse
     if (threadIdx.x == 0) s_sum = 0ull;
     __syncthreads();
     unsigned mine = 0;
-    for (int b = (int)threadIdx.x; b < nseg; b += (int)blockDim.x) { mine += P.free_cnt[b]; P.free_cnt[b] = 0u; }
+    for (int b = (int)threadIdx.x; b < nseg; b += (int)blockDim.x) { mine += P.free_cnt[(size_t)P.parity * MCB_MAX_SEG + b]; P.free_cnt[(size_t)P.parity * MCB_MAX_SEG + b] = 0u; }
     mine = __reduce_add_sync(0xFFFFFFFFu, mine);
     if ((threadIdx.x & 31u) == 0u && mine) atomicAdd(&s_sum, (unsigned long long)mine);
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned long long n = emit_quota(P, nseg > 0 ? s_sum : (unsigned long long)P.nslots);
-        P.ctr->next += n; P.ctr->emitted += n; P.ctr->live = 0ull;
+        P.ctr->next[P.parity] += n; P.ctr->emitted += n; P.ctr->live[P.parity] = 0ull;
     }
 }
 
@@ -860,7 +1007,7 @@ __global__ void k_traj(const StepParams P, const mcb_traj_desc t, const TrajDev 
         if (esc) { escaped = 1; break; }                                                                      // :267-271
         if (k < o.max_steps) { o.step_out[k] = sg.hit >= 0 ? sg.hit - sd.plane_begin : -1; o.step_out_kind[k] = sg.hit >= 0 ? T.cold[sg.hit].kind : -1; }
         const bool peri = sg.hit >= 0 && T.cold[sg.hit].kind == MCB_BDRY_PERI;
-        if (collide<false>(P, T, ph, sg)) { escaped = 2; break; }                                                    // :277-294
+        if (collide<false, false>(P, T, ph, sg)) { escaped = 2; break; }                                                    // :277-294
         if (peri) push(ph.px, ph.py, ph.pz);
         cur = sg.next_plane;
         if (!ph.active()) break;                                                                              // :295

@@ -18,6 +18,7 @@ static cudaError_t launch_step_box(const StepParams& P, int box, int grid, int b
 }
 template <int NCOMP, int TM>
 static cudaError_t launch_step_nd(const StepParams& P, int ndm, int box, int grid, int block, size_t smem, cudaStream_t s) {
+    if (ndm == 3) return launch_step_box<NCOMP, TM, 3>(P, box, grid, block, smem, s);
     if (ndm == 2) return launch_step_box<NCOMP, TM, 2>(P, box, grid, block, smem, s);
     if (ndm == 1) return launch_step_box<NCOMP, TM, 1>(P, box, grid, block, smem, s);
     return launch_step_box<NCOMP, TM, 0>(P, box, grid, block, smem, s);
@@ -34,7 +35,7 @@ static cudaError_t launch_step_n(const StepParams& P, int tm, int ndm, int box, 
         }
     }
     switch (tm) {
-    case MCB_TM_WARP: return launch_step_nd<NCOMP, MCB_TM_WARP>(P, ndm, box, grid, block, smem, s);
+    case MCB_TM_WARP: return launch_step_box<NCOMP, MCB_TM_WARP, 0>(P, box, grid, block, smem, s);     // 1-D histograms: no N-D grid (plan_run)
     case MCB_TM_BLOCK: return launch_step_nd<NCOMP, MCB_TM_BLOCK>(P, ndm, box, grid, block, smem, s);
     default: return launch_step_nd<NCOMP, MCB_TM_GLOBAL>(P, ndm, box, grid, block, smem, s);
     }
