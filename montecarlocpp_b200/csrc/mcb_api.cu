@@ -118,7 +118,8 @@ struct mcb_ctx {
     // problem / run state
     DevBuf<long long> emit_cdf;
     DevBuf<unsigned char> state[2]; long long slots_alloc = 0;          // warp-tiled slot state (mcb_device.cuh: StateView)
-    DevBuf<Counters> ctr; Counters* h_ctr = nullptr;     // pinned mirror
+    DevBuf<Counters> ctr; Counters* h_ctr = nullptr;     // pinned mirror (two slots), written by k_step itself through ...
+    Counters* d_hctr = nullptr;                          // ... its device address
     DevBuf<uint32_t> free_list, free_cnt;     // dense emission: per-CTA segments of free slot ids + their counts
     DevBuf<double> field;
 };
@@ -389,7 +390,7 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
         const int slot = (int)(it & 1);
         // fixed-point histograms are flushed between tiles: keep a tile's loop trips within the flush interval
         if (plan.tm != MCB_TM_GLOBAL) S_cur = std::min(S_cur, plan.trips);
-        P.st = view_of(c, cur); P.nslots = nslots; P.steps_per_launch = S_cur; P.parity = slot;
+        P.st = view_of(c, cur); P.nslots = nslots; P.steps_per_launch = S_cur; P.parity = slot; P.host_ctr = c->d_hctr + slot;
         const long long tiles = (nslots + plan.block - 1) / plan.block;
         const int grid = (int)std::min<long long>(plan.grid, std::max<long long>(tiles, 1));
         // K1: the first fill (every slot free) is its own dense kernel; afterwards every k_step warp refills, at the start of
@@ -408,12 +409,11 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
         CUDA_TRY(c, cudaEventRecord(c->evA[slot], c->stream));
         CUDA_TRY(c, launch_step(P, plan.tm, plan.ndm, c->all_box, plan.pad, grid, plan.block, plan.smem, c->stream));
         CUDA_TRY(c, cudaEventRecord(c->evB[slot], c->stream));
-        CUDA_TRY(c, cudaMemcpyAsync(&c->h_ctr[slot], c->ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(c, cudaEventRecord(c->evC[slot], c->stream));
+        // the launch's last CTA has mirrored the counters into h_ctr[slot] (StepParams::host_ctr): evB is all the host waits for
         launches++; step_launches++; slot_steps += nslots * (long long)std::min<long long>(S_cur, prob->maxloop);
         if (it == 0) continue;
         const int prev = slot ^ 1;
-        CUDA_TRY(c, cudaEventSynchronize(c->evC[prev]));
+        CUDA_TRY(c, cudaEventSynchronize(c->evB[prev]));
         float ms = 0.f; cudaEventElapsedTime(&ms, c->evA[prev], c->evB[prev]); step_ms_total += ms;
         const unsigned long long live = c->h_ctr[prev].live[prev], next = c->h_ctr[prev].next[prev ^ 1];     // launch it-1 had parity `prev`
         const bool all_emitted = next >= (unsigned long long)n_end;
@@ -424,7 +424,7 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
         }
         prev_steps = c->h_ctr[prev].steps; prev_stores = c->h_ctr[prev].stores;
         if (all_emitted && live == 0) {
-            CUDA_TRY(c, cudaEventSynchronize(c->evC[slot]));
+            CUDA_TRY(c, cudaEventSynchronize(c->evB[slot]));
             cudaEventElapsedTime(&ms, c->evA[slot], c->evB[slot]); step_ms_total += ms;
             break;
         }
@@ -505,7 +505,8 @@ int mcb_create(int device, mcb_ctx** out) {
         (e = cudaEventCreate(&c->evA[0])) != cudaSuccess || (e = cudaEventCreate(&c->evA[1])) != cudaSuccess ||
         (e = cudaEventCreate(&c->evB[0])) != cudaSuccess || (e = cudaEventCreate(&c->evB[1])) != cudaSuccess ||
         (e = cudaEventCreate(&c->evC[0])) != cudaSuccess || (e = cudaEventCreate(&c->evC[1])) != cudaSuccess ||
-        (e = c->ctr.alloc(1)) != cudaSuccess || (e = cudaMallocHost(&c->h_ctr, 2 * sizeof(Counters))) != cudaSuccess) {
+        (e = c->ctr.alloc(1)) != cudaSuccess || (e = cudaHostAlloc(&c->h_ctr, 2 * sizeof(Counters), cudaHostAllocMapped)) != cudaSuccess ||
+        (e = cudaHostGetDevicePointer(&c->d_hctr, c->h_ctr, 0)) != cudaSuccess) {
         g_create_err = cudaGetErrorString(e); delete c; return MCB_ECUDA;
     }
     *out = c;

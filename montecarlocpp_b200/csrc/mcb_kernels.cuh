@@ -874,6 +874,19 @@ __global__ void __launch_bounds__(NDM == 3 ? MCB_BLOCK_MAX_ND3 : (NDM == 2 ? MCB
         if (s_esc) atomicAdd(&P.ctr->esc, (unsigned long long)s_esc);
         if (lv) atomicAdd(&P.ctr->live[P.parity], lv);
         if (so) atomicAdd(&P.ctr->stores, so);
+        if (P.host_ctr) {
+            // the last CTA to get here mirrors the counters into pinned host memory: the host only waits for the event behind
+            // the launch -- no device-to-host copy sits between two k_step launches
+            __threadfence();
+            if (atomicAdd(&P.ctr->done, 1ull) == (unsigned long long)gridDim.x - 1ull) {
+                __threadfence();
+                const volatile unsigned long long* src = reinterpret_cast<const volatile unsigned long long*>(P.ctr);
+                volatile unsigned long long* dst = reinterpret_cast<volatile unsigned long long*>(P.host_ctr);
+                for (int k = 0; k < (int)(sizeof(Counters) / 8); ++k) dst[k] = src[k];
+                P.ctr->done = 0ull;
+                __threadfence_system();
+            }
+        }
     }
     // --- flush the shared-memory histogram(s): sum the copies, transpose row-major -> the field's column-major layout,
     //     one fp64 RED per non-zero entry
