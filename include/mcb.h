@@ -165,7 +165,9 @@ typedef struct mcb_problem_desc {
     int64_t step;              /* Cum*: step_  problem.cpp:562-563 (else 0)           */
     int64_t nemit;             /* nemit_ = emitPdf_.sum()  problem.cpp:337            */
     int64_t maxscat;           /* maxscat_                                            */
-    int64_t maxloop;           /* maxloop_ (already defaulted, problem.cpp:339)       */
+    int64_t maxloop;           /* maxloop_ (already defaulted, problem.cpp:339); limits of this library: maxloop < 2^32 - 1 (the
+                                * loop trip is the 32-bit Philox event counter), maxscat < 2^31, nemit < 2^36 (< 2^32 once
+                                * maxloop >= 2^31): the slot state packs pid | loop trip into one 64-bit word            */
     double  power;             /* power_   problem.cpp:341                            */
     const int64_t* emit_count; /* emitPdf_ [nemitter]  problem.cpp:329-335            */
 } mcb_problem_desc;
@@ -257,7 +259,11 @@ int  mcb_solve_raw_dev(mcb_ctx* ctx, const mcb_problem_desc* prob, uint64_t seed
 /* problem.cpp:439-444 on a raw device tally (in place): postProc, /cellVol, *power_. */
 int  mcb_finalize_dev(mcb_ctx* ctx, const mcb_problem_desc* prob, double* field_dev);
 
-/* The stream the library launches on (a cudaStream_t), for event timing by callers. */
+/* The stream the library launches on (a cudaStream_t, created cudaStreamNonBlocking).  STREAM CONTRACT: mcb_solve,
+ * mcb_solve_raw_dev and mcb_solve_raw return after synchronising this stream, so the raw tally is complete when they return;
+ * mcb_finalize_dev launches k_finalize on this stream and synchronises it.  Work a caller puts on ANOTHER stream between the
+ * two (e.g. an NCCL all-reduce of the raw tally) is NOT ordered before k_finalize: issue it on this stream, or synchronise /
+ * cudaStreamWaitEvent it before calling mcb_finalize_dev (bench.py and mcb_allreduce use the library's own stream). */
 int  mcb_stream(const mcb_ctx* ctx, void** stream);
 
 /* ---- several GPUs in one process (C++ callers; replaces the thread fan-out + `omp critical` sum of main.cpp:155-166).

@@ -120,13 +120,20 @@ struct mcb_ctx {
     DevBuf<unsigned char> state[2]; long long slots_alloc = 0;          // warp-tiled slot state (mcb_device.cuh: StateView)
     DevBuf<Counters> ctr; Counters* h_ctr = nullptr;     // pinned mirror (two slots), written by k_step itself through ...
     Counters* d_hctr = nullptr;                          // ... its device address
-    DevBuf<uint32_t> free_list, free_cnt;     // dense emission: per-CTA segments of free slot ids + their counts
     DevBuf<double> field;
+    DevBuf<uint32_t> free_list;  // fused emission: per-warp segments of free slot ids
 };
 
 namespace {
 
 StateView view_of(mcb_ctx* c, int which) { return StateView{c->state[which].p}; }
+
+// bits of the pid|step word given to the loop trip count: 28 by default (nemit < 2^36), up to 32 for very long histories
+uint32_t step_bits_for(long long maxloop) {
+    uint32_t b = MCB_STEP_BITS_MIN;
+    while (b < MCB_STEP_BITS_MAX && (maxloop >> b) != 0) ++b;
+    return b;
+}
 
 int check_problem(mcb_ctx* c, const mcb_problem_desc* p) {
     if (!p) { c->err = "null problem"; return MCB_EINVAL; }
@@ -148,9 +155,14 @@ int check_problem(mcb_ctx* c, const mcb_problem_desc* p) {
     long long tot = 0;
     for (int i = 0; i < c->nemitter; ++i) { if (p->emit_count[i] < 0) { c->err = "negative emit_count"; return MCB_EINVAL; } tot += p->emit_count[i]; }
     if (tot != p->nemit) { c->err = "nemit != sum(emit_count)"; return MCB_EINVAL; }
-    if (p->maxloop < 0 || p->maxloop > MCB_MAX_LOOP) { c->err = "maxloop out of range (< 2^28)"; return MCB_EINVAL; }
+    if (p->maxloop < 0 || p->maxloop > MCB_MAX_LOOP) { c->err = "maxloop out of range (< 2^32 - 1: the loop trip is the 32-bit Philox event counter)"; return MCB_EINVAL; }
     if (p->maxscat < 0 || p->maxscat > 0x7FFFFFFFll) { c->err = "maxscat out of range"; return MCB_EINVAL; }
-    if ((unsigned long long)p->nemit > MCB_MAX_PID) { c->err = "nemit out of range (< 2^36)"; return MCB_EINVAL; }
+    if ((unsigned long long)p->nemit >> (64 - step_bits_for(p->maxloop))) { c->err = "nemit out of range (< 2^36; < 2^32 when maxloop >= 2^31)"; return MCB_EINVAL; }
+    if (p->kind == MCB_PROB_CUMTEMP || p->kind == MCB_PROB_CUMFLUX) {
+        // bin of a deposit = ceil(nscat_before / step) with nscat_before <= maxscat - 1 must be a row of the field (problem.cpp:562-563)
+        const long long top = p->maxscat > 0 ? (p->maxscat - 1 + p->step - 1) / p->step : 0;
+        if (top > p->size) { c->err = "Cum* problem: step too small for maxscat and size (bin index beyond the field rows)"; return MCB_EINVAL; }
+    }
     return MCB_OK;
 }
 
@@ -187,9 +199,6 @@ struct RunPlan {
 #endif
 #ifndef MCB_ND_BALANCED
 #define MCB_ND_BALANCED 1      // N-D tally grids: the warp-balanced item walk (k_step NDM 3) instead of the per-lane serial walk
-#endif
-#ifndef MCB_EMIT_FUSED
-#define MCB_EMIT_FUSED 1       // steady phase: k_step refills its own free slots (no k_emit / k_emit_commit launches between the steps)
 #endif
 #ifndef MCB_DECAY_S
 #define MCB_DECAY_S 16         // loop trips per launch once nothing is left to emit
@@ -283,6 +292,7 @@ void fill_params(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, StepPa
     P->kind = prob->kind; P->rows = prob->rows; P->cols = (int32_t)c->cols; P->cum_step = prob->step > 0 ? prob->step : 1;
     P->maxscat = prob->maxscat; P->maxloop = prob->maxloop; P->seed = seed;
     P->maxscat32 = (uint32_t)prob->maxscat; P->maxloop32 = (uint32_t)prob->maxloop;
+    P->step_bits = step_bits_for(prob->maxloop); P->step_mask = P->step_bits >= 32 ? 0xFFFFFFFFu : (1u << P->step_bits) - 1u;
     for (int r = 0; r < 10; ++r) { P->rk[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u; P->rk[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u; }
     P->ctr = c->ctr.p; P->field_len = (long long)prob->rows * c->cols;
     P->so_mat = 16; P->so_geo = 16 + c->mv.bytes; P->so_hist = 16 + c->mv.bytes + c->gv.bytes;
@@ -353,7 +363,7 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
     apply_plan(plan, prob, &P);
     set_fixed_point(c, prob, plan, &P);
 
-    Counters init{}; init.next[0] = init.next[1] = (unsigned long long)n_begin;
+    Counters init{}; init.next = (unsigned long long)n_begin;
     CUDA_TRY(c, cudaMemcpyAsync(c->ctr.p, &init, sizeof init, cudaMemcpyHostToDevice, c->stream));
     int cur = 0; long long nslots = plan.slots;
     CUDA_TRY(c, cudaMemsetAsync(c->state[cur].p, 0, state_bytes(nslots), c->stream));        // every slot inactive
@@ -367,23 +377,15 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
     // previous launch; after the last particle dies one extra, empty launch has already been queued.
     const long long tail_slots = (long long)plan.grid * plan.block;      // one tile per CTA: finish in one launch
     int S_cur = plan.S;
-    // dense emission: k_step only lists free slots, k_emit fills them between launches
-    const bool dense = true;
-    const long long compact_pct = c->opt.compact_pct > 0 ? c->opt.compact_pct : MCB_COMPACT_PCT;
     bool host_all_emitted = false;
-    int nseg = 0;                        // free-list segments filled by the previous k_step (0: the first fill, every slot free)
-    if (dense) {
-        // one segment per k_step CTA, long enough for every slot the CTA visits
+    {   // fused emission: one free-slot segment per k_step warp, long enough for every slot the warp visits
         const long long tiles0 = (nslots + plan.block - 1) / plan.block;
         const long long grid0 = std::min<long long>(plan.grid, std::max<long long>(tiles0, 1));
-        const long long nwarps0 = plan.block / 32;
-        if (grid0 * nwarps0 > MCB_MAX_SEG) { c->err = "persistent grid too large for the free-list segments"; return MCB_ELIMIT; }
-        P.free_seg = (uint32_t)(((tiles0 + grid0 - 1) / grid0) * 32);       // one segment per k_step WARP: 32 slots per tile
-        CUDA_TRY(c, c->free_list.alloc((size_t)(grid0 * nwarps0) * P.free_seg));
-        CUDA_TRY(c, c->free_cnt.alloc(2 * MCB_MAX_SEG));                    // double-buffered by launch parity
-        CUDA_TRY(c, cudaMemsetAsync(c->free_cnt.p, 0, 2 * MCB_MAX_SEG * sizeof(uint32_t), c->stream));
-        P.free_list = c->free_list.p; P.free_cnt = c->free_cnt.p;
-    } else P.free_list = nullptr;
+        P.free_seg = (uint32_t)(((tiles0 + grid0 - 1) / grid0) * 32);
+        CUDA_TRY(c, c->free_list.alloc((size_t)(grid0 * (plan.block / 32)) * P.free_seg));
+        P.free_list = c->free_list.p;
+    }
+    const long long compact_pct = c->opt.compact_pct > 0 ? c->opt.compact_pct : MCB_COMPACT_PCT;
     long long steady_launches = 0; float steady_ms = 0.f;
     unsigned long long steady_steps = 0, steady_stores = 0, prev_steps = 0, prev_stores = 0;
     if (total > 0) for (long long it = 0;; ++it) {
@@ -393,19 +395,15 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
         P.st = view_of(c, cur); P.nslots = nslots; P.steps_per_launch = S_cur; P.parity = slot; P.host_ctr = c->d_hctr + slot;
         const long long tiles = (nslots + plan.block - 1) / plan.block;
         const int grid = (int)std::min<long long>(plan.grid, std::max<long long>(tiles, 1));
-        // K1: the first fill (every slot free) is its own dense kernel; afterwards every k_step warp refills, at the start of
-        // the launch, the slots it listed as free in the launch before (same grid, same slots: nothing is compacted while
-        // particles are left to emit).  MCB_EMIT_FUSED=0 keeps the two emission kernels between the k_step launches.
-        P.emit_fused = 0;
-        if (dense && !host_all_emitted) {
-            if (it == 0 || !MCB_EMIT_FUSED || grid * (plan.block / 32) != nseg) {
-                k_emit<<<(unsigned)(c->sm_count * 4), 256, 0, c->stream>>>(P, nseg);
-                k_emit_commit<<<1, 256, 0, c->stream>>>(P, nseg);
-                CUDA_TRY(c, cudaGetLastError());
-                launches += 2;
-            } else P.emit_fused = 1;
+        // K1: the first fill (every slot free) is its own dense kernel; afterwards k_step refills the slots that end inactive
+        // itself (32 at a time, ids from the atomic cursor Counters::next) while particles are left to emit
+        P.emit_enable = host_all_emitted ? 0 : 1;
+        if (it == 0) {
+            k_emit<<<(unsigned)(c->sm_count * 8), 256, 0, c->stream>>>(P);
+            k_emit_commit<<<1, 32, 0, c->stream>>>(P);
+            CUDA_TRY(c, cudaGetLastError());
+            launches += 2;
         }
-        nseg = grid * (plan.block / 32);
         CUDA_TRY(c, cudaEventRecord(c->evA[slot], c->stream));
         CUDA_TRY(c, launch_step(P, plan.tm, plan.ndm, c->all_box, plan.pad, grid, plan.block, plan.smem, c->stream));
         CUDA_TRY(c, cudaEventRecord(c->evB[slot], c->stream));
@@ -415,7 +413,7 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
         const int prev = slot ^ 1;
         CUDA_TRY(c, cudaEventSynchronize(c->evB[prev]));
         float ms = 0.f; cudaEventElapsedTime(&ms, c->evA[prev], c->evB[prev]); step_ms_total += ms;
-        const unsigned long long live = c->h_ctr[prev].live[prev], next = c->h_ctr[prev].next[prev ^ 1];     // launch it-1 had parity `prev`
+        const unsigned long long live = c->h_ctr[prev].live[prev], next = c->h_ctr[prev].next;     // launch it-1 had parity `prev`
         const bool all_emitted = next >= (unsigned long long)n_end;
         host_all_emitted = all_emitted;
         if (!all_emitted) {          // launch it-1 ran with a full population: steady-phase accounting
@@ -520,7 +518,7 @@ void mcb_destroy(mcb_ctx* c) {
     c->mat_blob.release(); c->f_wprob.release(); c->f_pprob.release(); c->f_walias.release(); c->f_palias.release();
     c->geo_blob.release(); c->emitters.release(); c->cell_vol.release(); c->emit_cdf.release();
     for (int w = 0; w < 2; ++w) c->state[w].release();
-    c->ctr.release(); c->field.release(); c->free_list.release(); c->free_cnt.release();
+    c->ctr.release(); c->field.release(); c->free_list.release();
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
     if (c->ev0) cudaEventDestroy(c->ev0); if (c->ev1) cudaEventDestroy(c->ev1);
     for (int k = 0; k < 2; ++k) { if (c->evA[k]) cudaEventDestroy(c->evA[k]); if (c->evB[k]) cudaEventDestroy(c->evB[k]); if (c->evC[k]) cudaEventDestroy(c->evC[k]); }
@@ -685,6 +683,7 @@ int mcb_upload_domain(mcb_ctx* c, const mcb_domain_desc* d) {
         if (S.accum >= 3) any_nd = std::max(any_nd, (S.shape[0] >= MCB_COOP_ND_CELLS || S.shape[1] >= MCB_COOP_ND_CELLS || S.shape[2] >= MCB_COOP_ND_CELLS) ? 2 : 1);
         const long long sp = S.shape[0] * S.shape[1] * S.shape[2];
         if (S.accum < -2 || S.accum > 4 || sp < 0) { c->err = "bad accum flag / shape"; return MCB_EINVAL; }
+        if (sp == 0 && S.accum != -2) { c->err = "subdomain without cells (shape 0) must have accum flag -2"; return MCB_EINVAL; }
         if (sp == 0) D.col_offset = -1;                                                                    // field.cpp:34
         else {
             D.col_offset = (int32_t)cols; cols += sp;
@@ -939,19 +938,19 @@ int mcb_trace(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
     P.maxloop = std::min<long long>(prob->maxloop, nsteps); P.maxloop32 = (uint32_t)P.maxloop;
     P.field = nullptr; P.do_tally = 0;
     P.steps_per_launch = (int)std::max<long long>(1, std::min<long long>(P.maxloop, 0x7FFFFFFF)); P.n_end = (unsigned long long)n_end;
-    P.st = view_of(c, 0); P.nslots = n; P.free_list = nullptr; P.free_cnt = nullptr;
-    Counters init{}; init.next[0] = init.next[1] = (unsigned long long)n_begin;
+    P.st = view_of(c, 0); P.nslots = n; P.emit_enable = 0;
+    Counters init{}; init.next = (unsigned long long)n_begin;
     CUDA_TRY(c, cudaMemcpyAsync(c->ctr.p, &init, sizeof init, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaMemsetAsync(c->state[0].p, 0, state_bytes(c->slots_alloc), c->stream));
-    k_emit<<<(unsigned)(c->sm_count * 8), 256, 0, c->stream>>>(P, 0);     // first fill: particle n_begin + j into slot j
-    k_emit_commit<<<1, 256, 0, c->stream>>>(P, 0);
+    k_emit<<<(unsigned)(c->sm_count * 8), 256, 0, c->stream>>>(P);     // first fill: particle n_begin + j into slot j
+    k_emit_commit<<<1, 32, 0, c->stream>>>(P);
     CUDA_TRY(c, cudaGetLastError());
     if (P.maxloop > 0) CUDA_TRY(c, launch_step(P, plan.tm, plan.ndm, c->all_box, plan.pad, plan.grid, plan.block, plan.smem, c->stream));
     DevBuf<double> dpos, ddir, dsn; DevBuf<long long> dw, dp, dnscat, dsteps; DevBuf<int32_t> dsign, dalive, dsdom, dcell;
     CUDA_TRY(c, dpos.alloc(3 * n)); CUDA_TRY(c, ddir.alloc(3 * n)); CUDA_TRY(c, dsn.alloc(n));
     CUDA_TRY(c, dw.alloc(n)); CUDA_TRY(c, dp.alloc(n)); CUDA_TRY(c, dnscat.alloc(n)); CUDA_TRY(c, dsteps.alloc(n));
     CUDA_TRY(c, dsign.alloc(n)); CUDA_TRY(c, dalive.alloc(n)); CUDA_TRY(c, dsdom.alloc(n)); CUDA_TRY(c, dcell.alloc(3 * n));
-    k_gather_trace<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(P.st, n, (unsigned long long)n_begin, n, (int)c->np,
+    k_gather_trace<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(P.st, n, (unsigned long long)n_begin, n, (int)c->np, P.step_bits,
         c->geo_blob.p, c->gv, dpos.p, ddir.p, dsn.p, dw.p, dp.p, dsign.p, dalive.p, dsdom.p, dnscat.p, dsteps.p, dcell.p);
     CUDA_TRY(c, cudaGetLastError());
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -979,6 +978,7 @@ int mcb_traj(mcb_ctx* c, const mcb_traj_desc* t, uint64_t seed, mcb_traj_out* o)
     P.mat_blob = c->mat_blob.p; P.mv = c->mv; P.geo_blob = c->geo_blob.p; P.gv = c->gv;
     P.emitters = c->emitters.p; P.nemitter = c->nemitter; P.seed = seed; P.maxscat = t->maxscat; P.maxloop = t->maxloop;
     P.maxscat32 = (uint32_t)std::min<long long>(t->maxscat, 0x7FFFFFFFll); P.maxloop32 = (uint32_t)t->maxloop;
+    P.step_bits = step_bits_for(t->maxloop); P.step_mask = P.step_bits >= 32 ? 0xFFFFFFFFu : (1u << P.step_bits) - 1u;
     for (int r = 0; r < 10; ++r) { P.rk[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u; P.rk[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u; }
     DevBuf<double> dpts; DevBuf<int32_t> ds[5]; DevBuf<long long> dcnt;
     CUDA_TRY(c, dpts.alloc((size_t)o->max_points * 3)); CUDA_TRY(c, dcnt.alloc(3));

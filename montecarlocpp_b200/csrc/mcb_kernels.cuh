@@ -97,16 +97,17 @@ struct Particle {
     __device__ __forceinline__ bool active() const { return (mlo >> 21) & 1u; }
     __device__ __forceinline__ bool killed() const { return (mlo >> 22) & 1u; }
     __device__ __forceinline__ uint32_t sdom() const { return mlo >> 23; }
-    __device__ __forceinline__ uint32_t step() const { return (uint32_t)ps & ((1u << MCB_STEP_BITS) - 1u); }
-    __device__ __forceinline__ unsigned long long pid() const { return ps >> MCB_STEP_BITS; }
-    __device__ __forceinline__ uint32_t pid_lo() const { return (uint32_t)(ps >> MCB_STEP_BITS); }
-    __device__ __forceinline__ uint32_t pid_hi() const { return (uint32_t)(ps >> (32 + MCB_STEP_BITS)); }
+    // pid|step: the split is a per-solve constant (StepParams::step_bits / step_mask, constant-bank operands)
+    __device__ __forceinline__ uint32_t step(const StepParams& P) const { return (uint32_t)ps & P.step_mask; }
+    __device__ __forceinline__ unsigned long long pid(const StepParams& P) const { return ps >> P.step_bits; }
+    __device__ __forceinline__ uint32_t pid_lo(const StepParams& P) const { return (uint32_t)(ps >> P.step_bits); }
+    __device__ __forceinline__ uint32_t pid_hi(const StepParams& P) const { return (uint32_t)((ps >> P.step_bits) >> 32); }
     __device__ __forceinline__ void set_wp(uint32_t v) { mlo = (mlo & ~0xFFFFFu) | v; }
     __device__ __forceinline__ void set_sdom(uint32_t v) { mlo = (mlo & 0x7FFFFFu) | (v << 23); }
     __device__ __forceinline__ void stop() { mlo &= ~(1u << 21); }                       // alive but finished (or never started)
     __device__ __forceinline__ void kill() { mlo = (mlo | (1u << 22)) & ~(1u << 21); }  // Phonon::kill phonon.cpp:47-50
-    __device__ __forceinline__ void init(uint32_t wp_, bool sign_, bool active_, uint32_t sdom_, unsigned long long pid_) {
-        mlo = wp_ | ((uint32_t)sign_ << 20) | ((uint32_t)active_ << 21) | (sdom_ << 23); nscat = 0; ps = pid_ << MCB_STEP_BITS;
+    __device__ __forceinline__ void init(uint32_t wp_, bool sign_, bool active_, uint32_t sdom_, unsigned long long pid_, uint32_t step_bits) {
+        mlo = wp_ | ((uint32_t)sign_ << 20) | ((uint32_t)active_ << 21) | (sdom_ << 23); nscat = 0; ps = pid_ << step_bits;
     }
     __device__ __forceinline__ unsigned long long meta() const { return (unsigned long long)mlo | ((unsigned long long)nscat << 32); }
     // the slot's bytes: four 16-B vectors at v, v+512, v+1024, v+1536 and the 8-B pid|step word at w (StateView layout)
@@ -221,7 +222,7 @@ __device__ __forceinline__ void emit_from(const DEmitter& E, Rng& g, Particle& p
     }
     normalize3(dx, dy, dz);                                  // Phonon ctor phonon.cpp:33-37
     ph.px = px; ph.py = py; ph.pz = pz; ph.dx = dx; ph.dy = dy; ph.dz = dz;
-    ph.init(0u, sign != 0u, false, (uint32_t)E.sdom, 0ull);           // the caller sets wp, active and the particle id
+    ph.init(0u, sign != 0u, false, (uint32_t)E.sdom, 0ull, 0u);       // the caller sets wp, active and the particle id
 }
 
 // problem.cpp:386-399 for particle `pid`: pick emitter, drawFluxProp, Emitter::emit, drawScatNext.  Out of line (it is long and
@@ -230,7 +231,7 @@ __device__ __forceinline__ void emit_from(const DEmitter& E, Rng& g, Particle& p
 struct EmitArgs {
     const DEmitter* emitters; const long long* emit_cdf; const double* f_wprob; const double* f_pprob;
     const int32_t* f_walias; const int32_t* f_palias; const double* lambda;
-    unsigned long long seed; double inv_bucket_w, inv_bucket_p; int32_t nemitter, nw, np, active;
+    unsigned long long seed; double inv_bucket_w, inv_bucket_p; int32_t nemitter, nw, np, active; uint32_t step_bits;
 };
 static __device__ __noinline__ void emit_particle_impl(const EmitArgs a, unsigned long long pid, Particle& ph) {
     // emitter = upper_bound(emitCdf, n)  (problem.cpp:386-387)
@@ -241,14 +242,14 @@ static __device__ __noinline__ void emit_particle_impl(const EmitArgs a, unsigne
     Tables T; T.nw = a.nw; T.np = a.np; T.inv_bucket_w = a.inv_bucket_w; T.inv_bucket_p = a.inv_bucket_p;
     const uint32_t wp = draw_prop(g, T, a.f_wprob, a.f_walias, a.f_pprob, a.f_palias);
     emit_from(E, g, ph);
-    ph.init(wp, ph.sign(), a.active != 0, ph.sdom(), pid);
+    ph.init(wp, ph.sign(), a.active != 0, ph.sdom(), pid, a.step_bits);
     ph.sn = draw_scat_next(g, a.lambda[wp]);
 }
 __device__ __forceinline__ void emit_particle(const StepParams& P, const Tables& T, unsigned long long pid, Particle& ph) {
     EmitArgs a;
     a.emitters = P.emitters; a.emit_cdf = P.emit_cdf; a.f_wprob = P.f_wprob; a.f_pprob = P.f_pprob; a.f_walias = P.f_walias; a.f_palias = P.f_palias;
     a.lambda = T.lambda; a.seed = P.seed; a.inv_bucket_w = T.inv_bucket_w; a.inv_bucket_p = T.inv_bucket_p;
-    a.nemitter = P.nemitter; a.nw = T.nw; a.np = T.np; a.active = P.maxloop > 0 ? 1 : 0;
+    a.nemitter = P.nemitter; a.nw = T.nw; a.np = T.np; a.active = P.maxloop > 0 ? 1 : 0; a.step_bits = P.step_bits;
     emit_particle_impl(a, pid, ph);
 }
 
@@ -373,7 +374,7 @@ __device__ __forceinline__ uint32_t advect_move(const Tables& T, Particle& ph, S
 template <bool BOX>
 __device__ __forceinline__ void scatter_draw(const StepParams& P, const Tables& T, Particle& ph, bool intr, const DPlaneCold* cb) {
     uint32_t a[4];
-    philox4x32_10_rk(ph.pid_lo(), ph.pid_hi(), ph.step(), 0u, P.rk, a);
+    philox4x32_10_rk(ph.pid_lo(P), ph.pid_hi(P), ph.step(P), 0u, P.rk, a);
     uint32_t w1 = a[0], w2 = a[1];                 // the two words of the direction draw
     bool ok = true;
     uint32_t wp = 0; double dist = 0.0;
@@ -381,7 +382,7 @@ __device__ __forceinline__ void scatter_draw(const StepParams& P, const Tables& 
         ok = T.nw > 1 && T.np > 1;
         if (ok) {
             uint32_t b[4];
-            philox4x32_10_rk(ph.pid_lo(), ph.pid_hi(), ph.step(), 1u, P.rk, b);
+            philox4x32_10_rk(ph.pid_lo(P), ph.pid_hi(P), ph.step(P), 1u, P.rk, b);
             uint32_t r = (uint32_t)(((double)a[0] + 0.5) * T.inv_bucket_w);
             uint32_t q = (uint32_t)(((double)a[2] + 0.5) * T.inv_bucket_p);
             ok = r < (uint32_t)T.nw && q < (uint32_t)T.np;
@@ -412,7 +413,7 @@ __device__ __forceinline__ void scatter_draw(const StepParams& P, const Tables& 
             renorm_unit(ph.dx, ph.dy, ph.dz);
         }
     } else {                                                           // intrinsic, replayed word by word
-        Rng g; g.begin(P.seed, ph.pid(), ph.step());
+        Rng g; g.begin(P.seed, ph.pid(P), ph.step(P));
         ph.set_wp(draw_prop(g, T, T.wprob, T.walias, T.pprob, T.palias));
         draw_iso(g, ph.dx, ph.dy, ph.dz);
         ph.sn = draw_scat_next(g, T.lambda[ph.wp()]);
@@ -469,7 +470,7 @@ __device__ __forceinline__ uint32_t collide(const StepParams& P, const Tables& T
             ph.dx -= c2 * h.nx; ph.dy -= c2 * h.ny; ph.dz -= c2 * h.nz;
             renorm_unit(ph.dx, ph.dy, ph.dz);
         } else if (kind == MCB_BDRY_DIFF) {                                    // boundary.cpp:308-312
-            Rng g; g.begin(P.seed, ph.pid(), ph.step());
+            Rng g; g.begin(P.seed, ph.pid(P), ph.step(P));
             double ax, ay, az; draw_aniso(g, false, ax, ay, az);
             matvec(cb.m, ax, ay, az, ph.dx, ph.dy, ph.dz);
             renorm_unit(ph.dx, ph.dy, ph.dz);
@@ -498,12 +499,12 @@ __device__ __forceinline__ uint32_t collide(const StepParams& P, const Tables& T
     } else {                                                                   // Material::scatter material.cpp:226-231
         bool fast = false;
         if (T.nw > 1 && T.np > 1) {
-            Draw d2; draw_event(P, T, ph.pid_lo(), ph.pid_hi(), ph.step(), d2);
+            Draw d2; draw_event(P, T, ph.pid_lo(P), ph.pid_hi(P), ph.step(P), d2);
             fast = d2.ok;
             if (fast) { ph.set_wp(d2.wp); ph.dx = d2.dx; ph.dy = d2.dy; ph.dz = d2.dz; ph.sn = d2.dist; }
         }
         if (!fast) {
-            Rng g; g.begin(P.seed, ph.pid(), ph.step());
+            Rng g; g.begin(P.seed, ph.pid(P), ph.step(P));
             ph.set_wp(draw_prop(g, T, T.wprob, T.walias, T.pprob, T.palias));
             draw_iso(g, ph.dx, ph.dy, ph.dz);
             ph.sn = draw_scat_next(g, T.lambda[ph.wp()]);
@@ -511,7 +512,7 @@ __device__ __forceinline__ uint32_t collide(const StepParams& P, const Tables& T
         }
         ph.nscat++;
     }
-    if (ph.nscat >= P.maxscat32 || ph.step() >= P.maxloop32) ph.stop();                       // :434, :401
+    if (ph.nscat >= P.maxscat32 || ph.step(P) >= P.maxloop32) ph.stop();                       // :434, :401
     return esc;
 }
 
@@ -665,48 +666,16 @@ __global__ void __launch_bounds__(NDM == 3 ? MCB_BLOCK_MAX_ND3 : (NDM == 2 ? MCB
     // inside this kernel runs the long emission path for a few dead lanes per warp at ~5 % lane efficiency).  Every WARP
     // appends to its own segment of the list (cursor = the warp's counter slot; a global cursor made every warp wait for
     // a returning L2 atomic once per tile) and the CTA publishes the counts at the end.
+    // K1 fused into the launch: a warp lists the slots that end inactive (its own segment of free_list) and, after its last
+    // tile, emits the next particles into them with dense lanes (problem.cpp:386-399).  Particle ids come from one atomic
+    // cursor (any slot may carry any particle: the Philox stream is keyed by the id), so no emission kernels run between the
+    // k_step launches (two launches and 25-45 us of every loop trip in round 1).  The emission call sits behind the tile loop,
+    // where nothing of the step is live: a call inside the loop made the 80-register kernels spill loop-carried values.
     uint32_t* const my_free = P.free_list + (size_t)(blockIdx.x * nwarps + warp) * P.free_seg;
-    const unsigned long long next0 = P.ctr->next[P.parity];
-    unsigned long long emit_now = 0;                            // particles this launch emits (all CTAs compute the same value)
-    // K1 fused into the launch (steady phase): the slots a warp listed as free in the previous launch are the slots it
-    // visits again now (same grid, same slot count), so the warp refills them itself before its first tile -- particle
-    // next + (free slots listed by the warps before it) + j into its j-th free slot, problem.cpp:386-399, 32 at a time --
-    // and the two emission launches per loop trip (k_emit, k_emit_commit: ~25-45 us of every iteration) disappear.  Every
-    // CTA sums the previous launch's per-warp counts itself (a few thousand words from L2).
-    if (P.emit_fused && P.free_list != nullptr && next0 < P.n_end) {
-        __shared__ unsigned s_red[64];
-        const uint32_t* cnt = P.free_cnt + (size_t)P.parity * MCB_MAX_SEG;
-        const int nseg = (int)(gridDim.x * nwarps), first = (int)(blockIdx.x * nwarps);
-        unsigned before = 0, all = 0;
-        for (int b = (int)threadIdx.x; b < nseg; b += (int)blockDim.x) { const unsigned v = cnt[b]; all += v; if (b < first) before += v; }
-        before = __reduce_add_sync(0xFFFFFFFFu, before); all = __reduce_add_sync(0xFFFFFFFFu, all);
-        if (lane == 0) { s_red[warp] = before; s_red[32 + warp] = all; }
-        __syncthreads();
-        before = 0; all = 0;
-        for (unsigned w = 0; w < nwarps; ++w) { before += s_red[w]; all += s_red[32 + w]; }
-        const unsigned mine = lane < nwarps ? cnt[first + (int)lane] : 0u;       // this CTA's warps
-        unsigned incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((int)lane >= o) incl += v; }
-        const unsigned n_w = __shfl_sync(0xFFFFFFFFu, mine, (int)warp), base = before + __shfl_sync(0xFFFFFFFFu, incl - mine, (int)warp);
-        const unsigned long long room = P.n_end - next0;
-        emit_now = (unsigned long long)all < room ? (unsigned long long)all : room;
-#pragma unroll 1
-        for (unsigned j = lane; j < n_w; j += 32u) {
-            if ((unsigned long long)(base + j) < room) {
-                Particle np_;
-                emit_particle(P, T, next0 + base + j, np_);
-                np_.store(P.st, (long long)my_free[j]);
-            }
-        }
-        __syncwarp();
-        asm volatile("fence.proxy.async;" ::: "memory");       // the refilled slots are read back through the TMA prefetch
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        P.ctr->next[P.parity ^ 1] = next0 + emit_now; P.ctr->live[P.parity ^ 1] = 0ull;
-        if (emit_now) atomicAdd(&P.ctr->emitted, emit_now);
-    }
-    const bool list_free = P.free_list != nullptr && next0 + emit_now < P.n_end;
+    __shared__ unsigned s_emitted;
+    if (threadIdx.x == 0) s_emitted = 0u;
+    const bool list_free = P.emit_enable && P.ctr->next < P.n_end;
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.ctr->live[P.parity ^ 1] = 0ull;
 
     // TMA state prefetch: a warp's 32 slots are one contiguous 2304-B group (StateView), bulk-copied into the warp's staging
     // buffer while the warp works on the group before it.  The buffer is free again as soon as the lanes have moved their
@@ -863,10 +832,27 @@ __global__ void __launch_bounds__(NDM == 3 ? MCB_BLOCK_MAX_ND3 : (NDM == 2 ? MCB
         }
         __syncwarp();
     }
+    // K1: refill the slots this warp listed (see above)
+    if (list_free) {
+        const unsigned n_w = s_wcnt[warp].w;
+        if (n_w) {
+            unsigned long long base = 0ull;
+            if (lane == 0) base = atomicAdd(&P.ctr->next, (unsigned long long)n_w);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            const unsigned long long room = base < P.n_end ? P.n_end - base : 0ull;
+            const unsigned ne = room < (unsigned long long)n_w ? (unsigned)room : n_w;
+#pragma unroll 1
+            for (unsigned j = lane; j < ne; j += 32u) {
+                Particle np_;
+                emit_particle(P, T, base + j, np_);
+                np_.store(P.st, (long long)my_free[j]);
+            }
+            if (lane == 0 && ne) { red_shared_u32(&s_emitted, ne); if (P.maxloop > 0) s_wcnt[warp].y += ne; }     // refilled slots are live
+        }
+    }
 
     // --- the CTA's counters: one global atomic each; the warps' free-list counts
     __syncthreads();
-    if (threadIdx.x < nwarps && P.free_cnt) P.free_cnt[(size_t)(P.parity ^ 1) * MCB_MAX_SEG + blockIdx.x * nwarps + threadIdx.x] = list_free ? s_wcnt[threadIdx.x].w : 0u;
     if (threadIdx.x == 0) {
         unsigned long long st = 0, lv = 0, so = 0;
         for (unsigned w = 0; w < nwarps; ++w) { st += s_wcnt[w].x; lv += s_wcnt[w].y; so += s_wcnt[w].z; }
@@ -874,6 +860,7 @@ __global__ void __launch_bounds__(NDM == 3 ? MCB_BLOCK_MAX_ND3 : (NDM == 2 ? MCB
         if (s_esc) atomicAdd(&P.ctr->esc, (unsigned long long)s_esc);
         if (lv) atomicAdd(&P.ctr->live[P.parity], lv);
         if (so) atomicAdd(&P.ctr->stores, so);
+        if (s_emitted) atomicAdd(&P.ctr->emitted, (unsigned long long)s_emitted);
         if (P.host_ctr) {
             // the last CTA to get here mirrors the counters into pinned host memory: the host only waits for the event behind
             // the launch -- no device-to-host copy sits between two k_step launches
@@ -898,64 +885,27 @@ __global__ void __launch_bounds__(NDM == 3 ? MCB_BLOCK_MAX_ND3 : (NDM == 2 ? MCB
 
 #ifdef MCB_AUX_KERNELS      // the non-template kernels live in ONE translation unit (mcb_api.cu)
 // ------------------------------------------------------------------------------- k_emit
-// K1, dense: particle next+j is emitted into the j-th free slot (problem.cpp:386-399), all lanes busy.  The free slots are
-// listed per k_step CTA (segment b of free_list holds free_cnt[b] entries); j is mapped to (segment, entry) through the
-// prefix sums of the counts, which every CTA of this kernel recomputes in shared memory (<= a few hundred entries).
-// nseg == 0: the first fill, every slot 0 .. nslots-1 is free.
-__device__ __forceinline__ unsigned long long emit_quota(const StepParams& P, unsigned long long nfree) {
-    const unsigned long long next = P.ctr->next[P.parity], room = P.n_end > next ? P.n_end - next : 0ull;
+// K1 for the FIRST fill (every slot is free; afterwards k_step refills its own slots): particle next + j into slot j
+// (problem.cpp:386-399), one thread per particle; k_emit_commit then advances the particle counter.
+__device__ __forceinline__ unsigned long long emit_quota(const StepParams& P) {
+    const unsigned long long next = P.ctr->next, room = P.n_end > next ? P.n_end - next : 0ull, nfree = (unsigned long long)P.nslots;
     return nfree < room ? nfree : room;
 }
-__global__ void __launch_bounds__(256) k_emit(const StepParams P, int nseg) {
-    __shared__ unsigned s_pre[MCB_MAX_SEG + 1];
-    unsigned long long nfree = (unsigned long long)P.nslots;
-    if (nseg > 0) {
-        for (int b = (int)threadIdx.x; b < nseg; b += (int)blockDim.x) s_pre[b + 1] = P.free_cnt[(size_t)P.parity * MCB_MAX_SEG + b];      // coalesced, in flight together
-        __syncthreads();
-        if (threadIdx.x < 32) {                                   // one warp: inclusive scan of the counts, 32 at a time
-            unsigned carry = 0;
-            for (int b0 = 0; b0 < nseg; b0 += 32) {
-                const int b = b0 + (int)threadIdx.x;
-                unsigned v = b < nseg ? s_pre[b + 1] : 0u;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xFFFFFFFFu, v, o); if ((int)threadIdx.x >= o) v += t; }
-                if (b < nseg) s_pre[b + 1] = carry + v;
-                carry += __shfl_sync(0xFFFFFFFFu, v, 31);
-            }
-            if (threadIdx.x == 0) s_pre[0] = 0u;
-        }
-        __syncthreads();
-        nfree = s_pre[nseg];
-    }
-    const unsigned long long next = P.ctr->next[P.parity], n = emit_quota(P, nfree);
+__global__ void __launch_bounds__(256) k_emit(const StepParams P) {
+    const unsigned long long next = P.ctr->next, n = emit_quota(P);
     Tables T;
     T.lambda = reinterpret_cast<const double*>(P.mat_blob + P.mv.off_lambda);
     T.nw = P.mv.nw; T.np = P.mv.np; T.inv_bucket_w = P.mv.inv_bucket_w; T.inv_bucket_p = P.mv.inv_bucket_p;
     for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (unsigned long long)gridDim.x * blockDim.x) {
-        long long i = (long long)j;
-        if (nseg > 0) {
-            int lo = 0, hi = nseg;                                 // segment b with pre[b] <= j < pre[b+1]
-            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((unsigned)j >= s_pre[mid]) lo = mid; else hi = mid; }
-            i = (long long)P.free_list[(size_t)lo * P.free_seg + ((unsigned)j - s_pre[lo])];
-        }
         Particle ph;
         emit_particle(P, T, next + j, ph);
-        ph.store(P.st, i);
+        ph.store(P.st, (long long)j);
     }
 }
-// after k_emit: advance the particle counter, empty the free lists (one CTA)
-__global__ void __launch_bounds__(256) k_emit_commit(const StepParams P, int nseg) {
-    __shared__ unsigned long long s_sum;
-    if (threadIdx.x == 0) s_sum = 0ull;
-    __syncthreads();
-    unsigned mine = 0;
-    for (int b = (int)threadIdx.x; b < nseg; b += (int)blockDim.x) { mine += P.free_cnt[(size_t)P.parity * MCB_MAX_SEG + b]; P.free_cnt[(size_t)P.parity * MCB_MAX_SEG + b] = 0u; }
-    mine = __reduce_add_sync(0xFFFFFFFFu, mine);
-    if ((threadIdx.x & 31u) == 0u && mine) atomicAdd(&s_sum, (unsigned long long)mine);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned long long n = emit_quota(P, nseg > 0 ? s_sum : (unsigned long long)P.nslots);
-        P.ctr->next[P.parity] += n; P.ctr->emitted += n; P.ctr->live[P.parity] = 0ull;
+__global__ void k_emit_commit(const StepParams P) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const unsigned long long n = emit_quota(P);
+        P.ctr->next += n; P.ctr->emitted += n; P.ctr->live[0] = 0ull; P.ctr->live[1] = 0ull;
     }
 }
 
@@ -987,7 +937,7 @@ __global__ void k_traj(const StepParams P, const mcb_traj_desc t, const TrajDev 
         if (npts < o.max_points) { o.points[3 * npts] = x; o.points[3 * npts + 1] = y; o.points[3 * npts + 2] = z; }
         npts++;
     };
-    Particle ph; ph.init(0u, true, true, 0u, 0ull);
+    Particle ph; ph.init(0u, true, true, 0u, 0ull, P.step_bits);
     Rng g; g.begin(P.seed, 0ull, 0u);
     ph.set_wp(t.has_prop ? (uint32_t)(t.w * T.np + t.p) : draw_prop(g, T, T.wprob, T.walias, T.pprob, T.palias));   // :232
     int cur = -1;
@@ -1001,7 +951,7 @@ __global__ void k_traj(const StepParams P, const mcb_traj_desc t, const TrajDev 
         const DEmitter& E = P.emitters[g.uint_below((uint32_t)P.nemitter)];
         const uint32_t wp = ph.wp();
         emit_from(E, g, ph);
-        ph.init(wp, true, true, ph.sdom(), 0ull);         // TrajProblem traces with sign +1 (problem.cpp:244-253)
+        ph.init(wp, true, true, ph.sdom(), 0ull, P.step_bits);         // TrajProblem traces with sign +1 (problem.cpp:244-253)
         cur = E.kind == MCB_EMIT_BDRY ? E.index : -1;
     }
     push(ph.px, ph.py, ph.pz);
@@ -1099,7 +1049,7 @@ __global__ void k_philox(unsigned long long seed, unsigned long long pid, uint32
 }
 
 // scatter the slot state to per-particle trace arrays (slot order is not particle order)
-__global__ void k_gather_trace(StateView st, long long nslots, unsigned long long n_begin, long long n, int np,
+__global__ void k_gather_trace(StateView st, long long nslots, unsigned long long n_begin, long long n, int np, uint32_t step_bits,
                                const unsigned char* geo_blob, GeometryView gv,
                                double* pos, double* dir, double* sn, long long* w, long long* p, int32_t* sign,
                                int32_t* alive, int32_t* sdom, long long* nscat, long long* steps, int32_t* cell) {
@@ -1107,7 +1057,7 @@ __global__ void k_gather_trace(StateView st, long long nslots, unsigned long lon
     if (i >= nslots) return;
     Particle ph;
     const unsigned long long meta = ph.load(st, i), ps = ph.ps;
-    const long long o = (long long)(MCB_PID(ps) - n_begin);
+    const long long o = (long long)((ps >> step_bits) - n_begin);
     if (o < 0 || o >= n) return;
     pos[3 * o] = ph.px; pos[3 * o + 1] = ph.py; pos[3 * o + 2] = ph.pz;
     dir[3 * o] = ph.dx; dir[3 * o + 1] = ph.dy; dir[3 * o + 2] = ph.dz;
@@ -1118,7 +1068,7 @@ __global__ void k_gather_trace(StateView st, long long nslots, unsigned long lon
     alive[o] = MCB_META_KILLED(meta) ? 0 : 1;
     sdom[o] = (int32_t)MCB_META_SDOM(meta);
     nscat[o] = MCB_META_NSCAT(meta);
-    steps[o] = MCB_STEP(ps);
+    steps[o] = (long long)(ps & ((1ull << step_bits) - 1ull));
     const DSdom* sds = reinterpret_cast<const DSdom*>(geo_blob + gv.off_sdom);
     const DSdom& sd = sds[MCB_META_SDOM(meta)];
     double c[3]; sdom_coord(sd, ph.px, ph.py, ph.pz, c);

@@ -329,6 +329,34 @@ def test_error_behaviour(omats):
     ctx.close()
 
 
+def test_long_histories_and_cum_bins_are_validated(gpu_ctx, omats):
+    """(a) the reference takes any `long` maxloop (default 100 * maxscat, problem.cpp:339): the pid|step word gives
+    the loop trip up to 32 bits (the Philox event counter), so maxloop >= 2^28 solves -- and gives the very field of a short
+    bound no history reaches; (b) a Cum* step too small for maxscat and size would index past the field rows: rejected."""
+    mat, dom = omats["grey"], cases.slab()
+    cases.upload(gpu_ctx, mat, dom)
+    base = orc.Problem(mat, dom, "multi", 20000, 50)
+    ref, rst = gpu_ctx.solve(base.desc, seed=SEED)
+    for maxloop in (1 << 28, (1 << 31) + 5, 0xFFFFFFFE):
+        d = abi.ProblemDesc.from_buffer_copy(base.desc)
+        d.maxloop = maxloop
+        got, gst = gpu_ctx.solve(d, seed=SEED)
+        assert (gst["emitted"], gst["steps"], gst["esc"]) == (rst["emitted"], rst["steps"], rst["esc"])
+        scale = np.abs(ref).max(axis=1, keepdims=True)
+        assert (np.abs(got - ref) <= 1e-9 * scale).all()
+    d = abi.ProblemDesc.from_buffer_copy(base.desc)
+    d.maxloop = 0xFFFFFFFF
+    with pytest.raises(capi.McbError) as e:
+        gpu_ctx.solve(d, seed=SEED)
+    assert e.value.code == abi.MCB_EINVAL and "maxloop" in str(e.value)
+    cum = orc.Problem(mat, dom, "cumtemp", 2000, 50, size=5)
+    bad = abi.ProblemDesc.from_buffer_copy(cum.desc)
+    bad.step = max(1, cum.desc.step // 2)
+    with pytest.raises(capi.McbError) as e:
+        gpu_ctx.solve(bad, seed=SEED)
+    assert e.value.code == abi.MCB_EINVAL and "step" in str(e.value)
+
+
 def test_host_mirror_solve_matches_oracle(matfiles, omats):
     """The C++ mirror of the reference API (Material -> FilmDomain/TubeDomain -> MultiProblem::solve) drives the
     same device path: identical counters and field as the oracle on the same Philox seed."""
