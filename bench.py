@@ -44,9 +44,8 @@ WORKLOADS = {
 }
 HEADLINE = "C2-slab100nm-si"
 SIDE_CONFIGS = ["C1-film100nm-si", "C3-wire32x32-si", "C4-tube-si", "C5-bulk128-si"]      # N = 1: measured beside the headline
-# committed ncu --set full captures of the steady-phase k_step launch of each workload (profiles/ncu_traffic.json)
-NCU_KEYS = {"C2-slab100nm-si": "k_step_steady_S1_C2", "C1-film100nm-si": "k_step_film_S1_C1", "C3-wire32x32-si": "k_step_wire_S1_C3",
-            "C4-tube-si": "k_step_tube_S1_C4", "C5-bulk128-si": "k_step_bulk128_S1_C5"}
+# committed ncu --set full captures of the steady-phase k_step launch of each workload: profiles/ncu_traffic.json (keyed by workload,
+# written by tools/ncu_traffic.py from the captures of tools/gpu_r2_final.sh)
 
 
 def parse():
@@ -329,7 +328,8 @@ def measure(runner, steps, warmup, world, seed0, e2e_steps, peaks, sampler=None)
         "nemit_per_gpu": runner.n_end - runner.n_begin, "phonon_steps_per_solve": tot["steps"] / steps, "esc": tot["esc"],
         "device_ms_per_step": device_ms / steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "kernel": f"k_step, steady-phase launches (S={runner.S}: population full, one state round trip per loop trip)",
+                     "kernel": f"k_step, steady-phase launches (S={runner.S}: population full, one state round trip per loop trip; the "
+                               "launch also refills the slots that end inactive -- K1 is fused into it)",
                      "algorithmic_bytes_per_launch": tot["steady_stores"] * B_ALG / max(1, tot["steady_launches"]),
                      "kernel_ms_per_launch": tot["steady_ms"] / max(1, tot["steady_launches"]),
                      "kernel_share_of_step": sdy_s / elapsed,
@@ -361,7 +361,7 @@ def ncu_capture(workload, mode, slots):
     """DRAM traffic / issue-slot utilisation of the steady k_step launch from the committed ncu --set full capture."""
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["kernels"]
-        k = tj[NCU_KEYS[workload]]
+        k = tj[workload]
         if mode != "streaming" or slots:
             return None, None
         return k.get("dram_bytes_per_launch"), k.get("issue_active_pct")
@@ -421,6 +421,16 @@ def run_ours(args):
         srec["roofline"]["issue_active_pct_ncu"] = issue
         srec["config"] = {"workload": name, "nemit_per_gpu": WORKLOADS[name][7], "maxscat": WORKLOADS[name][5],
                           "field": f"{r.prob.rows}x{r.dom.cols}"}
+        if args.mode == "streaming":            # the max-throughput schedule beside it (S = 16 loop trips per state round trip)
+            ctx.set_options(steps_per_launch=16, slots=0)
+            r.S = 16
+            r.step(60, timed=False)
+            barrier(world)
+            t3 = time.perf_counter()
+            rsteps = sum(r.step(4000 + i, timed=False)["steps"] for i in range(2))
+            barrier(world)
+            srec["resident_mode_value_per_gpu"] = rsteps / (time.perf_counter() - t3)
+            ctx.set_options(steps_per_launch=S, slots=0)
         side[name] = srec
         del r
 
