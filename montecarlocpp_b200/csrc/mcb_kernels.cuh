@@ -824,8 +824,10 @@ __global__ void __launch_bounds__(NDM == 3 ? MCB_BLOCK_MAX_ND3 : (NDM == 2 ? MCB
         // ids below nslots), bump the warp's counters
         const unsigned st_mask = __ballot_sync(0xFFFFFFFFu, was_active);
         const unsigned fm = list_free ? __ballot_sync(0xFFFFFFFFu, i < nslots) & ~run_mask : 0u;
-        uint4 wc = s_wcnt[warp];                                // broadcast read; only lane 0 writes it back
-        if ((fm >> lane) & 1u) my_free[wc.w + __popc(fm & ((1u << lane) - 1u))] = (uint32_t)i;
+        uint4 wc = make_uint4(0u, 0u, 0u, 0u);
+        if (lane == 0) wc = s_wcnt[warp];                       // the warp's slot is read and written by lane 0 only
+        const unsigned nlisted = __shfl_sync(0xFFFFFFFFu, wc.w, 0);
+        if ((fm >> lane) & 1u) my_free[nlisted + __popc(fm & ((1u << lane) - 1u))] = (uint32_t)i;
         if (lane == 0) {
             wc.x += tile_steps; wc.y += __popc(run_mask); wc.z += __popc(st_mask); wc.w += __popc(fm);
             s_wcnt[warp] = wc;
