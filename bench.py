@@ -421,6 +421,35 @@ def run_ours(args):
         srec["roofline"]["issue_active_pct_ncu"] = issue
         srec["config"] = {"workload": name, "nemit_per_gpu": WORKLOADS[name][7], "maxscat": WORKLOADS[name][5],
                           "field": f"{r.prob.rows}x{r.dom.cols}"}
+        if world > 1:
+            # SURVEY 8d C5 stress variant: the tally all-reduced many times per solve instead of once.  The algorithm has no
+            # per-step coupling, so the solve is cut into CHUNKS particle ranges per rank and every chunk's raw 67-MB tally is
+            # all-reduced on its own (on the library's stream) and added up: what frequent collectives would cost.
+            CHUNKS = 16
+            tmp = torch.zeros_like(r.raw)
+            span = (r.n_end - r.n_begin + CHUNKS - 1) // CHUNKS
+            barrier(world)
+            t4 = time.perf_counter()
+            ssteps = 0
+            with torch.cuda.stream(r.lib_stream):
+                r.raw.zero_()
+            for k in range(CHUNKS):
+                with torch.cuda.stream(r.lib_stream):
+                    tmp.zero_()
+                b0 = r.n_begin + k * span
+                ssteps += ctx.solve_raw_dev(r.prob.desc, tmp.data_ptr(), seed=77, n_begin=b0, n_end=min(r.n_end, b0 + span))["steps"]
+                with torch.cuda.stream(r.lib_stream):
+                    dist.all_reduce(tmp, op=dist.ReduceOp.SUM)
+                    r.raw.add_(tmp)
+            ctx.finalize_dev(r.prob.desc, r.raw.data_ptr())
+            barrier(world)
+            dt4 = time.perf_counter() - t4
+            tot4 = torch.tensor([float(ssteps)], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tot4, op=dist.ReduceOp.SUM)
+            srec["collective_stress"] = {"allreduces_per_solve": CHUNKS, "allreduce_bytes": r.raw.numel() * 8, "value": tot4.item() / dt4,
+                                         "ms_per_solve": 1e3 * dt4,
+                                         "note": "one solve cut into 16 particle chunks per rank, the raw tally all-reduced after every chunk"}
+            del tmp
         if args.mode == "streaming":            # the max-throughput schedule beside it (S = 16 loop trips per state round trip)
             ctx.set_options(steps_per_launch=16, slots=0)
             r.S = 16

@@ -112,6 +112,7 @@ struct mcb_ctx {
     bool has_dom = false; GeometryView gv{}; DevBuf<unsigned char> geo_blob;
     std::vector<DSdom> h_sdom; int nemitter = 0; int any_nd = 0;      // 0 / 1 / 2: see k_step's NDM
     int nd_mark_words = 0;       // warp-balanced N-D tally: 32-bit mark words a warp needs = max items of one flight (1 + sum of max_)
+    long long nd_max_cells = 0;  // ... and the largest max_ of an N-D grid axis (16-bit record fields)
     int all_box = 0;             // every subdomain is an axis-aligned box (k_step's BOX)
     int t1_ok = 0;               // every 1-D tally grid has unit column stride (the difference-array histograms apply)
     DevBuf<DEmitter> emitters; DevBuf<double> cell_vol; long long cols = 0;
@@ -216,13 +217,23 @@ int plan_run(mcb_ctx* c, const mcb_problem_desc* prob, long long nparticles, Run
     // fewer, fatter threads
     r->ndm = c->any_nd; r->nd_off = 0; r->nd_warp_bytes = 0;
 #if MCB_ND_BALANCED
-    if (c->any_nd) {                    // the per-warp record areas must leave room for the tables (very fine grids need many mark words)
+    int nd3_block = 0;
+    if (c->any_nd && c->nd_max_cells <= MCB_NDB_MAX_CELLS) {
+        // per-warp record areas (very fine grids need many mark words): take the largest CTA that still leaves room for one copy
+        // of the CTA histogram, else the largest that fits at all (the tally then goes to the global field)
         const size_t wb = (size_t)(MCB_NDB_FIXED + 4 * (c->nd_mark_words + 2) + 15) / 16 * 16;
-        const int blk = o.block > 0 ? std::min(o.block, MCB_BLOCK_MAX_ND3) : MCB_BLOCK_MAX_ND3;
-        if (base + 16 + (size_t)(blk / 32) * wb <= budget) { r->ndm = 3; r->nd_warp_bytes = (uint32_t)wb; }
+        const size_t hist1 = o.tally_mode == 2 ? 0 : (size_t)c->cols * 4u * (size_t)((3 * prob->rows) | 1);
+        const int top = o.block > 0 ? std::min(o.block, MCB_BLOCK_MAX_ND3) : MCB_BLOCK_MAX_ND3;
+        for (int pass = 0; pass < 2 && !nd3_block; ++pass)
+            for (int blk = top; blk >= 256 && !nd3_block; blk -= 128)
+                if (base + 16 + (size_t)(blk / 32) * wb + (pass == 0 ? hist1 : 0) <= budget) nd3_block = blk;
+        if (nd3_block) { r->ndm = 3; r->nd_warp_bytes = (uint32_t)wb; }
     }
 #endif
-    const int block_max = r->ndm == 3 ? MCB_BLOCK_MAX_ND3 : (c->any_nd == 2 ? MCB_BLOCK_MAX_ND : (c->any_nd == 1 ? MCB_BLOCK_MAX_ND1 : MCB_BLOCK_MAX));
+    int block_max = c->any_nd == 2 ? MCB_BLOCK_MAX_ND : (c->any_nd == 1 ? MCB_BLOCK_MAX_ND1 : MCB_BLOCK_MAX);
+#if MCB_ND_BALANCED
+    if (r->ndm == 3) block_max = nd3_block;
+#endif
     r->block = o.block > 0 ? std::min(o.block, block_max) : block_max;
     if (r->block % 32 != 0 || o.block > 1024) { c->err = "block must be a multiple of 32, <= 1024"; return MCB_EINVAL; }
     r->S = o.steps_per_launch > 0 ? o.steps_per_launch : 16;
@@ -632,7 +643,7 @@ int mcb_upload_domain(mcb_ctx* c, const mcb_domain_desc* d) {
     for (int i = 0; i < d->npair; ++i) if (d->pairs[i] < 0 || d->pairs[i] >= d->nplane) { c->err = "pair id out of range"; return MCB_EINVAL; }
     std::vector<DSdom> sd(d->nsdom); std::vector<double> cell_vol; int any_nd = 0; double flight_max = 0.0;
     int all_box = 1, t1_ok = 1;
-    long long cols = 0, nd_mark_words = 0;
+    long long cols = 0, nd_mark_words = 0, nd_max_cells = 0;
     for (int s = 0; s < d->nsdom; ++s) {
         const mcb_sdom_desc& S = d->sdoms[s]; DSdom& D = sd[s]; std::memset(&D, 0, sizeof D);
         if (S.plane_count <= 0 || S.plane_begin < 0 || S.plane_begin + S.plane_count > d->nplane) { c->err = "sdom plane range out of bounds"; return MCB_EINVAL; }
@@ -677,6 +688,7 @@ int mcb_upload_domain(mcb_ctx* c, const mcb_domain_desc* d) {
         }
         if (S.accum >= 3) {
             nd_mark_words = std::max<long long>(nd_mark_words, 1 + S.max[0] + S.max[1] + S.max[2]);
+            nd_max_cells = std::max<long long>(nd_max_cells, std::max(S.max[0], std::max(S.max[1], S.max[2])));
             // BOX kernels take coord() as div * (inv_dd * (p_d - o_d)): every off-diagonal entry of inv_ must be an exact zero
             if (D.aabb) for (int r = 0; r < 3; ++r) for (int k = 0; k < 3; ++k) if (r != k && S.inv[r + 3 * k] != 0.0) all_box = 0;
         }
@@ -764,7 +776,7 @@ int mcb_upload_domain(mcb_ctx* c, const mcb_domain_desc* d) {
     CUDA_TRY(c, cudaMemcpy(c->emitters.p, em.data(), em.size() * sizeof(DEmitter), cudaMemcpyHostToDevice));
     CUDA_TRY(c, c->cell_vol.alloc(cell_vol.size()));
     if (!cell_vol.empty()) CUDA_TRY(c, cudaMemcpy(c->cell_vol.p, cell_vol.data(), cell_vol.size() * 8, cudaMemcpyHostToDevice));
-    c->gv = v; c->h_sdom = sd; c->nemitter = d->nemitter; c->cols = cols; c->any_nd = any_nd; c->nd_mark_words = (int)std::min<long long>(nd_mark_words, 1 << 20); c->flight_max = flight_max; c->has_dom = true;
+    c->gv = v; c->h_sdom = sd; c->nemitter = d->nemitter; c->cols = cols; c->any_nd = any_nd; c->nd_mark_words = (int)std::min<long long>(nd_mark_words, 1 << 20); c->nd_max_cells = nd_max_cells; c->flight_max = flight_max; c->has_dom = true;
     c->all_box = all_box; c->t1_ok = t1_ok;
     return MCB_OK;
 }
