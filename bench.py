@@ -395,10 +395,11 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     rec, clocks = measure(head, args.steps, args.warmup, world, 0, max(1, min(args.steps, 5)), peaks, sampler)
 
-    # ---- the other schedule, for reference: resident mode (S = 16 loop trips per state round trip, 8 tiles per thread)
+    # ---- the other schedule, for reference: the library's DEFAULT (no options: every phonon resident when the state fits in
+    # memory, S = 16 loop trips per state round trip) -- what mcb_solve does for a caller who sets nothing
     other = None
     if args.mode == "streaming":
-        ctx.set_options(steps_per_launch=16, slots=148 * 768 * 8)
+        ctx.set_options(steps_per_launch=0, slots=0)
         head.S = 16
         head.step(50, timed=False)
         barrier(world)
@@ -451,7 +452,7 @@ def run_ours(args):
                                          "note": "one solve cut into 16 particle chunks per rank, the raw tally all-reduced after every chunk"}
             del tmp
         if args.mode == "streaming":            # the max-throughput schedule beside it (S = 16 loop trips per state round trip)
-            ctx.set_options(steps_per_launch=16, slots=0)
+            ctx.set_options(steps_per_launch=0, slots=0)        # the library's default schedule
             r.S = 16
             r.step(60, timed=False)
             barrier(world)
@@ -468,7 +469,7 @@ def run_ours(args):
         nw, npol = head.mat.desc.nw, head.mat.desc.np
         h2d = nw * npol * (8 * 3 + 1) + nw * 10 + nw * npol * 12 + nw * 12 + 2048     # tables + alias + geometry (approx, bytes)
         d2h = head.prob.rows * head.dom.cols * 8
-        slots = args.slots if args.slots else 148 * 768 * 32          # library default: 32 tiles per CTA (768 threads for 1-D tallies)
+        slots = args.slots if args.slots else 148 * 768 * 48          # library default for an explicit S: 48 tiles per warp (768-thread CTAs for 1-D tallies)
         traffic, issue = ncu_capture(args.workload, args.mode, args.slots)
         roof = rec["roofline"]
         roof.update({"traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, committed capture "
@@ -502,8 +503,11 @@ def run_ours(args):
             line["configs"] = side
         if other is not None:
             line["resident_mode"] = {"value_per_gpu": other[0] / other[1], "unit": "phonon-steps/s", "steps_per_launch": 16,
-                                     "slots": 148 * 768 * 8, "note": "rank-0 rate of the max-throughput schedule (state kept in "
-                                     "registers for 16 loop trips per HBM round trip); not the mode the roofline is quoted on"}
+                                     "slots": "library default: every phonon of the solve resident when the two state buffers fit in half "
+                                              "of the free device memory",
+                                     "note": "rank-0 rate of the library's default schedule (mcb_options all zero: state kept in registers for "
+                                             "16 loop trips per HBM round trip, the population only decays); not the mode the roofline is "
+                                             "quoted on (SURVEY 8d rule iv: B_alg / 16 by construction)"}
         if not args.no_cpu_baseline and world == 1:      # reported on rank 0 at N=1 only
             rate, dt, steps, cores, n, kind_ = cpu_reference_rate(args.workload, min(args.cpu_sample, nemit), 4242)
             line["cpu_baseline"] = {"value": rate, "unit": "phonon-steps/s", "cores": cores, "kind": kind_,

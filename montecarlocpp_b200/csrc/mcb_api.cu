@@ -201,9 +201,17 @@ struct RunPlan {
 #ifndef MCB_ND_BALANCED
 #define MCB_ND_BALANCED 1      // N-D tally grids: the warp-balanced item walk (k_step NDM 3) instead of the per-lane serial walk
 #endif
-#ifndef MCB_DECAY_S
-#define MCB_DECAY_S 16         // loop trips per launch once nothing is left to emit
+#ifndef MCB_TILES_PER_WARP
+#define MCB_TILES_PER_WARP 48
 #endif
+#ifndef MCB_DECAY_S
+#define MCB_DECAY_S 16         // loop trips per launch once nothing is left to emit (before the hazard is known)
+#endif
+#ifndef MCB_DECAY_ADAPT_PCT
+#define MCB_DECAY_ADAPT_PCT 30 // decay phase: loop trips per launch chosen so that about this share of the live phonons terminates (0: fixed)
+#endif
+#define MCB_DECAY_S_MIN 4
+#define MCB_DECAY_S_MAX 64
 #ifndef MCB_COMPACT_PCT
 #define MCB_COMPACT_PCT 90
 #endif
@@ -237,7 +245,23 @@ int plan_run(mcb_ctx* c, const mcb_problem_desc* prob, long long nparticles, Run
     r->block = o.block > 0 ? std::min(o.block, block_max) : block_max;
     if (r->block % 32 != 0 || o.block > 1024) { c->err = "block must be a multiple of 32, <= 1024"; return MCB_EINVAL; }
     r->S = o.steps_per_launch > 0 ? o.steps_per_launch : 16;
-    long long slots = o.slots > 0 ? o.slots : (long long)c->sm_count * r->block * 32;   // ~3.6 M resident phonons
+    // streaming schedule: MCB_TILES_PER_WARP tiles per warp (5.5 M resident phonons for the 1-D kernels; 32 tiles: C1 -8 %, C3 -4 %:
+    // a launch is then so short that its fixed costs -- table staging, flush, emission tail -- weigh more; 64: C2 -4 %)
+    long long slots = o.slots > 0 ? o.slots : (long long)c->sm_count * r->block * MCB_TILES_PER_WARP;
+    if (o.slots <= 0 && o.steps_per_launch <= 0) {
+        // The library's default schedule (no options set) keeps EVERY phonon of the solve resident when the two state buffers fit
+        // in half of the device memory that is available: the first fill emits them all with dense lanes and every launch then
+        // runs S = 16 loop trips per state round trip on a population that only decays (C1 +30 %, C3 / C5 +35 ... +50 % over a
+        // 3.6-M-slot population that is refilled while it streams).  An explicit slots / steps_per_launch keeps the streaming
+        // schedule the HBM roofline is quoted on.
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            const size_t have = 2 * state_bytes(c->slots_alloc);
+            const long long cap = (long long)((free_b + have) / 2 / (2 * (MCB_GROUP_BYTES / 32)));
+            slots = std::max(slots, std::min<long long>(nparticles, cap));
+        }
+        cudaGetLastError();
+    }
     slots = std::min(slots, std::max<long long>(nparticles, 1));
     if (slots > 0x7FFFFF00ll) { c->err = "too many resident slots (< 2^31)"; return MCB_ELIMIT; }
     r->slots = slots;
@@ -388,13 +412,17 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
     // previous launch; after the last particle dies one extra, empty launch has already been queued.
     const long long tail_slots = (long long)plan.grid * plan.block;      // one tile per CTA: finish in one launch
     int S_cur = plan.S;
+    if (MCB_DECAY_ADAPT_PCT > 0 && c->opt.steps_per_launch <= 0 && nslots >= total) S_cur = MCB_DECAY_S_MIN;   // everything resident: start short, then adapt
     bool host_all_emitted = false;
+    unsigned long long last_live = (unsigned long long)nslots;
     {   // fused emission: one free-slot segment per k_step warp, long enough for every slot the warp visits
         const long long tiles0 = (nslots + plan.block - 1) / plan.block;
         const long long grid0 = std::min<long long>(plan.grid, std::max<long long>(tiles0, 1));
         P.free_seg = (uint32_t)(((tiles0 + grid0 - 1) / grid0) * 32);
-        CUDA_TRY(c, c->free_list.alloc((size_t)(grid0 * (plan.block / 32)) * P.free_seg));
-        P.free_list = c->free_list.p;
+        if (nslots < total) {               // (every phonon resident after the first fill: nothing is ever refilled)
+            CUDA_TRY(c, c->free_list.alloc((size_t)(grid0 * (plan.block / 32)) * P.free_seg));
+            P.free_list = c->free_list.p;
+        }
     }
     const long long compact_pct = c->opt.compact_pct > 0 ? c->opt.compact_pct : MCB_COMPACT_PCT;
     long long steady_launches = 0; float steady_ms = 0.f;
@@ -408,7 +436,7 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
         const int grid = (int)std::min<long long>(plan.grid, std::max<long long>(tiles, 1));
         // K1: the first fill (every slot free) is its own dense kernel; afterwards k_step refills the slots that end inactive
         // itself (32 at a time, ids from the atomic cursor Counters::next) while particles are left to emit
-        P.emit_enable = host_all_emitted ? 0 : 1;
+        P.emit_enable = (host_all_emitted || !P.free_list) ? 0 : 1;
         if (it == 0) {
             k_emit<<<(unsigned)(c->sm_count * 8), 256, 0, c->stream>>>(P);
             k_emit_commit<<<1, 32, 0, c->stream>>>(P);
@@ -431,6 +459,11 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
             steady_launches++; steady_ms += ms;
             steady_steps += c->h_ctr[prev].steps - prev_steps; steady_stores += c->h_ctr[prev].stores - prev_stores;
         }
+        // hazard of the population in launch it-1 (fraction of the live phonons that terminated per loop trip): sets the decay S below
+        const unsigned long long dsteps = c->h_ctr[prev].steps - prev_steps;
+        double hazard = -1.0;
+        if (all_emitted && last_live >= live && dsteps > 0) hazard = (double)(last_live - live) / (double)dsteps;
+        last_live = live;
         prev_steps = c->h_ctr[prev].steps; prev_stores = c->h_ctr[prev].stores;
         if (all_emitted && live == 0) {
             CUDA_TRY(c, cudaEventSynchronize(c->evB[slot]));
@@ -454,6 +487,12 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
         // once the survivors fit one tile per CTA let every thread run its phonon to termination
         if (all_emitted && c->opt.decay_mode != 1) {
             S_cur = std::max(plan.S, MCB_DECAY_S);
+#if MCB_DECAY_ADAPT_PCT > 0
+            // a young population terminates fast (C2: 6 % per loop trip -- 16 trips would leave 37 % of the lanes alive), an old
+            // one slowly: run as many loop trips per state round trip as let about MCB_DECAY_ADAPT_PCT % of the phonons terminate
+            if (hazard > 0.0) S_cur = (int)std::min<double>(MCB_DECAY_S_MAX, std::max<double>(MCB_DECAY_S_MIN, std::floor(0.01 * MCB_DECAY_ADAPT_PCT / hazard + 0.5)));
+            else if (hazard == 0.0) S_cur = MCB_DECAY_S_MAX;
+#endif
             if ((long long)live <= tail_slots) S_cur = (int)std::min<long long>(std::max<long long>(prob->maxloop, 1), 1 << 22);
         }
     }

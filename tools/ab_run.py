@@ -21,7 +21,7 @@ for wl in (sys.argv[1:] or ["slab", "film", "wire"]):
         dom = hostapi.Domain("film", [1e-6, 1e-7, 1e-6], [0, 20, 0], 1.0); prob = hostapi.FieldProblem(mat, dom, "multi", 4_000_000, 100)
     ctx.upload_domain(dom.desc)
     raw = torch.zeros(prob.rows * dom.cols, dtype=torch.float64, device="cuda")
-    for S, k in ((1, 32), (16, 8)):
+    for S, k in ((1, 48), (16, 8)):
         extra = {k_: int(v_) for k_, v_ in (kv.split("=") for kv in os.environ.get("AB_OPTS", "").split())}
         blk = int(os.environ.get("AB_BLOCK") or "768")
         ctx.set_options(steps_per_launch=S, slots=148 * blk * k, **extra)

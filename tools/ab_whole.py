@@ -15,7 +15,9 @@ for wl in (sys.argv[1:] or ["slab", "film"]):
     dom = hostapi.Domain(kind, dim, div, 1.0); prob = hostapi.FieldProblem(mat, dom, "multi", n, ms)
     ctx.upload_domain(dom.desc)
     raw = torch.zeros(prob.rows * dom.cols, dtype=torch.float64, device="cuda")
-    ctx.set_options(steps_per_launch=1, slots=0)
+    tiles = int(os.environ.get("AB_TILES") or "0")            # tiles per warp (0: library default, 32)
+    blk = 768 if wl in ("slab", "film") else 640
+    ctx.set_options(steps_per_launch=int(os.environ.get("AB_S") or "1"), slots=148 * blk * tiles)
     best = 1e9
     for rep in range(4):
         raw.zero_(); torch.cuda.synchronize()
