@@ -364,7 +364,7 @@ def ncu_capture(workload, mode, slots):
         k = tj[workload]
         if mode != "streaming" or slots:
             return None, None
-        return k.get("dram_bytes_per_launch"), k.get("issue_active_pct")
+        return k.get("dram_bytes_per_slot"), k.get("issue_active_pct")
     except Exception:
         return None, None
 
@@ -417,8 +417,8 @@ def run_ours(args):
     for name in names:
         r = Runner(ctx, name, WORKLOADS[name][7], world, rank, S, 0)
         srec, _ = measure(r, args.side_steps, 1, world, 10_000, 1 if world == 1 else 0, peaks)
-        traffic, issue = ncu_capture(name, args.mode, 0)
-        srec["roofline"]["traffic"] = traffic
+        per_slot, issue = ncu_capture(name, args.mode, 0)       # ncu DRAM bytes per visited slot x the slots one bench launch visits
+        srec["roofline"]["traffic"] = per_slot * srec["roofline"]["algorithmic_bytes_per_launch"] / B_ALG if per_slot else None
         srec["roofline"]["issue_active_pct_ncu"] = issue
         srec["config"] = {"workload": name, "nemit_per_gpu": WORKLOADS[name][7], "maxscat": WORKLOADS[name][5],
                           "field": f"{r.prob.rows}x{r.dom.cols}"}
@@ -469,11 +469,13 @@ def run_ours(args):
         nw, npol = head.mat.desc.nw, head.mat.desc.np
         h2d = nw * npol * (8 * 3 + 1) + nw * 10 + nw * npol * 12 + nw * 12 + 2048     # tables + alias + geometry (approx, bytes)
         d2h = head.prob.rows * head.dom.cols * 8
-        slots = args.slots if args.slots else 148 * 768 * 48          # library default for an explicit S: 48 tiles per warp (768-thread CTAs for 1-D tallies)
-        traffic, issue = ncu_capture(args.workload, args.mode, args.slots)
+        slots = args.slots if args.slots else 148 * 768 * 32          # library default for an explicit S: 32 ... 96 tiles per warp, ~ nemit / 3 (768-thread CTAs for 1-D tallies)
+        per_slot, issue = ncu_capture(args.workload, args.mode, args.slots)
         roof = rec["roofline"]
-        roof.update({"traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, committed capture "
-                                                         "profiles/ncu_traffic.json -- ncu cannot run inside the bench)",
+        traffic = per_slot * roof["algorithmic_bytes_per_launch"] / B_ALG if per_slot else None
+        roof.update({"traffic": traffic, "traffic_unit": "bytes per launch: ncu dram__bytes_read.sum + dram__bytes_write.sum per visited slot of the committed "
+                                                         "capture of this kernel (profiles/ncu_traffic.json -- ncu cannot run inside the bench) x the "
+                                                         "slots one launch of this run visits",
                      "issue_active_pct_ncu": issue,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
                      "note": f"B_alg = 128 B per state round trip (SURVEY 8d; the shipped layout moves {2 * SLOT_BYTES} B, see profiles/); "

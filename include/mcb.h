@@ -192,21 +192,27 @@ typedef struct mcb_stats {
     double  steady_ms;
 } mcb_stats;
 
-/* Tunables of the device schedule (not part of the physics). 0 = library default. */
+/* Tunables of the device schedule (not part of the physics). 0 = library default.
+ * With `slots` and `steps_per_launch` both 0 (the default) every phonon of the solve is kept resident when the two state
+ * buffers fit in half of the available device memory, and each launch runs several loop trips per state round trip on a
+ * population that only decays; setting either one selects the streaming schedule (resident population refilled while it
+ * streams), the one an HBM roofline can be quoted on. */
 typedef struct mcb_options {
-    int64_t slots;             /* resident particle slots (SoA length); default 32 tiles */
-                               /* per thread of the persistent grid                      */
-    int32_t steps_per_launch;  /* S: loop-body trips per state load/store             */
-    int32_t block;             /* threads per CTA                                     */
+    int64_t slots;             /* resident particle slots; streaming default: 32 ... 96  */
+                               /* tiles of 32 slots per warp (~ a third of the phonons)   */
+    int32_t steps_per_launch;  /* S: loop-body trips per state load/store while particles */
+                               /* are left to emit (1 = streaming)                        */
+    int32_t block;             /* threads per CTA (capped by the kernel's launch bounds)  */
     int32_t ctas_per_sm;       /* persistent grid = ctas_per_sm * SM count (default 1:   */
                                /* the tables + histograms fill one CTA's shared memory)  */
-    int32_t tally_mode;        /* 0 auto, 1 warp-private smem histograms, 2 global    */
-                               /* field (fp64 RED in L2), 3 one smem histogram per CTA */
-    int32_t decay_mode;        /* 0: once nothing is left to emit use S >= 16, compact,  */
-                               /*    then run the last survivors to termination;         */
+    int32_t tally_mode;        /* 0 auto, 1 shared-memory histograms (1-D difference     */
+                               /* arrays / one per CTA), 2 global field (fp64 RED in L2), */
+                               /* 3 one histogram per CTA                                 */
+    int32_t decay_mode;        /* 0: once nothing is left to emit choose S per launch    */
+                               /*    from the measured termination rate, compact, then    */
+                               /*    run the last survivors to termination;               */
                                /* 1: keep steps_per_launch throughout (compaction only)  */
-    int32_t emit_mode;         /* 0: dense emission kernel between step launches;        */
-                               /* 1: emit inside the step kernel (slot refilled at once) */
+    int32_t emit_mode;         /* must be 0 (emission is fused into the step kernel)      */
     int32_t compact_pct;       /* decay phase: compact the survivors when fewer than this */
                                /* percentage of the visited slots is live (0 = default)  */
 } mcb_options;

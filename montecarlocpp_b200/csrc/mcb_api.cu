@@ -201,9 +201,8 @@ struct RunPlan {
 #ifndef MCB_ND_BALANCED
 #define MCB_ND_BALANCED 1      // N-D tally grids: the warp-balanced item walk (k_step NDM 3) instead of the per-lane serial walk
 #endif
-#ifndef MCB_TILES_PER_WARP
-#define MCB_TILES_PER_WARP 48
-#endif
+#define MCB_TILES_MIN 32
+#define MCB_TILES_MAX 96
 #ifndef MCB_DECAY_S
 #define MCB_DECAY_S 16         // loop trips per launch once nothing is left to emit (before the hazard is known)
 #endif
@@ -245,9 +244,15 @@ int plan_run(mcb_ctx* c, const mcb_problem_desc* prob, long long nparticles, Run
     r->block = o.block > 0 ? std::min(o.block, block_max) : block_max;
     if (r->block % 32 != 0 || o.block > 1024) { c->err = "block must be a multiple of 32, <= 1024"; return MCB_EINVAL; }
     r->S = o.steps_per_launch > 0 ? o.steps_per_launch : 16;
-    // streaming schedule: MCB_TILES_PER_WARP tiles per warp (5.5 M resident phonons for the 1-D kernels; 32 tiles: C1 -8 %, C3 -4 %:
-    // a launch is then so short that its fixed costs -- table staging, flush, emission tail -- weigh more; 64: C2 -4 %)
-    long long slots = o.slots > 0 ? o.slots : (long long)c->sm_count * r->block * MCB_TILES_PER_WARP;
+    // streaming schedule: 32 ... 96 tiles per warp, about a third of the solve's phonons (3.6 M ... 10.9 M resident phonons for the
+    // 1-D kernels).  Long launches dilute a launch's fixed costs (table staging, flush, emission tail: C3 at 1e8 phonons +9 % with
+    // 96 tiles instead of 32), while a population close to the whole problem would leave hardly any steady launches.
+    long long slots = o.slots;
+    if (slots <= 0) {
+        const long long per_tile = (long long)c->sm_count * r->block;
+        const long long t = (std::max<long long>(nparticles, 1) / 3 + per_tile - 1) / per_tile;
+        slots = per_tile * std::min<long long>(MCB_TILES_MAX, std::max<long long>(MCB_TILES_MIN, t));
+    }
     if (o.slots <= 0 && o.steps_per_launch <= 0) {
         // The library's default schedule (no options set) keeps EVERY phonon of the solve resident when the two state buffers fit
         // in half of the device memory that is available: the first fill emits them all with dense lanes and every launch then

@@ -8,20 +8,21 @@ d = tempfile.mkdtemp()
 mat = hostapi.Material(*materials.write_silicon(d, nw=1000))
 ctx = capi.Context(0); ctx.upload_material(mat.desc)
 tag = os.environ.get("AB_TAG", "")
+NEMIT = int(os.environ.get("AB_NEMIT") or "4000000")       # enough phonons that launch 21 (ncu -s 20) is a steady one
 for wl in (sys.argv[1:] or ["slab", "film", "wire"]):
     if wl == "slab":
         dom = hostapi.Domain("slab", [100e-9] * 3, [100, 0, 0], 1.0); prob = hostapi.FieldProblem(mat, dom, "multi", 10_000_000, 1000)
     elif wl == "wire":
-        dom = hostapi.Domain("wire", [1e-6, 1e-7, 1e-7], [0, 32, 32], 1.0); prob = hostapi.FieldProblem(mat, dom, "multi", 4_000_000, 100)
+        dom = hostapi.Domain("wire", [1e-6, 1e-7, 1e-7], [0, 32, 32], 1.0); prob = hostapi.FieldProblem(mat, dom, "multi", NEMIT, 100)
     elif wl == "tube":
-        dom = hostapi.Domain("tube", [1e-6, 5e-8, 5e-8, 2e-8], [0, 8, 8, 4], 1.0); prob = hostapi.FieldProblem(mat, dom, "multi", 4_000_000, 100)
+        dom = hostapi.Domain("tube", [1e-6, 5e-8, 5e-8, 2e-8], [0, 8, 8, 4], 1.0); prob = hostapi.FieldProblem(mat, dom, "multi", NEMIT, 100)
     elif wl == "bulk":
-        dom = hostapi.Domain("bulk", [1e-6] * 3, [128, 128, 128], 1.0); prob = hostapi.FieldProblem(mat, dom, "multi", 4_000_000, 100)
+        dom = hostapi.Domain("bulk", [1e-6] * 3, [128, 128, 128], 1.0); prob = hostapi.FieldProblem(mat, dom, "multi", NEMIT, 100)
     else:
-        dom = hostapi.Domain("film", [1e-6, 1e-7, 1e-6], [0, 20, 0], 1.0); prob = hostapi.FieldProblem(mat, dom, "multi", 4_000_000, 100)
+        dom = hostapi.Domain("film", [1e-6, 1e-7, 1e-6], [0, 20, 0], 1.0); prob = hostapi.FieldProblem(mat, dom, "multi", NEMIT, 100)
     ctx.upload_domain(dom.desc)
     raw = torch.zeros(prob.rows * dom.cols, dtype=torch.float64, device="cuda")
-    for S, k in ((1, 48), (16, 8)):
+    for S, k in ((1, 32), (16, 8)):
         extra = {k_: int(v_) for k_, v_ in (kv.split("=") for kv in os.environ.get("AB_OPTS", "").split())}
         blk = int(os.environ.get("AB_BLOCK") or "768")
         ctx.set_options(steps_per_launch=S, slots=148 * blk * k, **extra)

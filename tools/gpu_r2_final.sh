@@ -9,8 +9,8 @@ timeout 1200 python bench.py > gpurun_out/bench_ours.json 2> gpurun_out/bench_ou
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-side-configs > gpurun_out/ncu_launch.log 2>&1
 for w in slab film wire tube bulk; do
-  blk=768; case $w in wire|tube|bulk) blk=640;; esac      # the library's default slot count: 148 x CTA threads x 48 tiles (tools/ab_run.py)
-  AB_BLOCK=$blk timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_step -s 20 -c 1 -f -o gpurun_out/prof_r2_final_$w \
+  blk=768; case $w in wire|tube|bulk) blk=640;; esac      # the library's default slot count: 148 x CTA threads x 32 tiles (tools/ab_run.py)
+  AB_NEMIT=8000000 AB_BLOCK=$blk timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_step -s 20 -c 1 -f -o gpurun_out/prof_r2_final_$w \
       python tools/ab_run.py $w > gpurun_out/ncu_full_final_$w.log 2>&1
   tail -1 gpurun_out/ncu_full_final_$w.log
 done

@@ -22,5 +22,9 @@ for wl, key in KEY.items():
                            "warp_instructions": val("smsp__inst_executed.sum"), "registers": val("launch__registers_per_thread"),
                            "block": val("launch__block_size"), "smem_dynamic_bytes": val("launch__shared_mem_per_block_dynamic"),
                            "lanes_per_instruction": val("smsp__thread_inst_executed_per_inst_executed.ratio")}
+    k = out["kernels"][key]
+    k["slots"] = 148 * int(k["block"]) * 32                     # tools/ab_run.py: 32 tiles per warp in the captured launch
+    k["dram_bytes_per_slot"] = k["dram_bytes_per_launch"] / k["slots"]
+    k["warp_instructions_per_warp_step"] = k["warp_instructions"] / (k["slots"] / 32)
 json.dump(out, open("profiles/ncu_traffic.json", "w"), indent=1)
 print(json.dumps(out, indent=1))
