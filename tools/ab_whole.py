@@ -17,7 +17,7 @@ for wl in (sys.argv[1:] or ["slab", "film"]):
     raw = torch.zeros(prob.rows * dom.cols, dtype=torch.float64, device="cuda")
     tiles = int(os.environ.get("AB_TILES") or "0")            # tiles per warp (0: library default, 32)
     blk = 768 if wl in ("slab", "film") else 640
-    ctx.set_options(steps_per_launch=int(os.environ.get("AB_S") or "1"), slots=148 * blk * tiles)
+    ctx.set_options(steps_per_launch=int(os.environ.get("AB_S") or "1"), slots=148 * blk * tiles, compact_pct=int(os.environ.get("AB_COMPACT") or "0"))
     best = 1e9
     for rep in range(4):
         raw.zero_(); torch.cuda.synchronize()
