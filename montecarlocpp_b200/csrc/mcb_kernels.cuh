@@ -1,13 +1,14 @@
 // mcb_kernels.cuh — the CUDA kernels (sm_100a) of the phonon Monte Carlo hot path.
 //
-//   k_emit      K1 (dense): the next particles are emitted into the free slots listed by k_step (problem.cpp:386-399),
-//               one thread per particle, full warps; k_emit_commit advances the particle counter.
-//   k_step      K2: S trips of the loop body (problem.cpp:401-435) per resident slot: advect -> tally -> boundary or
-//               intrinsic scattering.  State streams HBM -> registers -> HBM once per launch.  Material + geometry tables
-//               are staged into shared memory with a TMA bulk copy (cp.async.bulk + mbarrier); tallies go to warp-private
-//               shared-memory histograms (flushed once per CTA), one histogram per CTA, or straight to L2 with fp64 RED.
-//               Template modes: payload rows, tally destination, N-D walk (none / serial / warp-cooperative), and EMIT
-//               (emission inside the kernel: used by mcb_trace and as an option).
+//   k_step      K2 with K1 fused in: S trips of the loop body (problem.cpp:401-435) per resident slot: advect -> tally ->
+//               boundary or intrinsic scattering; after its last tile every warp refills the slots that ended inactive with the
+//               next particles (problem.cpp:386-399).  State streams HBM -> registers -> HBM once per launch (TMA bulk
+//               prefetch of the warp's next 2304-B group).  Material + geometry tables are staged into shared memory with a
+//               TMA bulk copy (cp.async.bulk + mbarrier).  Tallies: 1-D grids -> fixed-point difference-array histograms in
+//               shared memory; N-D grids -> warp-balanced item walk into one fixed-point histogram per CTA, or straight to L2
+//               with fp64 RED.  Template modes: payload rows, tally destination, N-D walk (none / serial / serial +
+//               cooperative pieces / warp-balanced items), axis-aligned boxes only, padded histogram columns.
+//   k_emit      K1 for the first fill (every slot free): one thread per particle; k_emit_commit advances the particle counter.
 //   k_compact   K3: stream-compacts the active slots of the decay phase (no reference analogue; replaces the `break`s at
 //               problem.cpp:411,425,434).
 //   k_finalize  K4: postProc, / cellVol, * power_ (problem.cpp:439-444).
@@ -663,10 +664,9 @@ __global__ void __launch_bounds__(NDM == 3 ? MCB_BLOCK_MAX_ND3 : (NDM == 2 ? MCB
     // fixed-point histograms are flushed by the CTA between tiles at least every fx_flush_trips loop trips (the host keeps
     // steps_per_launch below that), which bounds the number of deposits an entry can receive (set_fixed_point, mcb_api.cu)
     int since_flush = 0;
-    // dense emission: free slots are only LISTED here; k_emit fills them between launches with full warps (emitting
-    // inside this kernel runs the long emission path for a few dead lanes per warp at ~5 % lane efficiency).  Every WARP
-    // appends to its own segment of the list (cursor = the warp's counter slot; a global cursor made every warp wait for
-    // a returning L2 atomic once per tile) and the CTA publishes the counts at the end.
+    // Free slots are only LISTED during the tile loop (refilling a slot the moment its phonon terminates would run the long
+    // emission path for a few dead lanes per warp at ~5 % lane efficiency).  Every WARP appends to its own segment of the list
+    // (cursor = the warp's counter slot; a global cursor made every warp wait for a returning L2 atomic once per tile).
     // K1 fused into the launch: a warp lists the slots that end inactive (its own segment of free_list) and, after its last
     // tile, emits the next particles into them with dense lanes (problem.cpp:386-399).  Particle ids come from one atomic
     // cursor (any slot may carry any particle: the Philox stream is keyed by the id), so no emission kernels run between the
@@ -821,8 +821,7 @@ __global__ void __launch_bounds__(NDM == 3 ? MCB_BLOCK_MAX_ND3 : (NDM == 2 ? MCB
             run_mask = __ballot_sync(0xFFFFFFFFu, ph.active());
         }
         if (was_active) ph.store_group(P.st, g, lane);
-        // end of the tile: list the slots that ended inactive (every slot of the group exists in memory; k_emit only takes
-        // ids below nslots), bump the warp's counters
+        // end of the tile: list the slots that ended inactive (only ids below nslots), bump the warp's counters
         const unsigned st_mask = __ballot_sync(0xFFFFFFFFu, was_active);
         const unsigned fm = list_free ? __ballot_sync(0xFFFFFFFFu, i < nslots) & ~run_mask : 0u;
         uint4 wc = make_uint4(0u, 0u, 0u, 0u);
