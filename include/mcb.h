@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MCB_ABI_VERSION 1
+#define MCB_ABI_VERSION 2
 
 /* error codes */
 #define MCB_OK          0
@@ -190,6 +190,8 @@ typedef struct mcb_stats {
     int64_t steady_steps;
     int64_t steady_stores;
     double  steady_ms;
+    int64_t compactions;       /* K3 passes over the survivors of the decay phase ... (ABI version 2) */
+    int64_t sorts;             /* ... of which were counting sorts by cell (mcb_options::sort_mode)     */
 } mcb_stats;
 
 /* Tunables of the device schedule (not part of the physics). 0 = library default.
@@ -215,6 +217,16 @@ typedef struct mcb_options {
     int32_t emit_mode;         /* must be 0 (emission is fused into the step kernel)      */
     int32_t compact_pct;       /* decay phase: compact the survivors when fewer than this */
                                /* percentage of the visited slots is live (0 = default)  */
+    int32_t sort_mode;         /* K3 with a key: 0 = unordered compaction (default);      */
+                               /* 1 = every compaction is a counting sort of the          */
+                               /*     survivors by (subdomain, tally cell), i.e. by the   */
+                               /*     field column their position lies in;                */
+                               /* k >= 2 = sort whenever the population has shrunk by a   */
+                               /*     factor k since the last sort, plain compaction      */
+                               /*     in between.  Results do not depend on the order     */
+                               /*     of the slots (the RNG stream is keyed by particle). */
+                               /* (the struct keeps its size: the field fills former     */
+                               /*  tail padding; ABI version 2)                           */
 } mcb_options;
 
 typedef struct mcb_ctx mcb_ctx;
@@ -334,6 +346,16 @@ typedef struct mcb_traj_out {
 } mcb_traj_out;
 
 int  mcb_traj(mcb_ctx* ctx, const mcb_traj_desc* traj, uint64_t seed, mcb_traj_out* out);
+
+/* K3 probe (no reference analogue: the reference's loop `break`s, problem.cpp:411,425,434, and never reorders phonons).
+ * Particles [n_begin, n_end) after emission and `nsteps` loop trips (no tally) are compacted -- unordered (sorted = 0) or
+ * by the counting sort behind mcb_options::sort_mode (sorted = 1) -- and the resulting slots are described in slot order:
+ * bin key, field column of the phonon's cell (Field::init column range of its subdomain + coord2index, field.cpp:25-45,
+ * subdomain.cpp:148-159) and particle id, -1 for an inactive slot.  Arrays of length n_end - n_begin; bin = column /
+ * *cols_per_bin.  Integer parity probe: the active slots are a permutation of the survivors, contiguous from slot 0, and
+ * with sorted = 1 their bins are non-decreasing. */
+int  mcb_sort_probe(mcb_ctx* ctx, const mcb_problem_desc* prob, uint64_t seed, int64_t n_begin, int64_t n_end,
+                    int64_t nsteps, int32_t sorted, int64_t* bin, int64_t* col, int64_t* pid, int64_t* cols_per_bin);
 
 /* Subdomain::coord + coord2index (subdomain.cpp:148-159) on caller-supplied
  * positions: bit-exact integer parity probe. pos [3n], sdom [n] -> index [3n]. */

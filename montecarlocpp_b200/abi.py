@@ -6,7 +6,7 @@ the CPU oracle.
 """
 import ctypes as C
 
-MCB_ABI_VERSION = 1
+MCB_ABI_VERSION = 2
 MCB_OK, MCB_EINVAL, MCB_ENODEVICE, MCB_ECUDA, MCB_ESTATE, MCB_ELIMIT = 0, -1, -2, -3, -4, -5
 BDRY_SPEC, BDRY_DIFF, BDRY_INTER, BDRY_ISOT, BDRY_PERI = range(5)
 SHAPE_NONE, SHAPE_PARALLELOGRAM, SHAPE_TRIANGLE, SHAPE_POLYGON = range(4)
@@ -75,7 +75,7 @@ class Stats(C.Structure):
                 ("device_ms", C.c_double), ("step_ms", C.c_double),
                 ("step_launches", C.c_int64), ("slot_steps", C.c_int64), ("state_stores", C.c_int64),
                 ("steady_launches", C.c_int64), ("steady_steps", C.c_int64), ("steady_stores", C.c_int64),
-                ("steady_ms", C.c_double)]
+                ("steady_ms", C.c_double), ("compactions", C.c_int64), ("sorts", C.c_int64)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -84,7 +84,7 @@ class Stats(C.Structure):
 class Options(C.Structure):
     _fields_ = [("slots", C.c_int64), ("steps_per_launch", C.c_int32), ("block", C.c_int32),
                 ("ctas_per_sm", C.c_int32), ("tally_mode", C.c_int32), ("decay_mode", C.c_int32),
-                ("emit_mode", C.c_int32), ("compact_pct", C.c_int32)]
+                ("emit_mode", C.c_int32), ("compact_pct", C.c_int32), ("sort_mode", C.c_int32)]
 
 
 class TraceOut(C.Structure):

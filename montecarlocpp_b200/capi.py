@@ -17,7 +17,7 @@ SYMBOLS = [
     "mcb_create", "mcb_destroy", "mcb_last_error", "mcb_abi_version", "mcb_build_info", "mcb_set_options", "mcb_get_options",
     "mcb_upload_material", "mcb_upload_domain", "mcb_field_cols", "mcb_solve", "mcb_solve_raw_dev",
     "mcb_finalize_dev", "mcb_stream", "mcb_trace", "mcb_cell_index", "mcb_accumulate", "mcb_get_alias",
-    "mcb_philox_words", "mcb_traj", "mcb_device_count", "mcb_solve_raw", "mcb_allreduce", "mcb_finalize",
+    "mcb_philox_words", "mcb_traj", "mcb_device_count", "mcb_solve_raw", "mcb_allreduce", "mcb_finalize", "mcb_sort_probe",
 ]
 
 _lib = None
@@ -51,6 +51,7 @@ def lib():
         L.mcb_stream.argtypes = [vp, C.POINTER(vp)]
         L.mcb_trace.argtypes = [vp, C.POINTER(abi.ProblemDesc), C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.POINTER(abi.TraceOut)]
         L.mcb_traj.argtypes = [vp, C.POINTER(abi.TrajDesc), C.c_uint64, C.POINTER(abi.TrajOut)]
+        L.mcb_sort_probe.argtypes = [vp, C.POINTER(abi.ProblemDesc), C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, lp, lp, lp, lp]
         L.mcb_cell_index.argtypes = [vp, C.c_int64, dp, ip, lp]
         L.mcb_accumulate.argtypes = [vp, C.c_int32, C.c_int64, ip, dp, dp, dp, dp]
         L.mcb_get_alias.argtypes = [vp, C.c_int, dp, ip, dp, ip]
@@ -132,6 +133,16 @@ class Context:
         bufs, out = abi.trace_buffers(n_end - n_begin)
         self._check(lib().mcb_trace(self.h, C.byref(prob_desc), seed, n_begin, n_end, nsteps, C.byref(out)))
         return bufs
+
+    def sort_probe(self, prob_desc, seed, n_begin, n_end, nsteps, sorted_=True):
+        """K3 probe: (bin, column, particle id) per slot after compaction / the counting sort, and columns per bin."""
+        n = n_end - n_begin
+        b, c, p = (np.zeros(n, np.int64) for _ in range(3))
+        cpb = C.c_int64(0)
+        self._check(lib().mcb_sort_probe(self.h, C.byref(prob_desc), seed, n_begin, n_end, nsteps, 1 if sorted_ else 0,
+                                         b.ctypes.data_as(abi.c_int64_p), c.ctypes.data_as(abi.c_int64_p),
+                                         p.ctypes.data_as(abi.c_int64_p), C.byref(cpb)))
+        return b, c, p, cpb.value
 
     def traj(self, traj_desc, seed):
         bufs, out = abi.traj_buffers(traj_desc.maxloop)

@@ -123,6 +123,7 @@ struct mcb_ctx {
     Counters* d_hctr = nullptr;                          // ... its device address
     DevBuf<double> field;
     DevBuf<uint32_t> free_list;  // fused emission: per-warp segments of free slot ids
+    DevBuf<uint32_t> sort_keys, sort_bins;   // K3 with a key (mcb_options::sort_mode): bin of every slot, bin counts / cursors
 };
 
 namespace {
@@ -381,6 +382,37 @@ int upload_cdf(mcb_ctx* c, const mcb_problem_desc* prob) {
     return MCB_OK;
 }
 
+// K3: move the active slots of state[cur] (the first `nslots`) to the front of state[other], whose first `bound` slots are
+// cleared first (bound >= number of active slots).  sorted = false: unordered stream compaction (k_compact); true: counting
+// sort by (subdomain, tally cell) bin (k_sort_count / k_sort_scan / k_sort_scatter, mcb_kernels.cuh).
+void sort_geometry(const mcb_ctx* c, uint32_t* cols_per_bin, uint32_t* nbins) {
+    const long long cols = std::max<long long>(c->cols, 1);
+    *cols_per_bin = (uint32_t)((cols + MCB_SORT_MAX_BINS - 1) / MCB_SORT_MAX_BINS);
+    *nbins = (uint32_t)((cols + *cols_per_bin - 1) / *cols_per_bin);
+}
+int compact_slots(mcb_ctx* c, int cur, long long nslots, long long bound, bool sorted, long long* launches) {
+    const int other = cur ^ 1;
+    const unsigned grid = (unsigned)std::min<long long>((nslots + 255) / 256, (long long)c->sm_count * 8);
+    CUDA_TRY(c, cudaMemsetAsync(&c->ctr.p->compact_cursor, 0, sizeof(unsigned long long), c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(c->state[other].p, 0, state_bytes(bound), c->stream));
+    if (!sorted) {
+        k_compact<<<grid, 256, 0, c->stream>>>(view_of(c, cur), view_of(c, other), nslots, c->ctr.p);
+        CUDA_TRY(c, cudaGetLastError());
+        *launches += 1;
+        return MCB_OK;
+    }
+    uint32_t cpb, nbins; sort_geometry(c, &cpb, &nbins);
+    CUDA_TRY(c, c->sort_keys.alloc((size_t)nslots)); CUDA_TRY(c, c->sort_bins.alloc(nbins));
+    if (nbins * 4u > 48u * 1024u) CUDA_TRY(c, cudaFuncSetAttribute(k_sort_count, cudaFuncAttributeMaxDynamicSharedMemorySize, MCB_SORT_MAX_BINS * 4));
+    CUDA_TRY(c, cudaMemsetAsync(c->sort_bins.p, 0, (size_t)nbins * 4, c->stream));
+    k_sort_count<<<grid, 256, (size_t)nbins * 4, c->stream>>>(view_of(c, cur), nslots, c->geo_blob.p, c->gv, cpb, nbins, c->sort_keys.p, c->sort_bins.p);
+    k_sort_scan<<<1, 1024, 0, c->stream>>>(c->sort_bins.p, nbins, &c->ctr.p->compact_cursor);
+    k_sort_scatter<<<grid, 256, 0, c->stream>>>(view_of(c, cur), view_of(c, other), nslots, c->sort_keys.p, c->sort_bins.p);
+    CUDA_TRY(c, cudaGetLastError());
+    *launches += 3;
+    return MCB_OK;
+}
+
 // The schedule: launches of k_step over the resident slots until every particle of
 // [n_begin, n_end) has been emitted and has terminated; the tail is compacted.
 int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n_begin, int64_t n_end,
@@ -430,7 +462,7 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
         }
     }
     const long long compact_pct = c->opt.compact_pct > 0 ? c->opt.compact_pct : MCB_COMPACT_PCT;
-    long long steady_launches = 0; float steady_ms = 0.f;
+    long long steady_launches = 0, compactions = 0, sorts = 0, sorted_pop = nslots; float steady_ms = 0.f;
     unsigned long long steady_steps = 0, steady_stores = 0, prev_steps = 0, prev_stores = 0;
     if (total > 0) for (long long it = 0;; ++it) {
         const int slot = (int)(it & 1);
@@ -478,15 +510,15 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
         if (all_emitted && (long long)live * 100 < nslots * compact_pct && nslots > tail_slots) {
             // tail: compact the survivors so later launches stream only live state.  `live` is one launch old,
             // i.e. an upper bound (nothing is emitted any more); unused destination slots stay inactive.
-            const int other = cur ^ 1;
+            // sort_mode: the compaction is a counting sort by (subdomain, tally cell) -- always (1), or whenever the
+            // population has shrunk by the factor sort_mode since the last sort
             const long long bound = std::max<long long>((long long)live, 1);
-            CUDA_TRY(c, cudaMemsetAsync(&c->ctr.p->compact_cursor, 0, sizeof(unsigned long long), c->stream));
-            CUDA_TRY(c, cudaMemsetAsync(c->state[other].p, 0, state_bytes(bound), c->stream));
-            k_compact<<<(unsigned)std::min<long long>((nslots + 255) / 256, (long long)c->sm_count * 8), 256, 0, c->stream>>>(
-                view_of(c, cur), view_of(c, other), nslots, c->ctr.p);
-            CUDA_TRY(c, cudaGetLastError());
-            launches++;
-            cur = other; nslots = bound;
+            const int sm = c->opt.sort_mode;
+            const bool sorted = sm == 1 || (sm >= 2 && bound * sm <= sorted_pop);
+            if ((rc = compact_slots(c, cur, nslots, bound, sorted, &launches))) return rc;
+            compactions++;
+            if (sorted) { sorts++; sorted_pop = bound; }
+            cur ^= 1; nslots = bound;
         }
         // decay phase (nothing left to emit): launches are no longer full, so amortise them over >= 16 loop trips;
         // once the survivors fit one tile per CTA let every thread run its phonon to termination
@@ -512,6 +544,7 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
         stats->step_launches = step_launches; stats->slot_steps = slot_steps; stats->state_stores = (int64_t)c->h_ctr[0].stores;
         stats->steady_launches = steady_launches; stats->steady_steps = (int64_t)steady_steps;
         stats->steady_stores = (int64_t)steady_stores; stats->steady_ms = steady_ms;
+        stats->compactions = compactions; stats->sorts = sorts;
     }
     return MCB_OK;
 }
@@ -573,7 +606,7 @@ void mcb_destroy(mcb_ctx* c) {
     c->mat_blob.release(); c->f_wprob.release(); c->f_pprob.release(); c->f_walias.release(); c->f_palias.release();
     c->geo_blob.release(); c->emitters.release(); c->cell_vol.release(); c->emit_cdf.release();
     for (int w = 0; w < 2; ++w) c->state[w].release();
-    c->ctr.release(); c->field.release(); c->free_list.release();
+    c->ctr.release(); c->field.release(); c->free_list.release(); c->sort_keys.release(); c->sort_bins.release();
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
     if (c->ev0) cudaEventDestroy(c->ev0); if (c->ev1) cudaEventDestroy(c->ev1);
     for (int k = 0; k < 2; ++k) { if (c->evA[k]) cudaEventDestroy(c->evA[k]); if (c->evB[k]) cudaEventDestroy(c->evB[k]); if (c->evC[k]) cudaEventDestroy(c->evC[k]); }
@@ -583,7 +616,7 @@ void mcb_destroy(mcb_ctx* c) {
 
 int mcb_set_options(mcb_ctx* c, const mcb_options* o) {
     if (!c || !o) return MCB_EINVAL;
-    if (o->slots < 0 || o->steps_per_launch < 0 || o->block < 0 || o->ctas_per_sm < 0 || o->tally_mode < 0 || o->tally_mode > 3 || o->decay_mode < 0 || o->decay_mode > 1 || o->emit_mode != 0 || o->compact_pct < 0 || o->compact_pct > 100) {
+    if (o->slots < 0 || o->steps_per_launch < 0 || o->block < 0 || o->ctas_per_sm < 0 || o->tally_mode < 0 || o->tally_mode > 3 || o->decay_mode < 0 || o->decay_mode > 1 || o->emit_mode != 0 || o->compact_pct < 0 || o->compact_pct > 100 || o->sort_mode < 0) {
         c->err = "negative / unknown option"; return MCB_EINVAL;
     }
     c->opt = *o;
@@ -971,6 +1004,36 @@ int mcb_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
     return MCB_OK;
 }
 
+// the production kernels without the tally: every particle of the range is emitted into its own slot of state[0] (k_emit),
+// then one k_step launch runs `nsteps` loop trips (mcb_trace, mcb_sort_probe)
+// stop_after: the loop bound is cut to `nsteps` (every phonon ends inactive, mcb_trace); else the survivors stay active
+static int trace_run(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n_begin, int64_t n_end, int64_t nsteps, bool stop_after, StepParams* Pout) {
+    const long long n = n_end - n_begin;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    RunPlan plan;
+    mcb_options saved = c->opt; c->opt.slots = n; c->opt.tally_mode = 2; c->opt.block = 0;
+    int rc = plan_run(c, prob, n, &plan);
+    c->opt = saved;
+    if (rc) return rc;
+    if ((rc = ensure_slots(c, n))) return rc;
+    if ((rc = upload_cdf(c, prob))) return rc;
+    StepParams& P = *Pout; fill_params(c, prob, seed, &P);
+    apply_plan(plan, prob, &P);
+    if (stop_after) { P.maxloop = std::min<long long>(prob->maxloop, nsteps); P.maxloop32 = (uint32_t)P.maxloop; }
+    const long long trips = std::min<long long>(prob->maxloop, nsteps);
+    P.field = nullptr; P.do_tally = 0;
+    P.steps_per_launch = (int)std::max<long long>(1, std::min<long long>(trips, 0x7FFFFFFF)); P.n_end = (unsigned long long)n_end;
+    P.st = view_of(c, 0); P.nslots = n; P.emit_enable = 0;
+    Counters init{}; init.next = (unsigned long long)n_begin;
+    CUDA_TRY(c, cudaMemcpyAsync(c->ctr.p, &init, sizeof init, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(c->state[0].p, 0, state_bytes(c->slots_alloc), c->stream));
+    k_emit<<<(unsigned)(c->sm_count * 8), 256, 0, c->stream>>>(P);     // first fill: particle n_begin + j into slot j
+    k_emit_commit<<<1, 32, 0, c->stream>>>(P);
+    CUDA_TRY(c, cudaGetLastError());
+    if (trips > 0) CUDA_TRY(c, launch_step(P, plan.tm, plan.ndm, c->all_box, plan.pad, plan.grid, plan.block, plan.smem, c->stream));
+    return MCB_OK;
+}
+
 int mcb_trace(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n_begin, int64_t n_end, int64_t nsteps,
               mcb_trace_out* o) {
     if (!c) return MCB_EINVAL;
@@ -979,29 +1042,8 @@ int mcb_trace(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
     if (!o || n_begin < 0 || n_end > prob->nemit || n_begin > n_end || nsteps < 0) { c->err = "bad trace arguments"; return MCB_EINVAL; }
     const long long n = n_end - n_begin;
     if (n == 0) return MCB_OK;
-    CUDA_TRY(c, cudaSetDevice(c->device));
-    // the production kernels without the tally: every particle of the range is emitted into its own slot (k_emit), then
-    // one k_step launch runs `nsteps` loop trips
-    RunPlan plan;
-    mcb_options saved = c->opt; c->opt.slots = n; c->opt.tally_mode = 2; c->opt.block = 0;
-    rc = plan_run(c, prob, n, &plan);
-    c->opt = saved;
-    if (rc) return rc;
-    if ((rc = ensure_slots(c, n))) return rc;
-    if ((rc = upload_cdf(c, prob))) return rc;
-    StepParams P; fill_params(c, prob, seed, &P);
-    apply_plan(plan, prob, &P);
-    P.maxloop = std::min<long long>(prob->maxloop, nsteps); P.maxloop32 = (uint32_t)P.maxloop;
-    P.field = nullptr; P.do_tally = 0;
-    P.steps_per_launch = (int)std::max<long long>(1, std::min<long long>(P.maxloop, 0x7FFFFFFF)); P.n_end = (unsigned long long)n_end;
-    P.st = view_of(c, 0); P.nslots = n; P.emit_enable = 0;
-    Counters init{}; init.next = (unsigned long long)n_begin;
-    CUDA_TRY(c, cudaMemcpyAsync(c->ctr.p, &init, sizeof init, cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(c, cudaMemsetAsync(c->state[0].p, 0, state_bytes(c->slots_alloc), c->stream));
-    k_emit<<<(unsigned)(c->sm_count * 8), 256, 0, c->stream>>>(P);     // first fill: particle n_begin + j into slot j
-    k_emit_commit<<<1, 32, 0, c->stream>>>(P);
-    CUDA_TRY(c, cudaGetLastError());
-    if (P.maxloop > 0) CUDA_TRY(c, launch_step(P, plan.tm, plan.ndm, c->all_box, plan.pad, plan.grid, plan.block, plan.smem, c->stream));
+    StepParams P;
+    if ((rc = trace_run(c, prob, seed, n_begin, n_end, nsteps, true, &P))) return rc;
     DevBuf<double> dpos, ddir, dsn; DevBuf<long long> dw, dp, dnscat, dsteps; DevBuf<int32_t> dsign, dalive, dsdom, dcell;
     CUDA_TRY(c, dpos.alloc(3 * n)); CUDA_TRY(c, ddir.alloc(3 * n)); CUDA_TRY(c, dsn.alloc(n));
     CUDA_TRY(c, dw.alloc(n)); CUDA_TRY(c, dp.alloc(n)); CUDA_TRY(c, dnscat.alloc(n)); CUDA_TRY(c, dsteps.alloc(n));
@@ -1018,6 +1060,34 @@ int mcb_trace(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
 #undef MCB_COPY_OUT
     dpos.release(); ddir.release(); dsn.release(); dw.release(); dp.release(); dnscat.release(); dsteps.release();
     dsign.release(); dalive.release(); dsdom.release(); dcell.release();
+    return MCB_OK;
+}
+
+// K3 probe: the particles [n_begin, n_end) after emission and `nsteps` loop trips (no tally) are compacted -- unordered
+// (sorted = 0) or by the counting sort of mcb_options::sort_mode (sorted = 1) -- and the resulting slots are described in slot
+// order: bin key, field column and particle id (-1: inactive slot).  Parity probe for the integer work of the sort.
+int mcb_sort_probe(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n_begin, int64_t n_end, int64_t nsteps,
+                   int32_t sorted, int64_t* bin, int64_t* col, int64_t* pid, int64_t* cols_per_bin) {
+    if (!c) return MCB_EINVAL;
+    int rc = check_problem(c, prob);
+    if (rc) return rc;
+    if (!bin || !col || !pid || n_begin < 0 || n_end > prob->nemit || n_begin > n_end || nsteps < 0) { c->err = "bad sort-probe arguments"; return MCB_EINVAL; }
+    const long long n = n_end - n_begin;
+    uint32_t cpb, nbins; sort_geometry(c, &cpb, &nbins);
+    if (cols_per_bin) *cols_per_bin = cpb;
+    if (n == 0) return MCB_OK;
+    StepParams P;
+    if ((rc = trace_run(c, prob, seed, n_begin, n_end, nsteps, false, &P))) return rc;
+    long long launches = 0;
+    if ((rc = compact_slots(c, 0, n, n, sorted != 0, &launches))) return rc;
+    DevBuf<long long> dbin, dcol, dpid;
+    CUDA_TRY(c, dbin.alloc(n)); CUDA_TRY(c, dcol.alloc(n)); CUDA_TRY(c, dpid.alloc(n));
+    k_sort_probe<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(view_of(c, 1), n, c->geo_blob.p, c->gv, cpb, nbins, P.step_bits, dbin.p, dcol.p, dpid.p);
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaMemcpy(bin, dbin.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(c, cudaMemcpy(col, dcol.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(c, cudaMemcpy(pid, dpid.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
     return MCB_OK;
 }
 

@@ -999,6 +999,96 @@ __global__ void k_compact(StateView src, StateView dst, long long n, Counters* c
     }
 }
 
+// ------------------------------------------------------------------------------ k_sort_*
+// K3 with a key (mcb_options::sort_mode): the survivors are compacted AND ordered by (subdomain, tally cell), i.e. by the
+// field column their position lies in -- Field::init gives every subdomain a contiguous column range (field.cpp:25-45) and
+// a cell the column  offset + sum_d coord2index(coord(pos))_d * stride_d  (subdomain.cpp:148-159, field.cpp:38).  A counting
+// sort in three launches, every one of them over the slots the step kernel would visit:
+//   k_sort_count    key (bin = column / cols_per_bin, at most MCB_SORT_MAX_BINS bins) of every active slot; per-CTA histogram
+//                   in shared memory, then one global atomic per non-empty bin and CTA; the key is kept per slot (4 B)
+//   k_sort_scan     exclusive prefix sum of the bin counts by one CTA -> the first destination slot of every bin
+//   k_sort_scatter  every active slot takes the next destination slot of its bin (atomic cursor per bin) and is moved there
+// Slots of one bin end up contiguous; their order inside the bin is the order of the atomics (like k_compact's cursor, it
+// only permutes the summation order of the tallies: the RNG stream of a phonon is keyed by its particle id).
+#define MCB_SORT_MAX_BINS 16384
+#define MCB_SORT_NOKEY 0xFFFFFFFFu
+__device__ __forceinline__ long long sort_column(const DSdom& sd, double px, double py, double pz) {
+    if (sd.col_offset < 0) return 0;                                  // subdomain without cells: any bin
+    double c[3]; sdom_coord(sd, px, py, pz, c);
+    return (long long)sd.col_offset + coord2index1(c[0], sd.max[0]) + (long long)coord2index1(c[1], sd.max[1]) * sd.stride1 +
+           (long long)coord2index1(c[2], sd.max[2]) * sd.stride2;
+}
+__global__ void __launch_bounds__(256) k_sort_count(StateView src, long long n, const unsigned char* geo_blob, GeometryView gv,
+                                                    uint32_t cols_per_bin, uint32_t nbins, uint32_t* keys, uint32_t* bins) {
+    extern __shared__ uint32_t s_bins[];
+    for (uint32_t b = threadIdx.x; b < nbins; b += blockDim.x) s_bins[b] = 0u;
+    __syncthreads();
+    const DSdom* sds = reinterpret_cast<const DSdom*>(geo_blob + gv.off_sdom);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        // position and meta only: three of the slot's five pieces
+        const unsigned char* v = Particle::vec_ptr(src, i);
+        double px, py, pz, dx, sn; unsigned long long m;
+        ld_stream2(v + 1536, sn, m);
+        uint32_t key = MCB_SORT_NOKEY;
+        if (MCB_META_ACTIVE(m)) {
+            ld_stream2(v, px, py); ld_stream2(v + 512, pz, dx);
+            key = (uint32_t)(sort_column(sds[MCB_META_SDOM(m)], px, py, pz) / cols_per_bin);
+            key = min(key, nbins - 1u);
+            atomicAdd(&s_bins[key], 1u);
+        }
+        keys[i] = key;
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < nbins; b += blockDim.x) { const uint32_t v = s_bins[b]; if (v) atomicAdd(&bins[b], v); }
+}
+// one CTA of 1024 threads: bins[b] <- number of active slots in bins < b; total[0] <- number of active slots
+__global__ void __launch_bounds__(1024) k_sort_scan(uint32_t* bins, uint32_t nbins, unsigned long long* total) {
+    __shared__ uint32_t s_part[1024];
+    const uint32_t per = (nbins + 1023u) / 1024u, b0 = threadIdx.x * per, b1 = min(nbins, b0 + per);
+    uint32_t sum = 0;
+    for (uint32_t b = b0; b < b1; ++b) sum += bins[b];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    for (uint32_t o = 1; o < 1024u; o <<= 1) {                       // inclusive scan of the per-thread sums
+        const uint32_t v = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0u;
+        __syncthreads();
+        s_part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = s_part[threadIdx.x] - sum;
+    for (uint32_t b = b0; b < b1; ++b) { const uint32_t v = bins[b]; bins[b] = run; run += v; }
+    if (threadIdx.x == 1023u) *total = (unsigned long long)s_part[1023];
+}
+__global__ void __launch_bounds__(256) k_sort_scatter(StateView src, StateView dst, long long n, const uint32_t* keys, uint32_t* bins) {
+    const unsigned lane = threadIdx.x & 31u;
+    for (long long base = (long long)blockIdx.x * blockDim.x; base < n; base += (long long)gridDim.x * blockDim.x) {
+        const long long i = base + threadIdx.x;                      // the trip count is uniform across the CTA
+        const uint32_t key = i < n ? keys[i] : MCB_SORT_NOKEY;
+        // lanes of a warp that share the bin take consecutive destination slots with ONE atomic (neighbouring source slots of
+        // an already sorted population mostly do)
+        const unsigned peers = __match_any_sync(0xFFFFFFFFu, key);
+        if (key == MCB_SORT_NOKEY) continue;
+        Particle ph; ph.load(src, i);
+        const int leader = __ffs(peers) - 1;
+        uint32_t pos = 0;
+        if ((int)lane == leader) pos = atomicAdd(&bins[key], (uint32_t)__popc(peers));
+        pos = __shfl_sync(peers, pos, leader) + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+        ph.store(dst, (long long)pos);
+    }
+}
+// diagnostic behind mcb_sort_probe: bin key, field column and particle id of every slot (slot order); -1 for inactive slots
+__global__ void k_sort_probe(StateView st, long long n, const unsigned char* geo_blob, GeometryView gv, uint32_t cols_per_bin,
+                             uint32_t nbins, uint32_t step_bits, long long* bin, long long* col, long long* pid) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Particle ph; const unsigned long long m = ph.load(st, i);
+    bin[i] = col[i] = pid[i] = -1;
+    if (!MCB_META_ACTIVE(m)) return;
+    const DSdom* sds = reinterpret_cast<const DSdom*>(geo_blob + gv.off_sdom);
+    const long long cc = sort_column(sds[MCB_META_SDOM(m)], ph.px, ph.py, ph.pz);
+    col[i] = cc; bin[i] = (long long)min((uint32_t)(cc / cols_per_bin), nbins - 1u); pid[i] = (long long)(ph.ps >> step_bits);
+}
+
 // --------------------------------------------------------------------------- k_finalize
 // problem.cpp:439-444: postProc (problem.cpp:478-481,511-514,546-551,591-599,639-648), / cellVol, * power_
 __global__ void k_finalize(double* field, int rows, long long cols, int kind, long long size,

@@ -17,10 +17,12 @@ for wl in (sys.argv[1:] or ["slab", "film"]):
     raw = torch.zeros(prob.rows * dom.cols, dtype=torch.float64, device="cuda")
     tiles = int(os.environ.get("AB_TILES") or "0")            # tiles per warp (0: library default, 32)
     blk = 768 if wl in ("slab", "film") else 640
-    ctx.set_options(steps_per_launch=int(os.environ.get("AB_S") or "1"), slots=148 * blk * tiles, compact_pct=int(os.environ.get("AB_COMPACT") or "0"))
+    ctx.set_options(steps_per_launch=int(os.environ.get("AB_S") or "1"), slots=148 * blk * tiles, compact_pct=int(os.environ.get("AB_COMPACT") or "0"),
+                    sort_mode=int(os.environ.get("AB_SORT") or "0"))
     best = 1e9
     for rep in range(4):
         raw.zero_(); torch.cuda.synchronize()
         t = time.perf_counter(); st = ctx.solve_raw_dev(prob.desc, raw.data_ptr(), seed=rep); dt = time.perf_counter() - t
         if rep: best = min(best, dt)
-    print(f"  {tag:10s} {wl}: whole solve {st['steps']/best:.3e} steps/s  {best*1e3:7.1f} ms  launches {st['launches']}  k_step {st['step_ms']:.1f} ms (steady {st['steady_ms']:.1f})", flush=True)
+    print(f"  {tag:10s} {wl}: whole solve {st['steps']/best:.3e} steps/s  {best*1e3:7.1f} ms  launches {st['launches']}  k_step {st['step_ms']:.1f} ms (steady {st['steady_ms']:.1f})"
+          f"  compactions {st['compactions']} sorts {st['sorts']}", flush=True)
