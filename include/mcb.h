@@ -192,6 +192,10 @@ typedef struct mcb_stats {
     double  steady_ms;
     int64_t compactions;       /* K3 passes over the survivors of the decay phase ... (ABI version 2) */
     int64_t sorts;             /* ... of which were counting sorts by cell (mcb_options::sort_mode)     */
+    /* the TAIL: launches that run the last survivors (at most one tile per CTA) to termination; their duration is set by
+     * the longest remaining history (a phonon's loop trips are sequential), not by throughput */
+    double  tail_ms;
+    int64_t tail_steps;
 } mcb_stats;
 
 /* Tunables of the device schedule (not part of the physics). 0 = library default.
@@ -211,9 +215,13 @@ typedef struct mcb_options {
                                /* arrays / one per CTA), 2 global field (fp64 RED in L2), */
                                /* 3 one histogram per CTA                                 */
     int32_t decay_mode;        /* 0: once nothing is left to emit choose S per launch    */
-                               /*    from the measured termination rate, compact, then    */
-                               /*    run the last survivors to termination;               */
-                               /* 1: keep steps_per_launch throughout (compaction only)  */
+                               /*    from the measured termination rate; every launch     */
+                               /*    stores its survivors densely (compaction fused into  */
+                               /*    the step kernel); the last survivors run to the end; */
+                               /* 1: keep steps_per_launch throughout, separate           */
+                               /*    compaction passes;                                   */
+                               /* 2: like 0 with separate compaction passes (round-2      */
+                               /*    schedule, kept for A/B)                              */
     int32_t emit_mode;         /* must be 0 (emission is fused into the step kernel)      */
     int32_t compact_pct;       /* decay phase: compact the survivors when fewer than this */
                                /* percentage of the visited slots is live (0 = default)  */
@@ -225,9 +233,11 @@ typedef struct mcb_options {
                                /*     factor k since the last sort, plain compaction      */
                                /*     in between.  Results do not depend on the order     */
                                /*     of the slots (the RNG stream is keyed by particle). */
-                               /* (the struct keeps its size: the field fills former     */
-                               /*  tail padding; ABI version 2)                           */
-} mcb_options;
+                               /* A sort is its own pass (decay_mode 0 then behaves as 2) */
+    int32_t decay_pct;         /* decay phase: share (%) of the live phonons that may     */
+                               /* terminate per launch when S is chosen (0 = default: 12  */
+                               /* with the fused compaction, 30 with separate passes)     */
+} mcb_options;                 /* sort_mode, decay_pct: ABI version 2 */
 
 typedef struct mcb_ctx mcb_ctx;
 

@@ -75,7 +75,8 @@ class Stats(C.Structure):
                 ("device_ms", C.c_double), ("step_ms", C.c_double),
                 ("step_launches", C.c_int64), ("slot_steps", C.c_int64), ("state_stores", C.c_int64),
                 ("steady_launches", C.c_int64), ("steady_steps", C.c_int64), ("steady_stores", C.c_int64),
-                ("steady_ms", C.c_double), ("compactions", C.c_int64), ("sorts", C.c_int64)]
+                ("steady_ms", C.c_double), ("compactions", C.c_int64), ("sorts", C.c_int64),
+                ("tail_ms", C.c_double), ("tail_steps", C.c_int64)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -84,7 +85,7 @@ class Stats(C.Structure):
 class Options(C.Structure):
     _fields_ = [("slots", C.c_int64), ("steps_per_launch", C.c_int32), ("block", C.c_int32),
                 ("ctas_per_sm", C.c_int32), ("tally_mode", C.c_int32), ("decay_mode", C.c_int32),
-                ("emit_mode", C.c_int32), ("compact_pct", C.c_int32), ("sort_mode", C.c_int32)]
+                ("emit_mode", C.c_int32), ("compact_pct", C.c_int32), ("sort_mode", C.c_int32), ("decay_pct", C.c_int32), ("pad_", C.c_int32)]
 
 
 class TraceOut(C.Structure):

@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -212,6 +213,16 @@ struct RunPlan {
 #endif
 #define MCB_DECAY_S_MIN 4
 #define MCB_DECAY_S_MAX 64
+// decay phase with the compaction fused into k_step (the default): every launch stores its survivors densely, so a launch may
+// be short -- about this share of the live phonons terminates per launch (the lanes of a tile are 1 - share / 2 occupied on
+// average) -- as long as it still carries enough loop trips to dilute its fixed costs (table staging, flush, launch gap)
+#ifndef MCB_DECAY_FUSED_PCT
+#define MCB_DECAY_FUSED_PCT 12
+#endif
+#define MCB_DECAY_FUSED_S_MIN 2
+#ifndef MCB_DECAY_MIN_WORK
+#define MCB_DECAY_MIN_WORK 4000000ll   // phonon-steps per launch (~150 us)
+#endif
 #ifndef MCB_COMPACT_PCT
 #define MCB_COMPACT_PCT 90
 #endif
@@ -462,6 +473,18 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
         }
     }
     const long long compact_pct = c->opt.compact_pct > 0 ? c->opt.compact_pct : MCB_COMPACT_PCT;
+    // decay_mode 0 (default): K3 is fused into k_step -- once nothing is left to emit every launch stores its survivors densely
+    // into the other state buffer (StepParams::compact) and the launch behind it reads the slot count from device memory, so the
+    // host's one-launch-old counters never leave dead lanes in a tile.  Modes 1 / 2 (and the sorting compaction) keep the separate
+    // K3 pass of round 2: a launch then visits the survivors of the launch BEFORE the previous one.
+    const bool fused = c->opt.decay_mode == 0 && c->opt.sort_mode == 0;
+    const int decay_pct = c->opt.decay_pct > 0 ? c->opt.decay_pct : (fused ? MCB_DECAY_FUSED_PCT : MCB_DECAY_ADAPT_PCT);
+    bool prev_compacting = false;
+    // tail accounting: launches that run the last survivors (at most one tile per CTA) to termination are bound by the
+    // length of the longest history, not by throughput (mcb_stats::tail_ms / tail_steps)
+    bool tail_launch[2] = {false, false}, tail_next = false; float tail_ms = 0.f; unsigned long long tail_steps = 0;
+    static const bool launch_log = std::getenv("MCB_LAUNCH_LOG") != nullptr;      // per-launch trace on stderr (diagnostic)
+    long long log_nslots[2] = {0, 0}; int log_S[2] = {0, 0};
     long long steady_launches = 0, compactions = 0, sorts = 0, sorted_pop = nslots; float steady_ms = 0.f;
     unsigned long long steady_steps = 0, steady_stores = 0, prev_steps = 0, prev_stores = 0;
     if (total > 0) for (long long it = 0;; ++it) {
@@ -474,17 +497,22 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
         // K1: the first fill (every slot free) is its own dense kernel; afterwards k_step refills the slots that end inactive
         // itself (32 at a time, ids from the atomic cursor Counters::next) while particles are left to emit
         P.emit_enable = (host_all_emitted || !P.free_list) ? 0 : 1;
+        const bool compacting = fused && !P.emit_enable;
+        P.compact = compacting ? 1 : 0; P.st_out = view_of(c, cur ^ 1); P.use_dev_n = (compacting && prev_compacting) ? 1 : 0;
         if (it == 0) {
             k_emit<<<(unsigned)(c->sm_count * 8), 256, 0, c->stream>>>(P);
             k_emit_commit<<<1, 32, 0, c->stream>>>(P);
             CUDA_TRY(c, cudaGetLastError());
             launches += 2;
         }
+        tail_launch[slot] = tail_next; log_nslots[slot] = nslots; log_S[slot] = S_cur;
         CUDA_TRY(c, cudaEventRecord(c->evA[slot], c->stream));
         CUDA_TRY(c, launch_step(P, plan.tm, plan.ndm, c->all_box, plan.pad, grid, plan.block, plan.smem, c->stream));
         CUDA_TRY(c, cudaEventRecord(c->evB[slot], c->stream));
         // the launch's last CTA has mirrored the counters into h_ctr[slot] (StepParams::host_ctr): evB is all the host waits for
         launches++; step_launches++; slot_steps += nslots * (long long)std::min<long long>(S_cur, prob->maxloop);
+        const bool before_compacted = prev_compacting;            // launch it-1
+        if (compacting) { cur ^= 1; prev_compacting = true; }      // the launch behind this one reads what this one writes
         if (it == 0) continue;
         const int prev = slot ^ 1;
         CUDA_TRY(c, cudaEventSynchronize(c->evB[prev]));
@@ -498,6 +526,9 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
         }
         // hazard of the population in launch it-1 (fraction of the live phonons that terminated per loop trip): sets the decay S below
         const unsigned long long dsteps = c->h_ctr[prev].steps - prev_steps;
+        if (tail_launch[prev]) { tail_ms += ms; tail_steps += dsteps; }
+        if (launch_log) std::fprintf(stderr, "mcb launch %lld: slots<=%lld S=%d %.3f ms, %llu steps, live after %llu%s\n", it - 1, log_nslots[prev], log_S[prev],
+                                     ms, dsteps, live, tail_launch[prev] ? " (tail)" : "");
         double hazard = -1.0;
         if (all_emitted && last_live >= live && dsteps > 0) hazard = (double)(last_live - live) / (double)dsteps;
         last_live = live;
@@ -507,7 +538,10 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
             cudaEventElapsedTime(&ms, c->evA[slot], c->evB[slot]); step_ms_total += ms;
             break;
         }
-        if (all_emitted && (long long)live * 100 < nslots * compact_pct && nslots > tail_slots) {
+        // fused K3: launch it-1 stored exactly its `live` survivors, launch `it` (queued above) visits them, and the launch queued
+        // next visits the survivors of launch `it`: at most `live` (the kernel takes the exact count from device memory)
+        if (before_compacted && (long long)live < nslots) nslots = std::max<long long>((long long)live, 1);
+        if (!fused && all_emitted && (long long)live * 100 < nslots * compact_pct && nslots > tail_slots) {
             // tail: compact the survivors so later launches stream only live state.  `live` is one launch old,
             // i.e. an upper bound (nothing is emitted any more); unused destination slots stay inactive.
             // sort_mode: the compaction is a counting sort by (subdomain, tally cell) -- always (1), or whenever the
@@ -527,10 +561,12 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
 #if MCB_DECAY_ADAPT_PCT > 0
             // a young population terminates fast (C2: 6 % per loop trip -- 16 trips would leave 37 % of the lanes alive), an old
             // one slowly: run as many loop trips per state round trip as let about MCB_DECAY_ADAPT_PCT % of the phonons terminate
-            if (hazard > 0.0) S_cur = (int)std::min<double>(MCB_DECAY_S_MAX, std::max<double>(MCB_DECAY_S_MIN, std::floor(0.01 * MCB_DECAY_ADAPT_PCT / hazard + 0.5)));
+            const int s_min = fused ? MCB_DECAY_FUSED_S_MIN : MCB_DECAY_S_MIN;
+            if (hazard > 0.0) S_cur = (int)std::min<double>(MCB_DECAY_S_MAX, std::max<double>(s_min, std::floor(0.01 * decay_pct / hazard + 0.5)));
             else if (hazard == 0.0) S_cur = MCB_DECAY_S_MAX;
+            if (fused && live > 0) S_cur = (int)std::min<long long>(MCB_DECAY_S_MAX, std::max<long long>(S_cur, (MCB_DECAY_MIN_WORK + (long long)live - 1) / (long long)live));
 #endif
-            if ((long long)live <= tail_slots) S_cur = (int)std::min<long long>(std::max<long long>(prob->maxloop, 1), 1 << 22);
+            if ((long long)live <= tail_slots) { S_cur = (int)std::min<long long>(std::max<long long>(prob->maxloop, 1), 1 << 22); tail_next = true; }
         }
     }
     CUDA_TRY(c, cudaEventRecord(c->ev1, c->stream));
@@ -544,7 +580,7 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
         stats->step_launches = step_launches; stats->slot_steps = slot_steps; stats->state_stores = (int64_t)c->h_ctr[0].stores;
         stats->steady_launches = steady_launches; stats->steady_steps = (int64_t)steady_steps;
         stats->steady_stores = (int64_t)steady_stores; stats->steady_ms = steady_ms;
-        stats->compactions = compactions; stats->sorts = sorts;
+        stats->compactions = compactions; stats->sorts = sorts; stats->tail_ms = tail_ms; stats->tail_steps = (int64_t)tail_steps;
     }
     return MCB_OK;
 }
@@ -616,7 +652,7 @@ void mcb_destroy(mcb_ctx* c) {
 
 int mcb_set_options(mcb_ctx* c, const mcb_options* o) {
     if (!c || !o) return MCB_EINVAL;
-    if (o->slots < 0 || o->steps_per_launch < 0 || o->block < 0 || o->ctas_per_sm < 0 || o->tally_mode < 0 || o->tally_mode > 3 || o->decay_mode < 0 || o->decay_mode > 1 || o->emit_mode != 0 || o->compact_pct < 0 || o->compact_pct > 100 || o->sort_mode < 0) {
+    if (o->slots < 0 || o->steps_per_launch < 0 || o->block < 0 || o->ctas_per_sm < 0 || o->tally_mode < 0 || o->tally_mode > 3 || o->decay_mode < 0 || o->decay_mode > 2 || o->decay_pct < 0 || o->decay_pct > 100 || o->emit_mode != 0 || o->compact_pct < 0 || o->compact_pct > 100 || o->sort_mode < 0) {
         c->err = "negative / unknown option"; return MCB_EINVAL;
     }
     c->opt = *o;

@@ -684,7 +684,10 @@ __global__ void __launch_bounds__(NDM == 3 ? MCB_BLOCK_MAX_ND3 : (NDM == 2 ? MCB
     const bool staged = P.so_stage != 0u;
     const uint32_t a_buf = smem_u32(smem) + P.so_stage + warp * MCB_GROUP_BYTES;        // shared-memory addresses
     const uint32_t a_bar = smem_u32(smem) + P.so_wbar + warp * 8u;
-    const int ngroups = (int)((P.nslots + 31) >> 5);            // slots < 2^31 (plan_run)
+    // slots this launch visits: the host's count, or -- behind a compacting launch -- the count that launch published
+    long long nslots_ll = P.nslots;
+    if (P.use_dev_n) nslots_ll = min(nslots_ll, (long long)P.ctr->n_slots[P.parity ^ 1]);
+    const int ngroups = (int)((nslots_ll + 31) >> 5);           // slots < 2^31 (plan_run)
     const int gstride = (int)(gridDim.x * nwarps);
     uint32_t wphase = 0;
     if (staged) {
@@ -702,7 +705,7 @@ __global__ void __launch_bounds__(NDM == 3 ? MCB_BLOCK_MAX_ND3 : (NDM == 2 ? MCB
     __syncthreads();                                            // the counter slots are armed
 
     // tile = one group of 32 slots per warp: group g = (blockIdx + k gridDim) nwarps + warp; the trip count is CTA-uniform
-    const int nslots = (int)P.nslots;
+    const int nslots = (int)nslots_ll;
     for (int g = (int)(blockIdx.x * nwarps + warp), gt = (int)(blockIdx.x * nwarps); gt < ngroups; g += gstride, gt += gstride) {
         if (FX && P.do_tally) {
             // between tiles (CTA-uniform): flush before an entry could have received more than fx_flush_trips rounds of deposits
@@ -820,9 +823,22 @@ __global__ void __launch_bounds__(NDM == 3 ? MCB_BLOCK_MAX_ND3 : (NDM == 2 ? MCB
             if (escaped) red_shared_u32(&s_esc, 1u);                           // rare: Progress::incrEsc problem.cpp:111-118
             run_mask = __ballot_sync(0xFFFFFFFFu, ph.active());
         }
-        if (was_active) ph.store_group(P.st, g, lane);
+        unsigned st_mask;
+        if (P.compact) {
+            // K3 fused into the launch: the tile's survivors take the next slots of the output buffer (one atomic per tile; with
+            // several loop trips per tile its latency hides behind the other warps), terminated phonons are dropped
+            st_mask = run_mask;
+            if (run_mask) {
+                unsigned long long ob = 0ull;
+                if (lane == 0) ob = atomicAdd(&P.ctr->out_cursor, (unsigned long long)__popc(run_mask));
+                ob = __shfl_sync(0xFFFFFFFFu, ob, 0);
+                if ((run_mask >> lane) & 1u) ph.store(P.st_out, (long long)(ob + __popc(run_mask & ((1u << lane) - 1u))));
+            }
+        } else {
+            if (was_active) ph.store_group(P.st, g, lane);
+            st_mask = __ballot_sync(0xFFFFFFFFu, was_active);
+        }
         // end of the tile: list the slots that ended inactive (only ids below nslots), bump the warp's counters
-        const unsigned st_mask = __ballot_sync(0xFFFFFFFFu, was_active);
         const unsigned fm = list_free ? __ballot_sync(0xFFFFFFFFu, i < nslots) & ~run_mask : 0u;
         uint4 wc = make_uint4(0u, 0u, 0u, 0u);
         if (lane == 0) wc = s_wcnt[warp];                       // the warp's slot is read and written by lane 0 only
@@ -863,15 +879,25 @@ __global__ void __launch_bounds__(NDM == 3 ? MCB_BLOCK_MAX_ND3 : (NDM == 2 ? MCB
         if (lv) atomicAdd(&P.ctr->live[P.parity], lv);
         if (so) atomicAdd(&P.ctr->stores, so);
         if (s_emitted) atomicAdd(&P.ctr->emitted, (unsigned long long)s_emitted);
-        if (P.host_ctr) {
+        if (P.host_ctr || P.compact) {
             // the last CTA to get here mirrors the counters into pinned host memory: the host only waits for the event behind
             // the launch -- no device-to-host copy sits between two k_step launches
             __threadfence();
             if (atomicAdd(&P.ctr->done, 1ull) == (unsigned long long)gridDim.x - 1ull) {
                 __threadfence();
-                const volatile unsigned long long* src = reinterpret_cast<const volatile unsigned long long*>(P.ctr);
-                volatile unsigned long long* dst = reinterpret_cast<volatile unsigned long long*>(P.host_ctr);
-                for (int k = 0; k < (int)(sizeof(Counters) / 8); ++k) dst[k] = src[k];
+                if (P.compact) {
+                    // publish the number of slots written for the launch behind this one, re-arm the cursor and make the
+                    // rest of the last 32-slot group inactive (the buffer holds stale state from two launches ago)
+                    const unsigned long long n_out = *reinterpret_cast<volatile unsigned long long*>(&P.ctr->out_cursor);
+                    P.ctr->n_slots[P.parity] = n_out; P.ctr->out_cursor = 0ull;
+                    for (unsigned long long k = n_out; k < ((n_out + 31ull) & ~31ull); ++k) Particle::clear_meta(P.st_out, (long long)k);
+                    __threadfence();
+                }
+                if (P.host_ctr) {
+                    const volatile unsigned long long* src = reinterpret_cast<const volatile unsigned long long*>(P.ctr);
+                    volatile unsigned long long* dst = reinterpret_cast<volatile unsigned long long*>(P.host_ctr);
+                    for (int k = 0; k < (int)(sizeof(Counters) / 8); ++k) dst[k] = src[k];
+                }
                 P.ctr->done = 0ull;
                 __threadfence_system();
             }
