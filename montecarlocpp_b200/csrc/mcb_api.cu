@@ -479,7 +479,7 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
     // K3 pass of round 2: a launch then visits the survivors of the launch BEFORE the previous one.
     const bool fused = c->opt.decay_mode == 0 && c->opt.sort_mode == 0;
     const int decay_pct = c->opt.decay_pct > 0 ? c->opt.decay_pct : (fused ? MCB_DECAY_FUSED_PCT : MCB_DECAY_ADAPT_PCT);
-    bool prev_compacting = false;
+    bool prev_compacting = false, any_compacted = false, quiet = true;
     // tail accounting: launches that run the last survivors (at most one tile per CTA) to termination are bound by the
     // length of the longest history, not by throughput (mcb_stats::tail_ms / tail_steps)
     bool tail_launch[2] = {false, false}, tail_next = false; float tail_ms = 0.f; unsigned long long tail_steps = 0;
@@ -497,8 +497,11 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
         // K1: the first fill (every slot free) is its own dense kernel; afterwards k_step refills the slots that end inactive
         // itself (32 at a time, ids from the atomic cursor Counters::next) while particles are left to emit
         P.emit_enable = (host_all_emitted || !P.free_list) ? 0 : 1;
-        const bool compacting = fused && !P.emit_enable;
-        P.compact = compacting ? 1 : 0; P.st_out = view_of(c, cur ^ 1); P.use_dev_n = (compacting && prev_compacting) ? 1 : 0;
+        // ... unless (almost) nobody terminated in the last completed launch, or none has completed yet (a population that ends
+        // by maxscat loses nobody for its first maxscat loop trips): such a launch stores in place and spares its tiles the
+        // wait for the cursor
+        const bool compacting = fused && !P.emit_enable && !quiet;
+        P.compact = compacting ? 1 : 0; P.st_out = view_of(c, cur ^ 1); P.use_dev_n = any_compacted ? 1 : 0;
         if (it == 0) {
             k_emit<<<(unsigned)(c->sm_count * 8), 256, 0, c->stream>>>(P);
             k_emit_commit<<<1, 32, 0, c->stream>>>(P);
@@ -512,7 +515,8 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
         // the launch's last CTA has mirrored the counters into h_ctr[slot] (StepParams::host_ctr): evB is all the host waits for
         launches++; step_launches++; slot_steps += nslots * (long long)std::min<long long>(S_cur, prob->maxloop);
         const bool before_compacted = prev_compacting;            // launch it-1
-        if (compacting) { cur ^= 1; prev_compacting = true; }      // the launch behind this one reads what this one writes
+        prev_compacting = compacting;
+        if (compacting) { cur ^= 1; any_compacted = true; }        // the launches behind this one read what this one writes
         if (it == 0) continue;
         const int prev = slot ^ 1;
         CUDA_TRY(c, cudaEventSynchronize(c->evB[prev]));
@@ -566,6 +570,9 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
             else if (hazard == 0.0) S_cur = MCB_DECAY_S_MAX;
             if (fused && live > 0) S_cur = (int)std::min<long long>(MCB_DECAY_S_MAX, std::max<long long>(S_cur, (MCB_DECAY_MIN_WORK + (long long)live - 1) / (long long)live));
 #endif
+            // a launch compacts only when the last completed launch says it will lose at least ~1 % of its phonons: every tile of
+            // a compacting launch waits for one atomic on a single cursor (1e7 phonons at S = 4: 3e5 same-address atomics, ~0.6 ms)
+            quiet = !(hazard > 0.0 && hazard * S_cur >= 0.01) && (long long)live * 100 >= nslots * 95;     // (slow losses add up: compact below 95 %)
             if ((long long)live <= tail_slots) { S_cur = (int)std::min<long long>(std::max<long long>(prob->maxloop, 1), 1 << 22); tail_next = true; }
         }
     }

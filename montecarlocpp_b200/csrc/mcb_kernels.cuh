@@ -686,7 +686,7 @@ __global__ void __launch_bounds__(NDM == 3 ? MCB_BLOCK_MAX_ND3 : (NDM == 2 ? MCB
     const uint32_t a_bar = smem_u32(smem) + P.so_wbar + warp * 8u;
     // slots this launch visits: the host's count, or -- behind a compacting launch -- the count that launch published
     long long nslots_ll = P.nslots;
-    if (P.use_dev_n) nslots_ll = min(nslots_ll, (long long)P.ctr->n_slots[P.parity ^ 1]);
+    if (P.use_dev_n) nslots_ll = min(nslots_ll, (long long)P.ctr->n_slots);
     const int ngroups = (int)((nslots_ll + 31) >> 5);           // slots < 2^31 (plan_run)
     const int gstride = (int)(gridDim.x * nwarps);
     uint32_t wphase = 0;
@@ -889,7 +889,7 @@ __global__ void __launch_bounds__(NDM == 3 ? MCB_BLOCK_MAX_ND3 : (NDM == 2 ? MCB
                     // publish the number of slots written for the launch behind this one, re-arm the cursor and make the
                     // rest of the last 32-slot group inactive (the buffer holds stale state from two launches ago)
                     const unsigned long long n_out = *reinterpret_cast<volatile unsigned long long*>(&P.ctr->out_cursor);
-                    P.ctr->n_slots[P.parity] = n_out; P.ctr->out_cursor = 0ull;
+                    P.ctr->n_slots = n_out; P.ctr->out_cursor = 0ull;
                     for (unsigned long long k = n_out; k < ((n_out + 31ull) & ~31ull); ++k) Particle::clear_meta(P.st_out, (long long)k);
                     __threadfence();
                 }
