@@ -271,8 +271,11 @@ int plan_run(mcb_ctx* c, const mcb_problem_desc* prob, long long nparticles, Run
         // runs S = 16 loop trips per state round trip on a population that only decays (C1 +30 %, C3 / C5 +35 ... +50 % over a
         // 3.6-M-slot population that is refilled while it streams).  An explicit slots / steps_per_launch keeps the streaming
         // schedule the HBM roofline is quoted on.
+        // (the memory query is skipped when the buffers this context already holds are large enough: cudaMemGetInfo was measured
+        // to take 20-30 ms every few calls, as much as a whole C2 solve)
         size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+        if (nparticles <= c->slots_alloc) slots = std::max(slots, (long long)nparticles);
+        else if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
             const size_t have = 2 * state_bytes(c->slots_alloc);
             const long long cap = (long long)((free_b + have) / 2 / (2 * (MCB_GROUP_BYTES / 32)));
             slots = std::max(slots, std::min<long long>(nparticles, cap));
