@@ -132,21 +132,25 @@ def test_solve_matches_oracle_philox(gpu_ctx, omats, mname, dname, pkind, size):
     assert (np.abs(got - ref) <= 1e-9 * scale).all()
 
 
+ZERO_OPTS = dict(slots=0, steps_per_launch=0, block=0, ctas_per_sm=0, tally_mode=0, emit_mode=0, decay_mode=0, compact_pct=0, sort_mode=0, decay_pct=0)
+
+
 @pytest.mark.parametrize("opts", [dict(steps_per_launch=1, slots=4096), dict(steps_per_launch=7, slots=1000),
                                   dict(steps_per_launch=64, slots=0, tally_mode=2), dict(block=128, ctas_per_sm=1, slots=30000), dict(block=512, steps_per_launch=5),
                                   dict(tally_mode=3, steps_per_launch=3), dict(tally_mode=1, block=256, steps_per_launch=2),
-                                  dict(slots=1001, steps_per_launch=2)])
+                                  dict(slots=1001, steps_per_launch=2), dict(decay_mode=2), dict(decay_mode=1, steps_per_launch=3, compact_pct=99),
+                                  dict(decay_pct=3), dict(decay_pct=60, steps_per_launch=1, slots=8192), dict(sort_mode=1, decay_mode=2, compact_pct=99)])
 def test_schedule_options_do_not_change_results(gpu_ctx, omats, opts):
     """Slots / S / tally mode are scheduling only: Philox keyed by particle id makes the result
     independent of them (up to fp summation order)."""
     mat, dom = omats["silicon"], cases.film()
     cases.upload(gpu_ctx, mat, dom)
     prob = orc.Problem(mat, dom, "multi", 30000, 25)
-    gpu_ctx.set_options(slots=0, steps_per_launch=0, block=0, ctas_per_sm=0, tally_mode=0, emit_mode=0, decay_mode=0)
+    gpu_ctx.set_options(**ZERO_OPTS)
     base, bst = gpu_ctx.solve(prob.desc, seed=SEED)
-    gpu_ctx.set_options(**{**dict(slots=0, steps_per_launch=0, block=0, ctas_per_sm=0, tally_mode=0, emit_mode=0, decay_mode=0), **opts})
+    gpu_ctx.set_options(**{**ZERO_OPTS, **opts})
     got, gst = gpu_ctx.solve(prob.desc, seed=SEED)
-    gpu_ctx.set_options(slots=0, steps_per_launch=0, block=0, ctas_per_sm=0, tally_mode=0, emit_mode=0, decay_mode=0)
+    gpu_ctx.set_options(**ZERO_OPTS)
     assert (gst["steps"], gst["esc"], gst["emitted"]) == (bst["steps"], bst["esc"], bst["emitted"])
     scale = np.abs(base).max(axis=1, keepdims=True)
     assert (np.abs(got - base) <= 1e-9 * scale).all()
@@ -459,7 +463,7 @@ def test_nonbox_cells_match_oracle(gpu_ctx, omats, dname):
     emitters, generic plane loop, literal cellVol: per-particle state and whole solves against the oracle."""
     mat, dom = omats["grey"], cases.NONBOX[dname]()
     cases.upload(gpu_ctx, mat, dom)
-    gpu_ctx.set_options(slots=0, steps_per_launch=0, block=0, ctas_per_sm=0, tally_mode=0, emit_mode=0, decay_mode=0)
+    gpu_ctx.set_options(**ZERO_OPTS)
     prob = orc.Problem(mat, dom, "multi", 20000, 25)
     for k in (0, 30):
         ref = prob.trace(SEED, 0, 4000, k)

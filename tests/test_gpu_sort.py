@@ -97,3 +97,26 @@ def test_sorted_solve_equals_the_unsorted_one(gpu_ctx, omats, mname, dname, pkin
             assert (np.abs(got - base) <= 1e-9 * scale).all()
     finally:
         gpu_ctx.set_options(**zero)
+
+
+@pytest.mark.parametrize("mname,dname,pkind,maxscat", [("grey", "slab", "multi", 300), ("silicon", "slab", "cumflux", 60), ("silicon", "tube", "multi", 40)])
+def test_fused_compaction_equals_separate_passes(gpu_ctx, omats, mname, dname, pkind, maxscat):
+    """The decay phase with the compaction inside k_step (default) vs separate k_compact passes (decay_mode 2) vs a fixed S with
+    passes (decay_mode 1), on populations well above one tile per CTA, resident and streaming: counters identical, field to 1e-9."""
+    mat, dom = omats[mname], cases.DOMAINS[dname]()
+    cases.upload(gpu_ctx, mat, dom)
+    prob = orc.Problem(mat, dom, pkind, 700000, maxscat, size=5 if pkind.startswith("cum") else 0)
+    zero = dict(slots=0, steps_per_launch=0, block=0, ctas_per_sm=0, tally_mode=0, emit_mode=0, decay_mode=0, compact_pct=0, sort_mode=0, decay_pct=0)
+    try:
+        gpu_ctx.set_options(**{**zero, "decay_mode": 2})
+        base, bst = gpu_ctx.solve(prob.desc, seed=SEED)
+        scale = np.abs(base).max(axis=1, keepdims=True)
+        for opts in (dict(), dict(decay_pct=4), dict(decay_pct=40), dict(steps_per_launch=1, slots=148 * 768 * 3), dict(decay_mode=1, steps_per_launch=5)):
+            gpu_ctx.set_options(**{**zero, **opts})
+            got, gst = gpu_ctx.solve(prob.desc, seed=SEED)
+            assert (gst["steps"], gst["esc"], gst["emitted"]) == (bst["steps"], bst["esc"], bst["emitted"]), opts
+            assert (np.abs(got - base) <= 1e-9 * scale).all(), opts
+            if opts.get("decay_mode", 0) == 0:
+                assert gst["compactions"] == 0                      # no separate K3 pass ran
+    finally:
+        gpu_ctx.set_options(**zero)
