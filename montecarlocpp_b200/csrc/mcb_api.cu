@@ -1,7 +1,7 @@
 // mcb_api.cu — host side of the C ABI declared in include/mcb.h.
 //
-// Flattens the POD descriptors into device tables, drives the slot schedule (emit/refill + step
-// launches, tail compaction), finalises the field.  No CPU fallback: every entry point needs a
+// Flattens the POD descriptors into device tables, drives the slot schedule (first fill, step launches that
+// refill their own slots, compacting launches of the decay phase, optional sort), finalises the field.  No CPU fallback: every entry point needs a
 // working sm_100 device.  Reference citations: file:line relative to /root/reference/montecarlo/.
 #define MCB_AUX_KERNELS
 #include "mcb_kernels.cuh"

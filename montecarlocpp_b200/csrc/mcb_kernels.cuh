@@ -9,8 +9,13 @@
 //               with fp64 RED.  Template modes: payload rows, tally destination, N-D walk (none / serial / serial +
 //               cooperative pieces / warp-balanced items), axis-aligned boxes only, padded histogram columns.
 //   k_emit      K1 for the first fill (every slot free): one thread per particle; k_emit_commit advances the particle counter.
-//   k_compact   K3: stream-compacts the active slots of the decay phase (no reference analogue; replaces the `break`s at
+//               K3 fused in as well: in the decay phase (nothing left to emit) a launch stores its survivors DENSELY into the
+//               other state buffer (StepParams::compact; one cursor atomic per tile) and publishes the slot count for the launch
+//               behind it -- terminated phonons simply vanish (no reference analogue; replaces the `break`s at
 //               problem.cpp:411,425,434).
+//   k_compact   K3 as its own pass: unordered stream compaction (mcb_options::decay_mode 1 / 2 only).
+//   k_sort_*    K3 with a key: counting sort of the survivors by (subdomain, tally cell) (mcb_options::sort_mode), k_sort_probe
+//               behind mcb_sort_probe.
 //   k_finalize  K4: postProc, / cellVol, * power_ (problem.cpp:439-444).
 //   k_traj      TrajProblem::solve (problem.cpp:226-299) for one particle.
 //   k_cell_index / k_accumulate / k_gather_trace / k_philox: diagnostics behind mcb_cell_index / mcb_accumulate /
