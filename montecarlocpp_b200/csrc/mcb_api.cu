@@ -500,9 +500,9 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
         // K1: the first fill (every slot free) is its own dense kernel; afterwards k_step refills the slots that end inactive
         // itself (32 at a time, ids from the atomic cursor Counters::next) while particles are left to emit
         P.emit_enable = (host_all_emitted || !P.free_list) ? 0 : 1;
-        // ... unless (almost) nobody terminated in the last completed launch, or none has completed yet (a population that ends
-        // by maxscat loses nobody for its first maxscat loop trips): such a launch stores in place and spares its tiles the
-        // wait for the cursor
+        // K3 fused: once nothing is left to emit the launch stores its survivors densely into the other buffer -- unless (almost)
+        // nobody terminated in the last completed launch, or none has completed yet (a population that ends by maxscat loses
+        // nobody for its first maxscat loop trips): such a launch stores in place and spares its tiles the wait for the cursor
         const bool compacting = fused && !P.emit_enable && !quiet;
         P.compact = compacting ? 1 : 0; P.st_out = view_of(c, cur ^ 1); P.use_dev_n = any_compacted ? 1 : 0;
         if (it == 0) {
@@ -561,13 +561,14 @@ int run_solve(mcb_ctx* c, const mcb_problem_desc* prob, uint64_t seed, int64_t n
             if (sorted) { sorts++; sorted_pop = bound; }
             cur ^= 1; nslots = bound;
         }
-        // decay phase (nothing left to emit): launches are no longer full, so amortise them over >= 16 loop trips;
+        // decay phase (nothing left to emit): the population only shrinks, so run several loop trips per state round trip;
         // once the survivors fit one tile per CTA let every thread run its phonon to termination
         if (all_emitted && c->opt.decay_mode != 1) {
             S_cur = std::max(plan.S, MCB_DECAY_S);
 #if MCB_DECAY_ADAPT_PCT > 0
             // a young population terminates fast (C2: 6 % per loop trip -- 16 trips would leave 37 % of the lanes alive), an old
-            // one slowly: run as many loop trips per state round trip as let about MCB_DECAY_ADAPT_PCT % of the phonons terminate
+            // one slowly: run as many loop trips per state round trip as let about decay_pct % of the phonons terminate (12 with the
+            // fused compaction, 30 with separate passes), but enough of them to dilute the launch's fixed costs
             const int s_min = fused ? MCB_DECAY_FUSED_S_MIN : MCB_DECAY_S_MIN;
             if (hazard > 0.0) S_cur = (int)std::min<double>(MCB_DECAY_S_MAX, std::max<double>(s_min, std::floor(0.01 * decay_pct / hazard + 0.5)));
             else if (hazard == 0.0) S_cur = MCB_DECAY_S_MAX;
