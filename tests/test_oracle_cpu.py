@@ -314,3 +314,32 @@ def test_c_abi_library_exports_every_declared_symbol():
     assert src_hash == h.hexdigest(), "libmcb.so is stale: rebuild with `make -C montecarlocpp_b200/csrc`"
     # struct layouts agree with the C compiler's (sizes baked into the oracle, which includes the same header)
     assert C.sizeof(abi.PlaneDesc) == 8 * (4 + 2 + 9 + 9 + 3 + 1 + 3 + 1 + 24) and C.sizeof(abi.SdomDesc) % 8 == 0
+
+
+def test_ctypes_mirror_has_the_layout_of_the_c_header(tmp_path):
+    """include/mcb.h is the ABI; montecarlocpp_b200/abi.py mirrors it by hand.  Compile the header with gcc and compare sizeof and
+    every field offset of every struct (a field added on one side only -- as mcb_options / mcb_stats grew in ABI version 2 --
+    fails here, on the CPU)."""
+    import subprocess
+    pairs = {"mcb_material_desc": abi.MaterialDesc, "mcb_plane_desc": abi.PlaneDesc, "mcb_sdom_desc": abi.SdomDesc,
+             "mcb_emitter_desc": abi.EmitterDesc, "mcb_domain_desc": abi.DomainDesc, "mcb_problem_desc": abi.ProblemDesc,
+             "mcb_stats": abi.Stats, "mcb_options": abi.Options, "mcb_trace_out": abi.TraceOut, "mcb_traj_desc": abi.TrajDesc,
+             "mcb_traj_out": abi.TrajOut}
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "mcb.h"', "int main(void) {"]
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} sizeof %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            if fname.startswith("pad"):
+                continue                                  # explicit tail / alignment padding of the mirror
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    for line in out.strip().splitlines():
+        cname, what, val = line.split()
+        cls = pairs[cname]
+        want = C.sizeof(cls) if what == "sizeof" else getattr(cls, what).offset
+        assert int(val) == want, (cname, what, int(val), want)
